@@ -1,0 +1,102 @@
+/* libbsw_gpu.so -- the B200 drop-in for GenArchBench's bsw hot path.
+ *
+ * Replaces, behind a plain C ABI, the reference's per-batch kernel entry point
+ *     void BandedPairWiseSW::getScores16(SeqPair *pairArray, uint8_t *seqBufRef, uint8_t *seqBufQer,
+ *                                        int32_t numPairs, uint16_t numThreads, int32_t w)
+ *     (/root/reference/benchmarks/bsw/src/bandedSWA.h:300-305, bandedSWA.cpp:2679-2975),
+ * as called from the driver's region of interest (main_banded.cpp:338-350), together with the
+ * constructor that fixes the scoring parameters (bandedSWA.h:132-135, bandedSWA.cpp:48-97) and the
+ * destructor (bandedSWA.cpp:100-103).
+ *
+ * Same inputs (the caller's SeqPair array and the two base-code buffers, untouched), same six
+ * per-pair outputs written in place (score, tle, gtle, qle, gscore, max_off; bandedSWA.cpp:3336-3362),
+ * caller's order preserved. Differences from the reference, all deliberate:
+ *   - errors are returned, never exit()ed (reference: bandedSWA.cpp:91-96, 2720-2723);
+ *   - entries pairArray[n ..] are never written (reference pads in place, bandedSWA.cpp:2726-2732);
+ *   - call it with the WHOLE pair set (or multi-million chunks): binning, batching, packing, the
+ *     stream pipeline and the multi-GPU split happen inside; `numThreads` has no equivalent.
+ *
+ * No torch / CUDA types in any signature. Every entry point returns BSW_OK (0) or a BSW_ERR_* code.
+ */
+#ifndef BSW_GPU_H
+#define BSW_GPU_H
+#include "bsw_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bsw_handle bsw_handle;
+
+enum {
+    BSW_OK = 0,
+    BSW_ERR_ARG = 1,        /* null pointer / negative count / bad parameter */
+    BSW_ERR_NO_DEVICE = 2,  /* no usable CUDA device: the library has NO CPU fallback */
+    BSW_ERR_CUDA = 3,       /* a CUDA runtime call failed; see bsw_gpu_last_error() */
+    BSW_ERR_NOMEM = 4,      /* host or device allocation failed */
+    BSW_ERR_RANGE = 5,      /* a pair is outside the reference's valid domain (see bsw_gpu_batch) */
+    BSW_ERR_STATE = 6       /* staged-API call out of order */
+};
+
+/* == BandedPairWiseSW::BandedPairWiseSW (bandedSWA.cpp:48-97). Uses CUDA devices 0..n_gpus-1
+ * (n_gpus <= 0: all visible devices). Allocates per-GPU streams, pinned staging and device arenas. */
+int bsw_gpu_init(const bsw_params *params, int n_gpus, bsw_handle **out);
+/* Same, on an explicit device list (one process per GPU under torchrun passes {LOCAL_RANK}). */
+int bsw_gpu_init_devices(const bsw_params *params, int n_devices, const int *device_ids,
+                         bsw_handle **out);
+/* == BandedPairWiseSW::~BandedPairWiseSW (bandedSWA.cpp:100-103). */
+void bsw_gpu_free(bsw_handle *h);
+
+/* == getScores16 (bandedSWA.cpp:2679-2703) over n pairs with band width w.
+ * pairs[k].idr / .idq are byte offsets into ref / qer, .len1 / .len2 the lengths, .h0 the seed score.
+ * Writes only score, tle, gtle, qle, gscore, max_off of pairs[0..n).
+ * Valid domain (the reference's int16 kernel, SURVEY.md 8a note 4):
+ *   0 <= len1, len2 <= BSW_MAX_SEQ_LEN, 0 <= h0, h0 + len2*match <= 32767; otherwise BSW_ERR_RANGE
+ *   and nothing is written. One call at a time per handle (same rule as one object per thread in
+ *   the reference, bandedSWA.cpp:2771). */
+int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                  int64_t n, int32_t w);
+
+/* ---- staged variant of the same path, for measurement (bench.py `value` vs `e2e`) ----
+ * stage:  bin + pack + host->device; inputs stay resident in HBM.
+ * run:    launches the DP kernels over the resident batch; *kernel_ms = CUDA-event time on the
+ *         launching streams (max over GPUs). May be called repeatedly.
+ * fetch:  device->host + scatter of the six outputs into pairs[0..n) (same array order as staged). */
+int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                  int64_t n, int32_t w);
+int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms);
+int bsw_gpu_fetch_staged(bsw_handle *h, bsw_seqpair *pairs, int64_t n);
+
+typedef struct bsw_gpu_stats {
+    int64_t pairs;              /* pairs processed by the last batch / staged run */
+    int64_t kernel_launches;    /* launches of OUR kernels in the last batch / run_staged call */
+    int64_t h2d_bytes;          /* bytes copied host->device by the last batch / stage */
+    int64_t d2h_bytes;          /* bytes copied device->host by the last batch / fetch */
+    int64_t pairs_short;        /* pairs routed to the thread-per-pair shared-memory kernel */
+    int64_t pairs_long;         /* pairs routed to the long-pair kernel */
+    double  host_bin_ms;        /* last batch: validation + length binning */
+    double  host_pack_ms;       /* last batch: 2-bit packing into pinned staging (sum over workers) */
+    double  host_scatter_ms;    /* last batch: result scatter into SeqPair */
+    double  kernel_ms;          /* last batch: sum of CUDA-event kernel time, max over GPUs */
+    double  wall_ms;            /* last batch: wall time of the whole call */
+    int32_t n_gpus;
+    int32_t reserved;
+} bsw_gpu_stats;
+int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out);
+
+/* Integer-pipe microbenchmark on device `device`: packed s16x2 DPX instruction throughput in
+ * giga thread-instructions per second (warp-instructions * 32), all SMs, `which`:
+ *   0 VIADDMNMX.S16x2.RELU, 1 VIMNMX3.S16x2, 2 VIADD.16x2, 3 LOP3, 4 PRMT, 5 IMAD,
+ *   6 the bsw inner-loop mix. Used by bench.py for the `dpx_peak` roofline denominator. */
+int bsw_gpu_dpx_peak(int device, int which, double *ginstr_per_s, double *sm_mhz_est);
+
+const char *bsw_gpu_strerror(int code);
+/* Text of the last CUDA error seen by this handle (empty string if none). */
+const char *bsw_gpu_last_error(const bsw_handle *h);
+/* Library / kernel ABI version, bumped when bsw_seqpair handling changes. */
+int bsw_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
