@@ -1,0 +1,750 @@
+// libbsw_gpu.so: host pipeline + C ABI of the B200 bsw drop-in (include/bsw_gpu.h).
+//
+// Replaces BandedPairWiseSW::getScores16 / smithWatermanBatchWrapper16
+// (/root/reference/benchmarks/bsw/src/bandedSWA.cpp:2679-2975) as called from the driver's ROI
+// (main_banded.cpp:338-350). Where the reference pads, counting-sorts by len1, transposes AoS->SoA
+// per 32 lanes and unsorts (bandedSWA.cpp:2726-2761, 2811-2880, 2940-2960), this library
+//   1. cuts the caller's pair array into slabs,
+//   2. per slab: validates, length-bins (stable counting sort by len2 then len1), packs the bases
+//      2 bits each (4 bits for pairs holding an ambiguous base) into pinned memory -- all host cores,
+//   3. streams slabs through a ring of buffers per GPU: H2D, one kernel launch per length bin,
+//      D2H of 16-byte result records already in the caller's order,
+//   4. scatters the six outputs into the caller's SeqPair array.
+// There is NO CPU implementation of the DP in here: without a CUDA device init fails.
+#include "bsw_gpu.h"
+#include "bsw_kernels.cuh"
+#include "bsw_pack.h"
+
+#include <omp.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bswk;
+
+namespace {
+
+constexpr int kRing = 3;                       // slabs in flight per GPU
+constexpr int64_t kSlabPairs = 1 << 20;        // pairs per slab (upper bound)
+constexpr int64_t kSlabBases = 512ll << 20;    // bases per slab (upper bound)
+constexpr size_t kMaxSmem = 227 * 1024 - 64;   // opt-in shared memory per block on sm_100, minus the kernel's static bytes
+constexpr int kBinCols = 16;                   // query-length granularity of a launch bin
+constexpr int kVersion = 1;
+
+using Clock = std::chrono::steady_clock;
+inline double ms_since(Clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+}
+
+struct Launch {
+    int first;       // first sorted position
+    int n;           // pairs
+    int row_words, qs_words, tg_words, stage_bytes;
+    size_t smem;     // 0 => long kernel
+    int64_t work;    // sum len1*len2, for ordering
+};
+
+// One slab = the unit that travels through a stream. Host side pinned, device side plain.
+struct Slab {
+    // capacity
+    int64_t cap_pairs = 0;
+    size_t cap_blob = 0, cap_scratch = 0;
+    // pinned host
+    PairMeta *h_meta = nullptr;
+    uint32_t *h_blob = nullptr;
+    PairOut *h_out = nullptr;
+    // device
+    PairMeta *d_meta = nullptr;
+    uint32_t *d_blob = nullptr;
+    PairOut *d_out = nullptr;
+    unsigned char *d_scratch = nullptr;
+    // current contents
+    int64_t lo = 0;          // first pair (caller order) of the slab
+    int n = 0;               // pairs in the slab
+    int n_dev = 0;           // pairs that go to the device (non-empty sequences)
+    size_t blob_bytes = 0;
+    std::vector<Launch> launches;
+    std::vector<uint32_t> trivial;  // slab-local ids answered on the host (empty sequence)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    bool busy = false;
+    bool pinned = true;      // false for staged slabs (host side borrowed)
+};
+
+struct Device {
+    int id = 0;
+    Slab ring[kRing];
+    std::vector<Slab *> staged;  // device-resident slabs of the staged API
+};
+
+}  // namespace
+
+struct bsw_handle {
+    bsw_params P;
+    KParams K;
+    bool match1 = false, sym = false;
+    std::vector<Device> devs;
+    bsw_gpu_stats stats;
+    std::string err;
+    // staged state
+    int64_t staged_n = -1;
+    int32_t staged_w = 0;
+    // host scratch reused across slabs
+    std::vector<uint32_t> key, ord_a, ord_b;
+    std::vector<uint32_t> sizes;
+    std::vector<uint64_t> offs;
+};
+
+namespace {
+
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return BSW_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+void free_slab(Slab &s) {
+    if (s.pinned) {
+        if (s.h_meta) cudaFreeHost(s.h_meta);
+        if (s.h_blob) cudaFreeHost(s.h_blob);
+        if (s.h_out) cudaFreeHost(s.h_out);
+    }
+    if (s.d_meta) cudaFree(s.d_meta);
+    if (s.d_blob) cudaFree(s.d_blob);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.d_scratch) cudaFree(s.d_scratch);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slab();
+}
+
+int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
+    if (!s.stream) {
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&s.ev_k0));
+        CU(cudaEventCreate(&s.ev_k1));
+        CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    if (pairs > s.cap_pairs) {
+        int64_t cap = std::max<int64_t>(pairs, 1024);
+        if (s.pinned) {
+            if (s.h_meta) cudaFreeHost(s.h_meta);
+            if (s.h_out) cudaFreeHost(s.h_out);
+            s.h_meta = nullptr; s.h_out = nullptr;
+            CU(cudaHostAlloc((void **)&s.h_meta, sizeof(PairMeta) * cap, cudaHostAllocDefault));
+            CU(cudaHostAlloc((void **)&s.h_out, sizeof(PairOut) * cap, cudaHostAllocDefault));
+        }
+        if (s.d_meta) cudaFree(s.d_meta);
+        if (s.d_out) cudaFree(s.d_out);
+        s.d_meta = nullptr; s.d_out = nullptr;
+        CU(cudaMalloc((void **)&s.d_meta, sizeof(PairMeta) * cap));
+        CU(cudaMalloc((void **)&s.d_out, sizeof(PairOut) * cap));
+        s.cap_pairs = cap;
+    }
+    if (blob_bytes > s.cap_blob) {
+        size_t cap = std::max<size_t>(blob_bytes, 1 << 16);
+        if (s.pinned) {
+            if (s.h_blob) cudaFreeHost(s.h_blob);
+            s.h_blob = nullptr;
+            CU(cudaHostAlloc((void **)&s.h_blob, cap, cudaHostAllocDefault));
+        }
+        if (s.d_blob) cudaFree(s.d_blob);
+        s.d_blob = nullptr;
+        CU(cudaMalloc((void **)&s.d_blob, cap));
+        s.cap_blob = cap;
+    }
+    return BSW_OK;
+}
+
+// ---- host: per-slab preparation ----------------------------------------------------------------
+
+inline size_t smem_need(int row_words, int qs_words, int tg_words, int stage_bytes) {
+    size_t rows = (size_t)8 * row_words * kBlockPairs;
+    size_t r0 = std::max(rows, (size_t)stage_bytes);
+    return r0 + (size_t)2 * qs_words * kBlockPairs + (size_t)4 * tg_words * kBlockPairs;
+}
+
+// Stable parallel counting sort of `in` (indices) by key[in[.]] < nkeys into `out`.
+void counting_sort(const std::vector<uint32_t> &key_of, const uint32_t *in, uint32_t *out, int n,
+                   int nkeys, bool descending) {
+    int T = omp_get_max_threads();
+    if (n < (1 << 16)) T = 1;
+    std::vector<uint32_t> hist((size_t)T * nkeys, 0);
+#pragma omp parallel num_threads(T)
+    {
+        int t = omp_get_thread_num();
+        int lo = (int)((int64_t)n * t / T), hi = (int)((int64_t)n * (t + 1) / T);
+        uint32_t *hh = hist.data() + (size_t)t * nkeys;
+        for (int i = lo; i < hi; ++i) hh[key_of[in[i]]]++;
+#pragma omp barrier
+#pragma omp single
+        {
+            uint32_t run = 0;
+            for (int kk = 0; kk < nkeys; ++kk) {
+                int k = descending ? nkeys - 1 - kk : kk;
+                for (int tt = 0; tt < T; ++tt) {
+                    uint32_t c = hist[(size_t)tt * nkeys + k];
+                    hist[(size_t)tt * nkeys + k] = run;
+                    run += c;
+                }
+            }
+        }
+        for (int i = lo; i < hi; ++i) out[hh[key_of[in[i]]]++] = in[i];
+    }
+}
+
+// Validates, bins, sorts and packs slab [lo, lo+n) of the caller's arrays into s (host side).
+int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t *ref,
+                 const uint8_t *qer, int64_t lo, int n) {
+    const bsw_seqpair *pp = pairs + lo;
+    s.lo = lo; s.n = n;
+    s.launches.clear();
+    s.trivial.clear();
+
+    // 1. validate + keys
+    int bad = 0, maxq = 0, maxt = 0;
+    h->key.resize((size_t)n);      // len2
+    h->sizes.resize((size_t)n);    // len1
+#pragma omp parallel for reduction(| : bad) reduction(max : maxq) reduction(max : maxt) schedule(static)
+    for (int k = 0; k < n; ++k) {
+        const bsw_seqpair &p = pp[k];
+        if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN ||
+            p.h0 < 0 || (int64_t)p.h0 + (int64_t)p.len2 * h->P.match > 32767)
+            bad |= 1;
+        h->key[(size_t)k] = (uint32_t)std::max(p.len2, 0);
+        h->sizes[(size_t)k] = (uint32_t)std::max(p.len1, 0);
+        maxq = std::max(maxq, p.len2);
+        maxt = std::max(maxt, p.len1);
+    }
+    if (bad) return BSW_ERR_RANGE;
+
+    // 2. order: empty pairs out, then stable sort by len1 then len2, both descending, so that a
+    //    warp holds pairs of equal query length and near-equal target length, heavy bins first.
+    h->ord_a.resize((size_t)n);
+    h->ord_b.resize((size_t)n);
+    int nd = 0;
+    for (int k = 0; k < n; ++k) {
+        if (pp[k].len1 == 0 || pp[k].len2 == 0) s.trivial.push_back((uint32_t)k);
+        else h->ord_a[(size_t)nd++] = (uint32_t)k;
+    }
+    s.n_dev = nd;
+    if (nd == 0) { s.blob_bytes = 0; return BSW_OK; }
+    counting_sort(h->sizes, h->ord_a.data(), h->ord_b.data(), nd, maxt + 1, true);
+    counting_sort(h->key, h->ord_b.data(), h->ord_a.data(), nd, maxq + 1, true);
+    const uint32_t *ord = h->ord_a.data();
+
+    // 3. launches: contiguous ranges of the sorted order sharing a query-length bin
+    {
+        int p = 0;
+        while (p < nd) {
+            const int q_hi = (int)h->key[ord[p]];
+            const int bin_lo = ((q_hi - 1) / kBinCols) * kBinCols;  // this launch takes len2 in (bin_lo, q_hi]
+            int e = p;
+            int t_hi = 0;
+            int64_t work = 0;
+            while (e < nd && (int)h->key[ord[e]] > bin_lo) {
+                t_hi = std::max(t_hi, (int)h->sizes[ord[e]]);
+                work += (int64_t)h->key[ord[e]] * h->sizes[ord[e]];
+                ++e;
+            }
+            Launch L;
+            L.first = p; L.n = e - p; L.work = work;
+            L.row_words = ((q_hi + 1) >> 1) + 1;
+            L.qs_words = (q_hi + 1) >> 1;
+            L.tg_words = (t_hi + 7) >> 3;
+            // staging: a block's narrow blobs, rounded up to 16 bytes
+            L.stage_bytes = (int)(((size_t)kBlockPairs * (seq_bytes(q_hi, false) + seq_bytes(t_hi, false)) + 15) & ~(size_t)15) + 16;
+            L.smem = smem_need(L.row_words, L.qs_words, L.tg_words, L.stage_bytes);
+            if (L.smem > kMaxSmem) L.smem = 0;  // long kernel
+            s.launches.push_back(L);
+            p = e;
+        }
+    }
+
+    // 4. blob offsets (narrow slots; every block of every launch starts 16-byte aligned)
+    h->offs.resize((size_t)nd + 1);
+    {
+        uint64_t run = 0;
+        for (const Launch &L : s.launches) {
+            for (int b = 0; b < L.n; ++b) {
+                if ((b % kBlockPairs) == 0) run = (run + 15) & ~(uint64_t)15;
+                const uint32_t k = ord[L.first + b];
+                h->offs[(size_t)(L.first + b)] = run;
+                run += slot_bytes(h->key[k], h->sizes[k]);
+            }
+        }
+        run = (run + 15) & ~(uint64_t)15;
+        h->offs[(size_t)nd] = run;
+    }
+    const uint64_t narrow_bytes = h->offs[(size_t)nd];
+    // worst case every pair is wide; the overflow area follows the narrow slots. Allocate lazily:
+    // first pass assumes 1/8 of the narrow size (+ slack), grows and repacks if exceeded.
+    int T = omp_get_max_threads();
+    std::vector<std::vector<uint8_t>> wide_buf((size_t)T);
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> wide_idx((size_t)T);  // (sorted pos, offset in thread buf)
+
+    int rc = ensure_slab(h, s, n, (size_t)narrow_bytes + 64);
+    if (rc) return rc;
+    uint8_t *blob = reinterpret_cast<uint8_t *>(s.h_blob);
+
+#pragma omp parallel num_threads(T)
+    {
+        int t = omp_get_thread_num();
+        std::vector<uint8_t> &wb = wide_buf[(size_t)t];
+        auto &wi = wide_idx[(size_t)t];
+#pragma omp for schedule(dynamic, 2048)
+        for (int p = 0; p < nd; ++p) {
+            const uint32_t k = ord[p];
+            const bsw_seqpair &sp = pp[k];
+            uint8_t *dst = blob + h->offs[(size_t)p];
+            const uint32_t qb = seq_bytes((uint32_t)sp.len2, false);
+            bool w1 = pack2bit(qer + sp.idq, sp.len2, dst);
+            bool w2 = pack2bit(ref + sp.idr, sp.len1, dst + qb);
+            PairMeta &m = s.h_meta[p];
+            m.off = (uint32_t)(h->offs[(size_t)p] >> 2);
+            m.id = k;
+            m.len2 = (uint16_t)sp.len2; m.len1 = (uint16_t)sp.len1;
+            m.h0 = (int16_t)sp.h0;
+            m.flags = 0;
+            if (w1 || w2) {
+                m.flags = 1;
+                const uint32_t wq = seq_bytes((uint32_t)sp.len2, true), wt = seq_bytes((uint32_t)sp.len1, true);
+                size_t o = wb.size();
+                o = (o + 3) & ~(size_t)3;
+                wb.resize(o + wq + wt);
+                pack4bit(qer + sp.idq, sp.len2, wb.data() + o);
+                pack4bit(ref + sp.idr, sp.len1, wb.data() + o + wq);
+                wi.emplace_back((uint32_t)p, (uint32_t)o);
+            }
+        }
+    }
+    // overflow area
+    uint64_t wide_total = 0;
+    std::vector<uint64_t> wbase((size_t)T);
+    for (int t = 0; t < T; ++t) {
+        wbase[(size_t)t] = narrow_bytes + wide_total;
+        wide_total += (wide_buf[(size_t)t].size() + 15) & ~(size_t)15;
+    }
+    s.blob_bytes = (size_t)(narrow_bytes + wide_total + 16);
+    if (s.blob_bytes > (size_t)0xFFFFFFFFull * 4) return BSW_ERR_RANGE;
+    if (wide_total) {
+        if (s.blob_bytes + 64 > s.cap_blob) {
+            // grow, keeping the narrow part
+            std::vector<uint8_t> keep(blob, blob + narrow_bytes);
+            rc = ensure_slab(h, s, n, s.blob_bytes + 64 + (s.blob_bytes >> 2));
+            if (rc) return rc;
+            blob = reinterpret_cast<uint8_t *>(s.h_blob);
+            memcpy(blob, keep.data(), (size_t)narrow_bytes);
+        }
+        for (int t = 0; t < T; ++t) {
+            if (wide_buf[(size_t)t].empty()) continue;
+            memcpy(blob + wbase[(size_t)t], wide_buf[(size_t)t].data(), wide_buf[(size_t)t].size());
+            for (auto &pr : wide_idx[(size_t)t]) {
+                // a wide pair keeps its narrow slot; the slot's first word points at the wide blob
+                uint32_t woff = (uint32_t)((wbase[(size_t)t] + pr.second) >> 2);
+                memcpy(blob + h->offs[(size_t)pr.first], &woff, 4);
+            }
+        }
+    }
+    memset(blob + s.blob_bytes - 16, 0, 16);
+    return BSW_OK;
+}
+
+// ---- device side of a slab ---------------------------------------------------------------------
+
+template <bool M1, bool SY>
+int launch_all(bsw_handle *h, Slab &s) {
+    for (const Launch &L : s.launches) {
+        const int grid = (L.n + kBlockPairs - 1) / kBlockPairs;
+        if (L.smem) {
+            auto kern = bsw_short_kernel<M1, SY>;
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+            kern<<<grid, kBlockPairs, L.smem, s.stream>>>(s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K,
+                                                         L.row_words, L.qs_words, L.tg_words, L.stage_bytes);
+        } else {
+            const size_t nthreads = (size_t)grid * kBlockPairs;
+            size_t need = (size_t)8 * L.row_words * nthreads +
+                          ((((size_t)2 * L.qs_words * nthreads) + 15) & ~(size_t)15) +
+                          (size_t)4 * L.tg_words * nthreads + 256;
+            if (need > s.cap_scratch) {
+                CU(cudaStreamSynchronize(s.stream));
+                if (s.d_scratch) cudaFree(s.d_scratch);
+                s.d_scratch = nullptr; s.cap_scratch = 0;
+                CU(cudaMalloc((void **)&s.d_scratch, need));
+                s.cap_scratch = need;
+            }
+            bsw_long_kernel<M1, SY><<<grid, kBlockPairs, 0, s.stream>>>(
+                s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K, L.row_words, L.qs_words, L.tg_words,
+                s.d_scratch);
+        }
+        CU(cudaGetLastError());
+        h->stats.kernel_launches++;
+        if (L.smem) h->stats.pairs_short += L.n; else h->stats.pairs_long += L.n;
+    }
+    return BSW_OK;
+}
+
+int launch_slab(bsw_handle *h, Slab &s) {
+    if (h->match1) return h->sym ? launch_all<true, true>(h, s) : launch_all<true, false>(h, s);
+    return h->sym ? launch_all<false, true>(h, s) : launch_all<false, false>(h, s);
+}
+
+// long launches of one slab must not share the scratch concurrently: they are on one stream -> serial.
+
+int upload_slab(bsw_handle *h, Slab &s) {
+    if (s.n_dev == 0) return BSW_OK;
+    CU(cudaMemcpyAsync(s.d_meta, s.h_meta, sizeof(PairMeta) * (size_t)s.n_dev, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.d_blob, s.h_blob, s.blob_bytes, cudaMemcpyHostToDevice, s.stream));
+    h->stats.h2d_bytes += (int64_t)(sizeof(PairMeta) * (size_t)s.n_dev + s.blob_bytes);
+    return BSW_OK;
+}
+
+int download_slab(bsw_handle *h, Slab &s) {
+    if (s.n_dev == 0) return BSW_OK;
+    CU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(PairOut) * (size_t)s.n, cudaMemcpyDeviceToHost, s.stream));
+    h->stats.d2h_bytes += (int64_t)(sizeof(PairOut) * (size_t)s.n);
+    return BSW_OK;
+}
+
+// writes the six outputs of slab s into the caller's array
+void scatter_slab(bsw_handle *h, const Slab &s, const PairOut *out, bsw_seqpair *pairs) {
+    bsw_seqpair *pp = pairs + s.lo;
+    const int n = s.n;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < n; ++k) {
+        const PairOut &o = out[k];
+        bsw_seqpair &p = pp[k];
+        p.score = o.score; p.qle = o.qle; p.tle = o.tle;
+        p.gtle = o.gtle; p.gscore = o.gscore; p.max_off = o.max_off;
+    }
+    // empty target or query: the DP loop never runs (bandedSWA.cpp:181 with tlen == 0 / end == 0)
+    for (uint32_t k : s.trivial) {
+        bsw_seqpair &p = pp[k];
+        p.score = p.h0; p.qle = 0; p.tle = 0; p.gtle = 0; p.gscore = -1; p.max_off = 0;
+    }
+    (void)h;
+}
+
+// slab boundaries over [0, n): by pair count and by bases
+void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts) {
+    cuts.clear();
+    cuts.push_back(0);
+    int64_t bases = 0, cnt = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        bases += (int64_t)std::max(pairs[k].len1, 0) + std::max(pairs[k].len2, 0);
+        ++cnt;
+        if (cnt >= kSlabPairs || bases >= kSlabBases) {
+            cuts.push_back(k + 1);
+            bases = 0; cnt = 0;
+        }
+    }
+    if (cuts.back() != n) cuts.push_back(n);
+}
+
+int finish_slab(bsw_handle *h, Slab &s, bsw_seqpair *pairs, double *kernel_ms_acc) {
+    if (!s.busy) return BSW_OK;
+    CU(cudaEventSynchronize(s.ev_done));
+    if (s.n_dev) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+        *kernel_ms_acc += ms;
+    }
+    auto t0 = Clock::now();
+    scatter_slab(h, s, s.h_out, pairs);
+    h->stats.host_scatter_ms += ms_since(t0);
+    s.busy = false;
+    return BSW_OK;
+}
+
+}  // namespace
+
+template <int W>
+static int run_peak(int iters, int blocks, int threads, uint32_t *sink, float *ms) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    dpx_peak_kernel<W><<<blocks, threads>>>(sink, 16, 3u);  // warm-up
+    cudaEventRecord(a);
+    dpx_peak_kernel<W><<<blocks, threads>>>(sink, iters, 3u);
+    cudaEventRecord(b);
+    cudaError_t e = cudaEventSynchronize(b);
+    cudaEventElapsedTime(ms, a, b);
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return e == cudaSuccess ? 0 : 1;
+}
+
+
+static void drop_staged(bsw_handle *h) {
+    for (Device &d : h->devs) {
+        cudaSetDevice(d.id);
+        for (Slab *s : d.staged) { free_slab(*s); delete s; }
+        d.staged.clear();
+    }
+    h->staged_n = -1;
+}
+
+
+// ================================================================================================
+extern "C" {
+
+int bsw_gpu_version(void) { return kVersion; }
+
+const char *bsw_gpu_strerror(int code) {
+    switch (code) {
+        case BSW_OK: return "ok";
+        case BSW_ERR_ARG: return "invalid argument";
+        case BSW_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case BSW_ERR_CUDA: return "CUDA runtime error";
+        case BSW_ERR_NOMEM: return "out of memory";
+        case BSW_ERR_RANGE: return "pair outside the int16 kernel's valid domain";
+        case BSW_ERR_STATE: return "staged API called out of order";
+        default: return "unknown error";
+    }
+}
+
+const char *bsw_gpu_last_error(const bsw_handle *h) { return h ? h->err.c_str() : ""; }
+
+int bsw_gpu_init_devices(const bsw_params *params, int n_devices, const int *device_ids,
+                         bsw_handle **out) {
+    if (!params || !out || n_devices < 0) return BSW_ERR_ARG;
+    *out = nullptr;
+    const bsw_params &p = *params;
+    if (p.e_del <= 0 || p.e_ins <= 0 || p.o_del < 0 || p.o_ins < 0 || p.match <= 0 || p.match > 127 ||
+        p.mismatch < 0 || p.mismatch > 128 || p.ambig < -128 || p.ambig > 127 || p.zdrop < 0 ||
+        p.zdrop > 32767 || p.o_del + p.e_del > 16383 || p.o_ins + p.e_ins > 16383)
+        return BSW_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return BSW_ERR_NO_DEVICE;
+    std::vector<int> ids;
+    if (device_ids && n_devices > 0) {
+        for (int i = 0; i < n_devices; ++i) {
+            if (device_ids[i] < 0 || device_ids[i] >= ndev) return BSW_ERR_ARG;
+            ids.push_back(device_ids[i]);
+        }
+    } else {
+        int want = n_devices > 0 ? n_devices : ndev;
+        if (want > ndev) return BSW_ERR_NO_DEVICE;
+        for (int i = 0; i < want; ++i) ids.push_back(i);
+    }
+    bsw_handle *h = new (std::nothrow) bsw_handle();
+    if (!h) return BSW_ERR_NOMEM;
+    h->P = p;
+    h->K = KParams{p.o_del, p.e_del, p.o_ins, p.e_ins, p.zdrop, p.end_bonus, p.match, p.mismatch, p.ambig, 0};
+    h->match1 = (p.match == 1);
+    h->sym = (p.o_del == p.o_ins && p.e_del == p.e_ins);
+    memset(&h->stats, 0, sizeof h->stats);
+    h->stats.n_gpus = (int)ids.size();
+    h->devs.resize(ids.size());
+    for (size_t d = 0; d < ids.size(); ++d) {
+        h->devs[d].id = ids[d];
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, ids[d]) != cudaSuccess || prop.major < 10) {
+            delete h;
+            return BSW_ERR_NO_DEVICE;  // kernels are sm_100a only
+        }
+    }
+    *out = h;
+    return BSW_OK;
+}
+
+int bsw_gpu_init(const bsw_params *params, int n_gpus, bsw_handle **out) {
+    return bsw_gpu_init_devices(params, n_gpus > 0 ? n_gpus : 0, nullptr, out);
+}
+
+void bsw_gpu_free(bsw_handle *h) {
+    if (!h) return;
+    for (Device &d : h->devs) {
+        cudaSetDevice(d.id);
+        for (Slab &s : d.ring) free_slab(s);
+        for (Slab *s : d.staged) { free_slab(*s); delete s; }
+    }
+    delete h;
+}
+
+int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out) {
+    if (!h || !out) return BSW_ERR_ARG;
+    *out = h->stats;
+    return BSW_OK;
+}
+
+int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                  int64_t n, int32_t w) {
+    if (!h || n < 0 || (n > 0 && (!pairs || !ref || !qer)) || w < 0) return BSW_ERR_ARG;
+    auto t_all = Clock::now();
+    const int ng = (int)h->devs.size();
+    bsw_gpu_stats &st = h->stats;
+    st.pairs = n; st.kernel_launches = 0; st.h2d_bytes = 0; st.d2h_bytes = 0;
+    st.pairs_short = 0; st.pairs_long = 0;
+    st.host_bin_ms = st.host_pack_ms = st.host_scatter_ms = st.kernel_ms = 0;
+    h->K.w = w;
+    if (n == 0) { st.wall_ms = 0; return BSW_OK; }
+
+    std::vector<int64_t> cuts;
+    cut_slabs(pairs, n, cuts);
+    const int nslabs = (int)cuts.size() - 1;
+    std::vector<double> kms((size_t)ng, 0.0);
+    int rc = BSW_OK;
+
+    for (int sidx = 0; sidx < nslabs && rc == BSW_OK; ++sidx) {
+        const int d = sidx % ng, r = (sidx / ng) % kRing;
+        Device &dev = h->devs[(size_t)d];
+        Slab &s = dev.ring[r];
+        CU(cudaSetDevice(dev.id));
+        rc = finish_slab(h, s, pairs, &kms[(size_t)d]);  // ring slot still owns an older slab
+        if (rc) break;
+        auto t0 = Clock::now();
+        rc = prepare_slab(h, s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]));
+        st.host_pack_ms += ms_since(t0);
+        if (rc) break;
+        if (s.n_dev) {
+            if ((rc = upload_slab(h, s))) break;
+            CU(cudaEventRecord(s.ev_k0, s.stream));
+            if ((rc = launch_slab(h, s))) break;
+            CU(cudaEventRecord(s.ev_k1, s.stream));
+            if ((rc = download_slab(h, s))) break;
+        }
+        CU(cudaEventRecord(s.ev_done, s.stream));
+        s.busy = true;
+    }
+    // drain (also on error, so that no stream still writes pinned memory we may free later)
+    for (int d = 0; d < ng; ++d) {
+        Device &dev = h->devs[(size_t)d];
+        cudaSetDevice(dev.id);
+        for (int r = 0; r < kRing; ++r) {
+            Slab &s = dev.ring[r];
+            if (!s.busy) continue;
+            if (rc == BSW_OK) rc = finish_slab(h, s, pairs, &kms[(size_t)d]);
+            else { cudaEventSynchronize(s.ev_done); s.busy = false; }
+        }
+    }
+    st.kernel_ms = *std::max_element(kms.begin(), kms.end());
+    st.wall_ms = ms_since(t_all);
+    return rc;
+}
+
+// ---- staged API --------------------------------------------------------------------------------
+
+int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                  int64_t n, int32_t w) {
+    if (!h || n < 0 || (n > 0 && (!pairs || !ref || !qer)) || w < 0) return BSW_ERR_ARG;
+    drop_staged(h);
+    bsw_gpu_stats &st = h->stats;
+    st.pairs = n; st.h2d_bytes = 0; st.d2h_bytes = 0; st.kernel_launches = 0;
+    st.pairs_short = st.pairs_long = 0;
+    h->K.w = w;
+    const int ng = (int)h->devs.size();
+    std::vector<int64_t> cuts;
+    cut_slabs(pairs, n, cuts);
+    const int nslabs = (int)cuts.size() - 1;
+    for (int sidx = 0; sidx < nslabs; ++sidx) {
+        Device &dev = h->devs[(size_t)(sidx % ng)];
+        CU(cudaSetDevice(dev.id));
+        Slab *s = new (std::nothrow) Slab();
+        if (!s) return BSW_ERR_NOMEM;
+        dev.staged.push_back(s);
+        int rc = prepare_slab(h, *s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]));
+        if (rc) { drop_staged(h); return rc; }
+        if ((rc = upload_slab(h, *s))) { drop_staged(h); return rc; }
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    h->staged_n = n; h->staged_w = w;
+    return BSW_OK;
+}
+
+int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms) {
+    if (!h) return BSW_ERR_ARG;
+    if (h->staged_n < 0) return BSW_ERR_STATE;
+    h->K.w = h->staged_w;
+    h->stats.kernel_launches = 0;
+    h->stats.pairs_short = h->stats.pairs_long = 0;
+    // all slabs of one GPU run back to back on that GPU's first stream; GPUs run concurrently
+    for (Device &dev : h->devs) {
+        if (dev.staged.empty()) continue;
+        CU(cudaSetDevice(dev.id));
+        cudaStream_t st0 = dev.staged[0]->stream;
+        CU(cudaEventRecord(dev.staged[0]->ev_k0, st0));
+        for (Slab *s : dev.staged) {
+            cudaStream_t keep = s->stream;
+            s->stream = st0;
+            int rc = s->n_dev ? launch_slab(h, *s) : BSW_OK;
+            s->stream = keep;
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(dev.staged[0]->ev_k1, st0));
+    }
+    float worst = 0.f;
+    for (Device &dev : h->devs) {
+        if (dev.staged.empty()) continue;
+        CU(cudaSetDevice(dev.id));
+        CU(cudaEventSynchronize(dev.staged[0]->ev_k1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, dev.staged[0]->ev_k0, dev.staged[0]->ev_k1));
+        worst = std::max(worst, ms);
+    }
+    h->stats.kernel_ms = worst;
+    if (kernel_ms) *kernel_ms = worst;
+    return BSW_OK;
+}
+
+int bsw_gpu_fetch_staged(bsw_handle *h, bsw_seqpair *pairs, int64_t n) {
+    if (!h || !pairs) return BSW_ERR_ARG;
+    if (h->staged_n < 0 || n != h->staged_n) return BSW_ERR_STATE;
+    h->stats.d2h_bytes = 0;
+    for (Device &dev : h->devs) {
+        CU(cudaSetDevice(dev.id));
+        for (Slab *s : dev.staged) {
+            if (s->n_dev) {
+                int rc = download_slab(h, *s);
+                if (rc) return rc;
+                CU(cudaStreamSynchronize(s->stream));
+            }
+            scatter_slab(h, *s, s->h_out, pairs);
+        }
+    }
+    return BSW_OK;
+}
+
+// ---- integer-pipe microbenchmark -----------------------------------------------------------------
+
+int bsw_gpu_dpx_peak(int device, int which, double *ginstr_per_s, double *sm_mhz_est) {
+    if (!ginstr_per_s) return BSW_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return BSW_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BSW_ERR_NO_DEVICE;
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+    uint32_t *sink = nullptr;
+    if (cudaMalloc((void **)&sink, 4096) != cudaSuccess) return BSW_ERR_NOMEM;
+    float ms = 0.f;
+    int rc = 0;
+    switch (which) {
+        case 0: rc = run_peak<0>(iters, blocks, threads, sink, &ms); break;
+        case 1: rc = run_peak<1>(iters, blocks, threads, sink, &ms); break;
+        case 2: rc = run_peak<2>(iters, blocks, threads, sink, &ms); break;
+        case 3: rc = run_peak<3>(iters, blocks, threads, sink, &ms); break;
+        case 4: rc = run_peak<4>(iters, blocks, threads, sink, &ms); break;
+        case 5: rc = run_peak<5>(iters, blocks, threads, sink, &ms); break;
+        case 6: rc = run_peak<6>(iters, blocks, threads, sink, &ms); break;
+        case 7: rc = run_peak<7>(iters, blocks, threads, sink, &ms); break;
+        case 8: rc = run_peak<8>(iters, blocks, threads, sink, &ms); break;
+        default: cudaFree(sink); return BSW_ERR_ARG;
+    }
+    cudaFree(sink);
+    if (rc) return BSW_ERR_CUDA;
+    // thread-instructions of the measured kind: iters * 4 (unroll) * 8 (chains) per thread
+    double per_thread = (double)iters * 4.0 * 8.0 * (which == 8 ? 2.0 : 1.0);
+    double total = per_thread * (double)threads * (double)blocks;
+    *ginstr_per_s = total / (ms * 1e-3) / 1e9;
+    if (sm_mhz_est) *sm_mhz_est = (double)prop.clockRate / 1000.0;
+    return BSW_OK;
+}
+
+}  // extern "C"

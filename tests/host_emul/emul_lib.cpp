@@ -1,0 +1,52 @@
+// TEST INFRASTRUCTURE: runs the product's per-pair device code (unpack_pair + extend_pair from
+// genarchbench_b200/csrc/bsw_kernels.cuh) and host packers (bsw_pack.h) on the CPU through the
+// intrinsic emulation in dpx_host_emul.h. Used only by tests/test_host_emulation.py to check the
+// kernel's ALGORITHM against the oracle where no GPU exists; it is not a product path.
+#define BSW_HOST_EMUL 1
+#include "bsw_kernels.cuh"
+#include "bsw_pack.h"
+#include "bsw_types.h"
+#include <vector>
+
+using namespace bswk;
+
+extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
+                              const uint8_t *qer, int64_t n, int32_t w) {
+    KParams K{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w};
+    const bool m1 = p->match == 1, sym = p->o_del == p->o_ins && p->e_del == p->e_ins;
+#pragma omp parallel
+    {
+        std::vector<uint2> he;
+        std::vector<uint16_t> qs;
+        std::vector<uint32_t> tg, blob;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t k = 0; k < n; ++k) {
+            bsw_seqpair &sp = pairs[k];
+            if (sp.len1 == 0 || sp.len2 == 0) {
+                sp.score = sp.h0; sp.qle = sp.tle = sp.gtle = 0; sp.gscore = -1; sp.max_off = 0;
+                continue;
+            }
+            he.assign((size_t)((sp.len2 + 1) / 2 + 2), uint2{0xDEADBEEFu, 0xDEADBEEFu});
+            qs.assign((size_t)((sp.len2 + 1) / 2 + 1), 0xDEAD);
+            tg.assign((size_t)((sp.len1 + 7) / 8 + 1), 0xDEADBEEFu);
+            blob.assign((size_t)(seq_bytes(sp.len2, true) + seq_bytes(sp.len1, true)) / 4 + 4, 0);
+            uint8_t *b = reinterpret_cast<uint8_t *>(blob.data());
+            bool wide = pack2bit(qer + sp.idq, sp.len2, b);
+            wide |= pack2bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, false));
+            if (wide) {
+                pack4bit(qer + sp.idq, sp.len2, b);
+                pack4bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, true));
+            }
+            Rows R{he.data(), qs.data(), tg.data(), 1};
+            unpack_pair(blob.data(), sp.len2, sp.len1, wide, R);
+            PairResult r;
+            if (m1) r = sym ? extend_pair<true, true>(R, sp.len2, sp.len1, sp.h0, K)
+                            : extend_pair<true, false>(R, sp.len2, sp.len1, sp.h0, K);
+            else r = sym ? extend_pair<false, true>(R, sp.len2, sp.len1, sp.h0, K)
+                         : extend_pair<false, false>(R, sp.len2, sp.len1, sp.h0, K);
+            sp.score = r.score; sp.qle = r.qle; sp.tle = r.tle; sp.gtle = r.gtle;
+            sp.gscore = r.gscore; sp.max_off = r.max_off;
+        }
+    }
+    return 0;
+}
