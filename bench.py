@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- bsw (banded Smith-Waterman seed extension) throughput on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch: BASELINE.json config 3 ("bsw large-shape single
+GPU": 10 M synthetic 151-bp read / ref-window pairs, w=100, default scoring) PER GPU (weak scaling;
+N=8 is config 5, 80 M pairs). Rank r generates its own shard (seed 1003 + 7919 r); there is no
+data-path collective (pairs are independent) -- torch.distributed only provides the barrier and the
+max-over-ranks / sum-over-ranks reductions.
+
+  value : GCUPS = DP cells the reference's scalar loop visits (counted on the device by
+          the COUNT kernel, checked against the oracle in tests) / device time (CUDA events on the
+          launching stream, inputs resident in HBM), whole job, max time over ranks.
+  e2e   : the same metric through the drop-in call bsw_gpu_batch with HOST buffers: binning, 2-bit
+          packing into pinned memory, H2D, kernels, D2H and the scatter into SeqPair all inside the
+          timed region (wall clock around the call, max over ranks).
+  roofline : integer/DPX pipe (this path is neither HBM- nor tensor-bound):
+          achieved = cells/s * 2.5 packed-s16x2 instructions, peak = VIADDMNMX.S16x2.RELU issue rate
+          measured live on this GPU (bsw_gpu_dpx_peak). An `hbm` sanity entry uses MEASURED_PEAKS.json.
+  cpu_baseline : the UNMODIFIED reference getScores16 (oracle/_ref, OpenMP over 512-pair batches as in
+          main_banded.cpp:338-350) on the box's host cores, bounded sample, rank 0 at N=1.
+  --impl reference : only that CPU arm, same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RANK = int(os.environ.get("RANK", 0))
+LOCAL_RANK = int(os.environ.get("LOCAL_RANK", 0))
+WORLD = int(os.environ.get("WORLD_SIZE", 1))
+NCORES = os.cpu_count() or 1
+# host packing threads: share the box's cores between the ranks (set before OpenMP loads)
+os.environ.setdefault("OMP_NUM_THREADS", str(max(1, NCORES // max(WORLD, 1))))
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = ("bsw config 3 (large-shape): synthetic 151-bp read / ref-window extension pairs, "
+            "w=100, match 1 / mismatch 4 / gap 6+1 / zdrop 100 / end bonus 5")
+INSTR_PER_CELL = 2.5          # 5 packed-s16x2 DPX instructions per 2 cells
+BYTES_PER_PAIR_FMT = "ceil(len1/4)+ceil(len2/4)+12+24"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return {}
+
+
+def algorithmic_bytes(pairs: np.ndarray) -> int:
+    """per pair ceil(len1/4)+ceil(len2/4) packed bases + 12 B of lengths/h0 + 24 B out."""
+    l1 = pairs["len1"].astype(np.int64)
+    l2 = pairs["len2"].astype(np.int64)
+    return int(((l1 + 3) // 4 + (l2 + 3) // 4 + 36).sum())
+
+
+def reference_arm(args, batch, cells_fn) -> dict:
+    """Times the reference CPU implementation of the path on a bounded sample, all host threads."""
+    import oracle
+    n = min(len(batch), args.cpu_sample)
+    sample = batch.slice(0, n)
+    cells = cells_fn(sample)
+    kind = "reference" if oracle.reference_available() else "port"
+    isa = oracle.reference_isas()[0] if kind == "reference" else None
+    threads = NCORES
+
+    def one():
+        if kind == "reference":
+            return oracle.reference_batch(sample, nthreads=threads, isa=isa)
+        t0 = time.perf_counter()
+        oracle.oracle_batch(sample, nthreads=threads)
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup_cpu):
+        one()
+    secs = [one() for _ in range(args.steps_cpu)]
+    t = float(np.mean(secs))
+    return {"value": cells / t / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
+            "sample": f"first {n} pairs of the rank-0 workload, {args.steps_cpu} passes after "
+                      f"{args.warmup_cpu} warm-up, ROI = OpenMP loop over 512-pair getScores16 batches"
+                      + (f" ({isa} build of the reference)" if isa else " (oracle port)"),
+            "pairs_per_s": n / t, "ms_per_pass": t * 1e3, "cells": cells, "pairs": n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU (config 3: 10 M)")
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--steps-cpu", type=int, default=3)
+    ap.add_argument("--warmup-cpu", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+
+    from genarchbench_b200 import pairio, dist as bdist
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if args.impl == "reference":
+        if RANK != 0:
+            return
+        import oracle
+        batch = pairio.generate(3, min(args.pairs, args.cpu_sample), seed=bdist.shard_seed(1003, 0))
+        args.steps_cpu, args.warmup_cpu = max(1, args.steps), max(1, min(args.warmup, 2))
+        cb = reference_arm(args, batch, lambda b: oracle.oracle_batch(b.copy()))
+        line = {"impl": "reference", "metric": "bsw_gcups", "value": cb["value"], "unit": "GCUPS",
+                "n_gpus": args.gpus, "steps": args.steps_cpu, "warmup": args.warmup_cpu,
+                "ms_per_step": cb["ms_per_pass"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "pairs_per_step": cb["pairs"], "w": 100},
+                "pairs_per_s": cb["pairs_per_s"],
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    from genarchbench_b200 import bsw
+    rank, local_rank, world = bdist.init_process_group()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        bdist.barrier()
+        torch.cuda.synchronize()
+
+    batch = pairio.generate(3, args.pairs, seed=bdist.shard_seed(1003, rank))
+    g = bsw.BswGpu(devices=[local_rank])
+    g.stage(batch.pairs, batch.ref, batch.qer, 100)
+    cells = g.count_staged()                      # unit of work, outside any timed region
+    dpx_peak = bsw.dpx_peak(0, device=local_rank)  # Ginstr/s, measured live on this GPU
+
+    # ---- value: device-resident kernel throughput
+    for _ in range(args.warmup):
+        g.run_staged()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        dev_ms += g.run_staged()                  # CUDA events on the launching stream
+        launches += g.stats()["kernel_launches"]
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    (sum_cells, sum_pairs, sum_launch), (max_dev_ms, max_wall_ms) = bdist.reduce_stats(
+        [cells, len(batch), launches], [dev_ms, wall_ms])
+    ms_per_step = max_dev_ms / args.steps
+    gcups = sum_cells / (ms_per_step * 1e-3) / 1e9
+    pairs_per_s = sum_pairs / (ms_per_step * 1e-3)
+
+    # ---- e2e: through bsw_gpu_batch with host buffers
+    e2e_steps = args.e2e_steps or args.steps
+    work = batch.copy()
+    g.batch(work.pairs, work.ref, work.qer, 100)  # warm the pinned rings
+    sync_all()
+    t0 = time.perf_counter()
+    h2d = d2h = e2e_launch = 0
+    for _ in range(e2e_steps):
+        g.batch(work.pairs, work.ref, work.qer, 100)
+        st = g.stats()
+        h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]; e2e_launch += st["kernel_launches"]
+    last = dict(st)
+    sync_all()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    (sum_h2d, sum_d2h), (max_e2e_ms,) = bdist.reduce_stats([h2d, d2h], [e2e_ms])
+    e2e_step_s = max_e2e_ms / e2e_steps * 1e-3
+    checksum_ok = bool((work.outputs() != -1).any())
+
+    if rank != 0:
+        g.close()
+        return
+
+    peaks = measured_peaks()
+    alg_bytes = algorithmic_bytes(batch.pairs)
+    achieved_instr = cells / (dev_ms / args.steps * 1e-3) * INSTR_PER_CELL / 1e9   # this rank's GPU
+    roofline = {
+        "bound": "dpx_int", "kernel": "bsw_short_kernel<1,1,0> (thread-per-pair, s16x2 DPX)",
+        "achieved": achieved_instr, "peak": dpx_peak, "unit": "Ginstr/s (packed s16x2 thread-instructions)",
+        "frac": achieved_instr / dpx_peak, "instr_per_cell": INSTR_PER_CELL,
+        "peak_source": "measured live: VIADDMNMX.S16x2.RELU issue rate, all SMs (bsw_gpu_dpx_peak)",
+        "traffic": None,
+        "hbm": {"algorithmic_bytes_per_step": alg_bytes, "bytes_per_pair": BYTES_PER_PAIR_FMT,
+                "achieved_gbs": alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
+                "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json (of measured)"
+                if peaks.get("hbm_gbs") else "unavailable"},
+    }
+    cpu_baseline = None
+    if world == 1:
+        g2 = bsw.BswGpu(devices=[local_rank])
+
+        def count(b):
+            g2.stage(b.pairs, b.ref, b.qer, 100)
+            return g2.count_staged()
+        cb = reference_arm(args, batch, count)
+        g2.close()
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "pairs_per_s")}
+
+    line = {
+        "metric": "bsw_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": args.pairs, "global_pairs": int(sum_pairs),
+                   "cells_visited_per_step": int(sum_cells), "cells_rect_per_gpu": batch.cells_rect(),
+                   "w": 100, "parallelism": f"pair-sharded x{world}, no collective",
+                   "l2": f"inputs larger than L2: {alg_bytes / 1e6:.0f} MB of packed pairs + results per step vs 126 MB"},
+        "pairs_per_s": pairs_per_s,
+        "wall_ms_per_step": max_wall_ms / args.steps,
+        "clocks": clocks,
+        "e2e": {"value": sum_cells / e2e_step_s / 1e9, "unit": "GCUPS",
+                "pairs_per_s": sum_pairs / e2e_step_s, "ms_per_step": e2e_step_s * 1e3, "steps": e2e_steps,
+                "h2d_bytes_per_step": int(sum_h2d / e2e_steps), "d2h_bytes_per_step": int(sum_d2h / e2e_steps),
+                "host_pack_ms": last["host_pack_ms"], "host_scatter_ms": last["host_scatter_ms"],
+                "kernel_ms": last["kernel_ms"], "host_threads": int(os.environ["OMP_NUM_THREADS"]),
+                "api": "bsw_gpu_batch(SeqPair*, ref, qer, n, w) from host buffers", "results_written": checksum_ok},
+        "gpu_launches": int(sum_launch),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    g.close()
+
+
+if __name__ == "__main__":
+    main()

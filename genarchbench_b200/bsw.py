@@ -28,7 +28,7 @@ ERRORS = {1: "BSW_ERR_ARG", 2: "BSW_ERR_NO_DEVICE", 3: "BSW_ERR_CUDA", 4: "BSW_E
 
 # every symbol include/bsw_gpu.h declares
 EXPORTS = ("bsw_gpu_init", "bsw_gpu_init_devices", "bsw_gpu_free", "bsw_gpu_batch", "bsw_gpu_stage",
-           "bsw_gpu_run_staged", "bsw_gpu_fetch_staged", "bsw_gpu_get_stats", "bsw_gpu_dpx_peak",
+           "bsw_gpu_run_staged", "bsw_gpu_fetch_staged", "bsw_gpu_count_staged", "bsw_gpu_get_stats", "bsw_gpu_dpx_peak",
            "bsw_gpu_strerror", "bsw_gpu_last_error", "bsw_gpu_version")
 
 
@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         L.bsw_gpu_stage.argtypes = [vp, vp, vp, vp, i64, i32]
         L.bsw_gpu_run_staged.argtypes = [vp, C.POINTER(C.c_float)]
         L.bsw_gpu_fetch_staged.argtypes = [vp, vp, i64]
+        L.bsw_gpu_count_staged.argtypes = [vp, C.POINTER(C.c_int64)]
         L.bsw_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.bsw_gpu_dpx_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.bsw_gpu_strerror.argtypes = [C.c_int]
@@ -131,6 +132,12 @@ class BswGpu:
 
     def fetch_staged(self, pairs: np.ndarray) -> None:
         self._check(self._L.bsw_gpu_fetch_staged(self._h, pairs.ctypes.data, len(pairs)))
+
+    def count_staged(self) -> int:
+        """DP cells the reference's scalar loop visits for the staged batch (the GCUPS unit of work)."""
+        c = C.c_int64(0)
+        self._check(self._L.bsw_gpu_count_staged(self._h, C.byref(c)))
+        return int(c.value)
 
     def stats(self) -> dict:
         s = Stats()

@@ -362,12 +362,12 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
 
 // ---- device side of a slab ---------------------------------------------------------------------
 
-template <bool M1, bool SY>
+template <bool M1, bool SY, bool CNT>
 int launch_all(bsw_handle *h, Slab &s) {
     for (const Launch &L : s.launches) {
         const int grid = (L.n + kBlockPairs - 1) / kBlockPairs;
         if (L.smem) {
-            auto kern = bsw_short_kernel<M1, SY>;
+            auto kern = bsw_short_kernel<M1, SY, CNT>;
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
             kern<<<grid, kBlockPairs, L.smem, s.stream>>>(s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K,
                                                          L.row_words, L.qs_words, L.tg_words, L.stage_bytes);
@@ -383,7 +383,7 @@ int launch_all(bsw_handle *h, Slab &s) {
                 CU(cudaMalloc((void **)&s.d_scratch, need));
                 s.cap_scratch = need;
             }
-            bsw_long_kernel<M1, SY><<<grid, kBlockPairs, 0, s.stream>>>(
+            bsw_long_kernel<M1, SY, CNT><<<grid, kBlockPairs, 0, s.stream>>>(
                 s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K, L.row_words, L.qs_words, L.tg_words,
                 s.d_scratch);
         }
@@ -394,9 +394,13 @@ int launch_all(bsw_handle *h, Slab &s) {
     return BSW_OK;
 }
 
-int launch_slab(bsw_handle *h, Slab &s) {
-    if (h->match1) return h->sym ? launch_all<true, true>(h, s) : launch_all<true, false>(h, s);
-    return h->sym ? launch_all<false, true>(h, s) : launch_all<false, false>(h, s);
+int launch_slab(bsw_handle *h, Slab &s, bool count = false) {
+    if (count) {
+        if (h->match1) return h->sym ? launch_all<true, true, true>(h, s) : launch_all<true, false, true>(h, s);
+        return h->sym ? launch_all<false, true, true>(h, s) : launch_all<false, false, true>(h, s);
+    }
+    if (h->match1) return h->sym ? launch_all<true, true, false>(h, s) : launch_all<true, false, false>(h, s);
+    return h->sym ? launch_all<false, true, false>(h, s) : launch_all<false, false, false>(h, s);
 }
 
 // long launches of one slab must not share the scratch concurrently: they are on one stream -> serial.
@@ -538,7 +542,8 @@ int bsw_gpu_init_devices(const bsw_params *params, int n_devices, const int *dev
     bsw_handle *h = new (std::nothrow) bsw_handle();
     if (!h) return BSW_ERR_NOMEM;
     h->P = p;
-    h->K = KParams{p.o_del, p.e_del, p.o_ins, p.e_ins, p.zdrop, p.end_bonus, p.match, p.mismatch, p.ambig, 0};
+    h->K = KParams{p.o_del, p.e_del, p.o_ins, p.e_ins, p.zdrop, p.end_bonus, p.match, p.mismatch, p.ambig, 0,
+                   max_score_of(p.match, p.mismatch, p.ambig)};
     h->match1 = (p.match == 1);
     h->sym = (p.o_del == p.o_ins && p.e_del == p.e_ins);
     memset(&h->stats, 0, sizeof h->stats);
@@ -692,6 +697,34 @@ int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms) {
     }
     h->stats.kernel_ms = worst;
     if (kernel_ms) *kernel_ms = worst;
+    return BSW_OK;
+}
+
+int bsw_gpu_count_staged(bsw_handle *h, int64_t *cells_visited) {
+    if (!h || !cells_visited) return BSW_ERR_ARG;
+    if (h->staged_n < 0) return BSW_ERR_STATE;
+    h->K.w = h->staged_w;
+    int64_t total = 0;
+    for (Device &dev : h->devs) {
+        CU(cudaSetDevice(dev.id));
+        for (Slab *s : dev.staged) {
+            if (!s->n_dev) continue;
+            int rc = launch_slab(h, *s, true);
+            if (rc) return rc;
+            if ((rc = download_slab(h, *s))) return rc;
+            CU(cudaStreamSynchronize(s->stream));
+            int64_t sum = 0;
+            const int n = s->n;
+            const PairOut *o = s->h_out;
+            // entries of pairs answered on the host were never written by the device
+            std::vector<char> skip((size_t)n, 0);
+            for (uint32_t k : s->trivial) skip[k] = 1;
+#pragma omp parallel for reduction(+ : sum) schedule(static)
+            for (int k = 0; k < n; ++k) if (!skip[(size_t)k]) sum += o[k].cells;
+            total += sum;
+        }
+    }
+    *cells_visited = total;
     return BSW_OK;
 }
 

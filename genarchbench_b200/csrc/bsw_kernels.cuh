@@ -36,7 +36,18 @@ constexpr int kBlockPairs = 128;  // threads per block == pairs per block (host 
 
 struct KParams {
     int o_del, e_del, o_ins, e_ins, zdrop, end_bonus, match, mismatch, ambig, w;
+    // max(0, match, -mismatch, ambig), the reference wrapper's `max` (bandedSWA.cpp:2790-2793).
+    // Computed on the HOST: ptxas 12.9 (sm_100a) fuses max(max(max(match, -mismatch), ambig), 0)
+    // into one VIMNMX3.RELU and drops the negation (seen on B200: band came out as w).
+    int max_score;
 };
+__host__ __device__ inline int max_score_of(int match, int mismatch, int ambig) {
+    int mx = 0;
+    if (mx < match) mx = match;
+    if (mx < -mismatch) mx = -mismatch;
+    if (mx < ambig) mx = ambig;
+    return mx;
+}
 
 // 16 bytes per pair, sorted order (host: length-binned). `off` in 4-byte units from the blob base.
 struct __align__(16) PairMeta {
@@ -49,7 +60,8 @@ struct __align__(16) PairMeta {
 };
 
 struct __align__(16) PairOut {  // one STG.128 per pair
-    int16_t score, qle, tle, gtle, gscore, max_off, pad0, pad1;
+    int16_t score, qle, tle, gtle, gscore, max_off;
+    uint32_t cells;   // COUNT kernels only: DP cells the reference's scalar loop visits for this pair
 };
 
 __host__ __device__ inline uint32_t seq_bytes(uint32_t len, bool wide) {
@@ -81,11 +93,23 @@ struct Rows {
     uint32_t *tg;
     int stride;  // threads sharing the arrays (blockDim for shared memory, grid-wide for global)
     __device__ __forceinline__ uint2 &HE(int g) const { return he[(size_t)g * stride]; }
-    __device__ __forceinline__ uint16_t &H16(int j) const {
-        return reinterpret_cast<uint16_t *>(&he[(size_t)(j >> 1) * stride].x)[j & 1];
+    // 16-bit views of the rows. They go through the SAME 32-bit words the packed loop reads and
+    // writes (no differently-typed aliases the compiler could reorder around the uint2 accesses).
+    __device__ __forceinline__ uint32_t getH16(int j) const {
+        const uint32_t w = he[(size_t)(j >> 1) * stride].x;
+        return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
     }
-    __device__ __forceinline__ uint16_t &E16(int j) const {
-        return reinterpret_cast<uint16_t *>(&he[(size_t)(j >> 1) * stride].y)[j & 1];
+    __device__ __forceinline__ uint32_t getE16(int j) const {
+        const uint32_t w = he[(size_t)(j >> 1) * stride].y;
+        return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+    }
+    // sets Hs[j] = hv and E[j] = ev, leaving the other half of the word pair untouched
+    __device__ __forceinline__ void setHE16(int j, uint32_t hv, uint32_t ev) const {
+        uint2 &p = he[(size_t)(j >> 1) * stride];
+        uint2 v = p;
+        if (j & 1) { v.x = (v.x & 0xFFFFu) | (hv << 16); v.y = (v.y & 0xFFFFu) | (ev << 16); }
+        else { v.x = (v.x & 0xFFFF0000u) | hv; v.y = (v.y & 0xFFFF0000u) | ev; }
+        p = v;
     }
     __device__ __forceinline__ uint16_t &QS(int g) const { return qs[(size_t)g * stride]; }
     __device__ __forceinline__ uint32_t &TG(int w) const { return tg[(size_t)w * stride]; }
@@ -161,15 +185,13 @@ __device__ inline void unpack_pair(const uint32_t *blob, int qlen, int tlen, boo
 
 struct PairResult {
     int score, qle, tle, gtle, gscore, max_off;
+    uint32_t cells;
 };
 
 // per-pair band, the vector wrapper's rule (bandedSWA.cpp:2898-2919): uint16 arithmetic, integer
 // division, then +1.
 __device__ __forceinline__ int pair_band(const KParams &P, int qlen) {
-    int mx = 0;
-    if (mx < P.match) mx = P.match;
-    if (mx < -P.mismatch) mx = -P.mismatch;
-    if (mx < P.ambig) mx = P.ambig;
+    const int mx = P.max_score;
     uint32_t q = (uint32_t)(qlen * mx) & 0xFFFFu;
     uint32_t a = (q + (uint32_t)(P.end_bonus - P.o_ins)) & 0xFFFFu;
     int band = min(P.w, max((int)(a / (uint32_t)P.e_ins) + 1, 1));
@@ -181,7 +203,10 @@ __device__ __forceinline__ int pair_band(const KParams &P, int qlen) {
 // The DP of one pair over row storage R (already holding qs[] and tg[]).
 //   MATCH1: match score == 1 (M = Hd + min(s, Hd) needs no multiply)
 //   SYM   : o_del == o_ins && e_del == e_ins (one T for both gap kinds)
-template <bool MATCH1, bool SYM>
+//   COUNT : also track the reference's exact leading trim and count the cells its scalar loop would
+//           visit (bandedSWA.cpp:191-216; the commented SW_cells++ at :215) -- the unit of work of
+//           the GCUPS metric. Used once per input outside any timed region.
+template <bool MATCH1, bool SYM, bool COUNT>
 __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int h0, const KParams &P) {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
@@ -214,11 +239,17 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
     int best = h0, best_i = -1, best_j = -1, g_i = -1, gsc = -1, off = 0;
     int beg = 0, end = qlen;
     uint32_t tword = 0;
+    int xbeg = 0;            // COUNT: the reference's exact beg (ours lags it by whole words)
+    uint32_t cells = 0;
 
     for (int i = 0; i < budget; ++i) {
         if (beg < i - band) beg = i - band;
         if (end > i + band + 1) end = i + band + 1;
         if (beg >= end) break;
+        if (COUNT) {
+            if (xbeg < i - band) xbeg = i - band;
+            cells += (uint32_t)(end - xbeg);
+        }
 
         if ((i & 7) == 0) tword = R.TG(i >> 3);
         const uint32_t tcode = (tword >> (4 * (i & 7))) & 0x7u;
@@ -229,8 +260,8 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
 
         // Lanes outside [beg, end) of the first / last word must see zero inputs: clear the stale
         // (never read again) entries instead of masking inside the loop.
-        if (beg & 1) { R.H16(beg - 1) = 0; R.E16(beg - 1) = 0; }
-        if (end & 1) { R.H16(end) = 0; R.E16(end) = 0; }
+        if (beg & 1) R.setHE16(beg - 1, 0u, 0u);
+        if (end & 1) R.setHE16(end, 0u, 0u);
 
         const int g0 = beg >> 1, g1 = (end - 1) >> 1;
         uint32_t hprev = (uint32_t)hleft << 16;  // .hi = H(i, 2*g0 - 1)
@@ -273,8 +304,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             hlast = (int)(h & 0xFFFFu);          // word g1 already holds { .., H(i,end-1) } / E[end]=0
         } else {
             hlast = (int)(h >> 16);
-            R.H16(end) = (uint16_t)hlast;
-            R.E16(end) = 0;
+            R.setHE16(end, (uint32_t)hlast, 0u);
         }
         if (end == qlen) {                        // bandedSWA.cpp:218-221
             if (!(gsc > hlast)) g_i = i;
@@ -297,6 +327,11 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             if (best - m - abs(di - dj) > P.zdrop) break;
         }
 
+        if (COUNT) {   // the reference's scan (bandedSWA.cpp:234-235), on the rows just written
+            int j = xbeg;
+            while (j < end && R.getH16(j) == 0 && R.getE16(j) == 0) ++j;
+            xbeg = j;
+        }
         // leading trim (not semantic: skipped cells are all-zero; done lazily, one word per row)
         {
             const uint2 z = R.HE(g0);
@@ -334,6 +369,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
     PairResult r;
     r.score = best; r.qle = best_j + 1; r.tle = best_i + 1;
     r.gtle = g_i + 1; r.gscore = gsc; r.max_off = off;
+    r.cells = cells;
     return r;
 }
 
@@ -342,7 +378,7 @@ __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const Pa
     union { PairOut o; uint4 v; } u;
     u.o.score = (int16_t)r.score; u.o.qle = (int16_t)r.qle; u.o.tle = (int16_t)r.tle;
     u.o.gtle = (int16_t)r.gtle; u.o.gscore = (int16_t)r.gscore; u.o.max_off = (int16_t)r.max_off;
-    u.o.pad0 = 0; u.o.pad1 = 0;
+    u.o.cells = r.cells;
     reinterpret_cast<uint4 *>(out)[id] = u.v;
 }
 
@@ -352,7 +388,7 @@ __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const Pa
 //   meta[k] for k in [first, first+n) (sorted), blob = packed sequences; the blobs of one block are
 //   contiguous and start 16-byte aligned (host guarantees), so the block copies them with uint4 loads.
 // ---------------------------------------------------------------------------------------------
-template <bool MATCH1, bool SYM>
+template <bool MATCH1, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
                  PairOut *__restrict__ out, int n, KParams P, int row_words, int qs_words,
@@ -401,7 +437,7 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     __syncthreads();  // staging (aliased by the rows) is dead from here on
     if (!active) return;
 
-    PairResult r = extend_pair<MATCH1, SYM>(R, m.len2, m.len1, m.h0, P);
+    PairResult r = extend_pair<MATCH1, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
     store_result(out, m.id, r);
 }
 
@@ -411,7 +447,7 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
 //   scratch layout: he[row_words][nthreads] (uint2) | qs[qs_words][nthreads] (u16, padded to 4 B)
 //                   | tg[tg_words][nthreads] (u32)
 // ---------------------------------------------------------------------------------------------
-template <bool MATCH1, bool SYM>
+template <bool MATCH1, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
                 PairOut *__restrict__ out, int n, KParams P, int row_words, int qs_words,
@@ -429,7 +465,7 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     p += (((size_t)2 * qs_words * nthreads) + 15) & ~(size_t)15;
     R.tg = reinterpret_cast<uint32_t *>(p) + k;
     unpack_pair((m.flags & 1) ? blob + blob[m.off] : blob + m.off, m.len2, m.len1, m.flags & 1, R);
-    PairResult r = extend_pair<MATCH1, SYM>(R, m.len2, m.len1, m.h0, P);
+    PairResult r = extend_pair<MATCH1, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
     store_result(out, m.id, r);
 }
 

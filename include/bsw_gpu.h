@@ -66,6 +66,10 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
                   int64_t n, int32_t w);
 int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms);
 int bsw_gpu_fetch_staged(bsw_handle *h, bsw_seqpair *pairs, int64_t n);
+/* Unit of work of the GCUPS metric for the staged batch: the number of DP cells the reference's
+ * scalar loop visits (bandedSWA.cpp:191-216, the commented SW_cells++ at :215), counted on the device
+ * by a COUNT variant of the kernel that tracks the reference's exact beg/end. Not for timed regions. */
+int bsw_gpu_count_staged(bsw_handle *h, int64_t *cells_visited);
 
 typedef struct bsw_gpu_stats {
     int64_t pairs;              /* pairs processed by the last batch / staged run */

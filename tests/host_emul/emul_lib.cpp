@@ -12,7 +12,8 @@ using namespace bswk;
 
 extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
                               const uint8_t *qer, int64_t n, int32_t w) {
-    KParams K{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w};
+    KParams K{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w,
+              max_score_of(p->match, p->mismatch, p->ambig)};
     const bool m1 = p->match == 1, sym = p->o_del == p->o_ins && p->e_del == p->e_ins;
 #pragma omp parallel
     {
@@ -40,12 +41,13 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
             Rows R{he.data(), qs.data(), tg.data(), 1};
             unpack_pair(blob.data(), sp.len2, sp.len1, wide, R);
             PairResult r;
-            if (m1) r = sym ? extend_pair<true, true>(R, sp.len2, sp.len1, sp.h0, K)
-                            : extend_pair<true, false>(R, sp.len2, sp.len1, sp.h0, K);
-            else r = sym ? extend_pair<false, true>(R, sp.len2, sp.len1, sp.h0, K)
-                         : extend_pair<false, false>(R, sp.len2, sp.len1, sp.h0, K);
+            if (m1) r = sym ? extend_pair<true, true, true>(R, sp.len2, sp.len1, sp.h0, K)
+                            : extend_pair<true, false, true>(R, sp.len2, sp.len1, sp.h0, K);
+            else r = sym ? extend_pair<false, true, true>(R, sp.len2, sp.len1, sp.h0, K)
+                         : extend_pair<false, false, true>(R, sp.len2, sp.len1, sp.h0, K);
             sp.score = r.score; sp.qle = r.qle; sp.tle = r.tle; sp.gtle = r.gtle;
             sp.gscore = r.gscore; sp.max_off = r.max_off;
+            sp.seqid = (int32_t)r.cells;   // test hook: cell count of the COUNT variant
         }
     }
     return 0;

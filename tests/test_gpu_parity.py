@@ -1,0 +1,147 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libbsw_gpu.so), against the golden
+vectors (reference outputs) and the oracle. Bit-exact on all six outputs. Run with -m gpu on a B200."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN_NAMES, assert_same_outputs, load_golden
+from genarchbench_b200 import bsw, pairio
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_gpu_matches_golden(name):
+    b, w, params, want = load_golden(name)
+    with bsw.BswGpu(**params) as g:
+        g.batch(b.pairs, b.ref, b.qer, w)
+    assert_same_outputs(b.outputs(), want, b, f"GPU vs golden[{name}]")
+
+
+# BASELINE.json configs 1, 2 and 4 at parity-test sizes (the oracle finishes in seconds)
+@pytest.mark.parametrize("config_id,n", [(1, 100000), (2, 100000), (4, 30000)])
+def test_gpu_matches_oracle_on_baseline_configs(gpu, config_id, n):
+    b = pairio.generate(config_id, n)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    gpu.batch(b.pairs, b.ref, b.qer, 100)
+    assert_same_outputs(b.outputs(), a.outputs(), b, f"GPU vs oracle, config {config_id}")
+    st = gpu.stats()
+    assert st["kernel_launches"] > 0 and st["pairs"] == n
+    if config_id == 2:
+        assert (a.outputs()[:, 0] > 127).mean() > 0.9      # the path int8 lanes could not hold
+
+
+def test_reference_interface_mirror():
+    """Reads like the reference driver: construct once, getScores16 per batch (main_banded.cpp:271-276,345)."""
+    b = pairio.generate(1, 5000, seed=31)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    sw = bsw.BandedPairWiseSW(6, 1, 6, 1, 100, 5, None, 1, 4, 1)
+    for lo in range(0, len(b), 512):                          # -b 512 as in regression_small.sh
+        part = b.pairs[lo:lo + 512]
+        sw.getScores16(part, b.ref, b.qer, len(part), 1, 100)
+    sw.close()
+    assert_same_outputs(b.outputs(), a.outputs(), b, "mirror class, 512-pair batches")
+
+
+@pytest.mark.parametrize("w", [1, 3, 10, 30, 200])
+def test_band_widths(gpu, w):
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 300, 0, 80, 0.3, 0.2
+    b = pairio.generate(c, 20000, seed=500 + w)
+    a = b.copy()
+    oracle.oracle_batch(a, w=w)
+    gpu.batch(b.pairs, b.ref, b.qer, w)
+    assert_same_outputs(b.outputs(), a.outputs(), b, f"w={w}")
+
+
+def test_empty_single_and_ragged(gpu):
+    e = pairio.from_sequences([([0], [0], 1)])
+    gpu.batch(e.pairs[:0], e.ref, e.qer, 100)                  # n = 0 is a no-op
+    gpu.batch(e.pairs, e.ref, e.qer, 100)
+    assert e.outputs()[0].tolist() == [2, 1, 1, 1, 2, 0]
+    rng = np.random.default_rng(3)
+    items = [(rng.integers(0, 5, l1).astype(np.uint8), rng.integers(0, 5, l2).astype(np.uint8), h0)
+             for l1, l2, h0 in [(0, 5, 3), (5, 0, 4), (1, 1, 0), (1, 900, 50), (900, 1, 50), (3, 2, 127),
+                                (129, 128, 60), (128, 127, 60), (2000, 1500, 200), (31, 32, 9), (33, 31, 9)]]
+    b = pairio.from_sequences(items)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    gpu.batch(b.pairs, b.ref, b.qer, 100)
+    assert_same_outputs(b.outputs(), a.outputs(), b, "ragged")
+
+
+def test_untouched_fields_and_padding(gpu):
+    """Only the six outputs of entries < n are written (the reference also clobbers n..round)."""
+    b = pairio.generate(1, 1000, seed=8)
+    before = b.pairs.copy()
+    gpu.batch(b.pairs, b.ref, b.qer, 100, n=900)
+    for f in ("idr", "idq", "id", "len1", "len2", "h0", "seqid", "regid"):
+        assert (b.pairs[f] == before[f]).all()
+    assert (b.pairs["score"][900:] == -1).all() and (b.pairs["score"][:900] >= 0).all()
+
+
+def test_out_of_domain_is_rejected(gpu):
+    b = pairio.from_sequences([([0, 1], [0, 1], 32767)])       # h0 + len2*match overflows int16
+    with pytest.raises(bsw.BswError) as e:
+        gpu.batch(b.pairs, b.ref, b.qer, 100)
+    assert e.value.code == 5 and (b.pairs["score"] == -1).all()
+
+
+def test_staged_api_matches_batch(gpu):
+    b = pairio.generate(1, 200000, seed=17)
+    s = b.copy()
+    gpu.batch(b.pairs, b.ref, b.qer, 100)
+    gpu.stage(s.pairs, s.ref, s.qer, 100)
+    ms = gpu.run_staged()
+    ms2 = gpu.run_staged()                                     # re-runnable on resident data
+    assert ms > 0 and ms2 > 0
+    gpu.fetch_staged(s.pairs)
+    assert (b.outputs() == s.outputs()).all()
+
+
+@pytest.mark.parametrize("config_id,n,w", [(1, 50000, 100), (2, 10000, 100), (4, 10000, 100), (4, 10000, 7)])
+def test_cell_count_matches_oracle(gpu, config_id, n, w):
+    """The GCUPS unit of work: the COUNT kernel's visited cells == the oracle's inner-loop count."""
+    b = pairio.generate(config_id, n, seed=60 + config_id)
+    a = b.copy()
+    cells = oracle.oracle_batch(a, w=w)
+    gpu.stage(b.pairs, b.ref, b.qer, w)
+    assert gpu.count_staged() == cells
+    gpu.fetch_staged(b.pairs)                                   # the COUNT variant's outputs are exact too
+    assert_same_outputs(b.outputs(), a.outputs(), b, "COUNT kernel outputs")
+
+
+def test_order_and_batching_invariance(gpu):
+    """Per-pair results do not depend on neighbours, order or slab boundaries."""
+    b = pairio.generate(4, 40000, seed=23)
+    gpu.batch(b.pairs, b.ref, b.qer, 100)
+    perm = np.random.default_rng(1).permutation(len(b))
+    p = pairio.PairBatch(b.pairs[perm].copy(), b.ref, b.qer)
+    for f in pairio.OUTPUT_FIELDS:
+        p.pairs[f] = -1
+    gpu.batch(p.pairs, p.ref, p.qer, 100)
+    assert (p.outputs() == b.outputs()[perm]).all()
+
+
+def test_full_size_properties_config3_sample(gpu):
+    """BASELINE config 3 shape at 4M pairs (multi-slab): permutation-invariant checksum, duplicate
+    pairs agree, and a random sample is bit-exact against the oracle."""
+    n = 4_000_000
+    b = pairio.generate(3, n)
+    # duplicate the first 1000 pairs at the end: same inputs, far-apart slabs
+    b.pairs[-1000:] = b.pairs[:1000]
+    gpu.batch(b.pairs, b.ref, b.qer, 100)
+    out = b.outputs()
+    assert (out[-1000:] == out[:1000]).all()
+    idx = np.random.default_rng(2).choice(n, 50000, replace=False)
+    samp = pairio.PairBatch(b.pairs[idx].copy(), b.ref, b.qer)
+    oracle.oracle_batch(samp)
+    assert_same_outputs(out[idx], samp.outputs(), samp, "4M-pair run, sampled")
+    assert gpu.stats()["pairs"] == n
+
+
+def test_dpx_peak_is_measurable():
+    v = bsw.dpx_peak(0)
+    assert 5e3 < v < 1e5                                        # giga thread-instructions / s

@@ -1,0 +1,48 @@
+"""The product's per-pair device code (genarchbench_b200/csrc/bsw_kernels.cuh: unpack_pair +
+extend_pair) and host packers, compiled for the CPU against an emulation of the CUDA intrinsics
+(tests/host_emul), checked against the golden vectors and the oracle. Catches algorithmic errors
+without a GPU; the GPU parity tests (-m gpu) remain the real gate."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN_NAMES, ROOT, assert_same_outputs, load_golden
+from genarchbench_b200 import pairio
+
+
+@pytest.fixture(scope="module")
+def emul():
+    d = os.path.join(ROOT, "tests", "host_emul")
+    so = os.path.join(d, "libbsw_emul.so")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-fopenmp", "-shared", "-w", f"-I{d}",
+                    f"-I{ROOT}/genarchbench_b200/csrc", f"-I{ROOT}/include", "-o", so,
+                    os.path.join(d, "emul_lib.cpp")], check=True)
+    L = C.CDLL(so)
+    L.bsw_emul_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+
+    def run(b, w=100, params=None):
+        L.bsw_emul_batch(oracle._params_array(params), b.pairs.ctypes.data, b.ref.ctypes.data,
+                         b.qer.ctypes.data, len(b), w)
+        return b.outputs()
+    return run
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_device_code_matches_golden(emul, name):
+    b, w, params, want = load_golden(name)
+    assert_same_outputs(emul(b, w, params), want, b, f"emulated kernel vs golden[{name}]")
+
+
+@pytest.mark.parametrize("w", [1, 2, 5, 17, 100])
+def test_device_code_matches_oracle_on_small_bands(emul, w):
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 200, 0, 60, 0.3, 0.2
+    b = pairio.generate(c, 6000, seed=300 + w)
+    a = b.copy()
+    oracle.oracle_batch(a, w=w)
+    assert_same_outputs(emul(b, w), a.outputs(), b, f"emulated kernel vs oracle, w={w}")

@@ -1,0 +1,56 @@
+"""Pair generator and the reference's 3-line text pair format (main_banded.cpp:152-206)."""
+import numpy as np
+
+from genarchbench_b200 import pairio
+
+
+def test_generator_is_deterministic_and_thread_independent():
+    a = pairio.generate(1, 20000, nthreads=1)
+    b = pairio.generate(1, 20000, nthreads=7)
+    assert (a.pairs == b.pairs).all() and (a.ref == b.ref).all() and (a.qer == b.qer).all()
+    c = pairio.generate(1, 20000, seed=1)
+    assert not (a.pairs["len2"] == c.pairs["len2"]).all()
+
+
+def test_preset_shapes():
+    c1 = pairio.generate(1, 50000)
+    assert c1.pairs["len2"].min() >= 1 and c1.pairs["len2"].max() <= 132
+    assert (c1.pairs["len1"] == c1.pairs["len2"] + np.minimum(np.maximum(c1.pairs["len2"] - 5, 1), 200)).all()
+    h0 = c1.pairs["h0"]
+    assert ((h0 >= 19) & (h0 <= 120) | (h0 <= 1)).all()
+    c2 = pairio.generate(2, 5000)
+    assert c2.pairs["len2"].min() >= 250 and c2.pairs["len2"].max() <= 300
+    c4 = pairio.generate(4, 20000)
+    assert c4.pairs["len2"].min() >= 30 and c4.pairs["len2"].max() <= 1000
+    assert ((c4.pairs["len1"] - c4.pairs["len2"]) <= 200).all()
+    # ambiguous bases present but rare; only codes 0..4
+    assert c1.ref.max() <= 4 and c1.qer.max() <= 4
+    n_amb = sum(int((c1.ref[p["idr"]:p["idr"] + p["len1"]] == 4).any() or
+                    (c1.qer[p["idq"]:p["idq"] + p["len2"]] == 4).any()) for p in c1.pairs[:5000])
+    assert 30 < n_amb < 200
+
+
+def test_text_roundtrip(tmp_path):
+    b = pairio.generate(4, 300, seed=3)
+    path = str(tmp_path / "pairs.txt")
+    pairio.write_text(path, b)
+    with open(path) as f:
+        lines = f.read().split("\n")
+    assert len(lines) == 3 * len(b) + 1 and set("".join(lines[1:3])) <= set("01234")
+    r = pairio.read_text(path)
+    assert len(r) == len(b)
+    for f in ("len1", "len2", "h0"):
+        assert (r.pairs[f] == b.pairs[f]).all()
+    for k in (0, 17, len(b) - 1):
+        p, q = b.pairs[k], r.pairs[k]
+        assert (b.ref[p["idr"]:p["idr"] + p["len1"]] == r.ref[q["idr"]:q["idr"] + q["len1"]]).all()
+        assert (b.qer[p["idq"]:p["idq"] + p["len2"]] == r.qer[q["idq"]:q["idq"] + q["len2"]]).all()
+    assert (r.pairs["score"] == -1).all()   # outputs initialised like loadPairs (main_banded.cpp:200-201)
+
+
+def test_seqpair_layout_matches_reference_struct():
+    d = pairio.SEQPAIR_DTYPE
+    assert d.itemsize == 72
+    want = dict(idr=0, idq=8, id=16, len1=24, len2=28, h0=32, seqid=36, regid=40, score=44, tle=48,
+                gtle=52, qle=56, gscore=60, max_off=64)     # SURVEY 8a row 1 (offsetof-verified)
+    assert {k: d.fields[k][1] for k in want} == want
