@@ -284,7 +284,7 @@ def main():
         "e2e": {"value": sum_cells / e2e_step_s / 1e9, "unit": "GCUPS",
                 "pairs_per_s": sum_pairs / e2e_step_s, "ms_per_step": e2e_step_s * 1e3, "steps": e2e_steps,
                 "h2d_bytes_per_step": int(sum_h2d / e2e_steps), "d2h_bytes_per_step": int(sum_d2h / e2e_steps),
-                "host_pack_ms": last["host_pack_ms"], "host_scatter_ms": last["host_scatter_ms"],
+                "host_ms": {k[5:-3]: round(last[k], 3) for k in last if k.startswith("host_")},
                 "kernel_ms": last["kernel_ms"], "host_threads": int(os.environ["OMP_NUM_THREADS"]),
                 "api": "bsw_gpu_batch(SeqPair*, ref, qer, n, w) from host buffers", "results_written": checksum_ok},
         "gpu_launches": int(sum_launch),

@@ -76,10 +76,16 @@ struct Slab {
     bool pinned = true;      // false for staged slabs (host side borrowed)
 };
 
+constexpr int kAux = 4;   // launch streams per GPU: length bins of a slab run concurrently
+
 struct Device {
     int id = 0;
     Slab ring[kRing];
     std::vector<Slab *> staged;  // device-resident slabs of the staged API
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t aux_ev[kAux] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr;
+    bool attr_set[2][2][2] = {{{false, false}, {false, false}}, {{false, false}, {false, false}}};
 };
 
 }  // namespace
@@ -97,7 +103,10 @@ struct bsw_handle {
     // host scratch reused across slabs
     std::vector<uint32_t> key, ord_a, ord_b;
     std::vector<uint32_t> sizes;
-    std::vector<uint64_t> offs;
+    std::vector<uint32_t> offs;      // slot offsets of the sorted pairs, in 4-byte words
+    std::vector<int16_t> h0s;
+    std::vector<uint8_t> flags;
+    std::vector<uint32_t> chunk_off, binmax;
 };
 
 namespace {
@@ -203,132 +212,119 @@ void counting_sort(const std::vector<uint32_t> &key_of, const uint32_t *in, uint
     }
 }
 
-// Validates, bins, sorts and packs slab [lo, lo+n) of the caller's arrays into s (host side).
+// Validates, packs, bins and sorts slab [lo, lo+n) of the caller's arrays into s (host side).
+//   pass A  (parallel, reads the SeqPair records once): validate, pull out len2 / len1 / h0, size
+//           every chunk of kChunk pairs;
+//   pass B  (parallel over chunks, streaming): 2-bit pack each pair's query and target, in the
+//           CALLER's order, into a 16-byte aligned slot of the pinned blob; pairs holding an ambiguous
+//           base are also packed 4 bits per base into a per-thread overflow buffer;
+//   sort    two stable counting sorts of the pair indices (len1, then len2, descending);
+//   pass C  (parallel, sorted order): gather the 16-byte PairMeta records;
+//   plan    one launch per query-length bin, from the len2 histogram.
 int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t *ref,
                  const uint8_t *qer, int64_t lo, int n) {
+    constexpr int kChunk = 4096;
     const bsw_seqpair *pp = pairs + lo;
+    bsw_gpu_stats &st = h->stats;
     s.lo = lo; s.n = n;
     s.launches.clear();
     s.trivial.clear();
+    auto t0 = Clock::now();
 
-    // 1. validate + keys
-    int bad = 0, maxq = 0, maxt = 0;
+    // ---- pass A
+    const int nchunks = (n + kChunk - 1) / kChunk;
+    int bad = 0, maxq = 0, maxt = 0, ntriv = 0;
     h->key.resize((size_t)n);      // len2
     h->sizes.resize((size_t)n);    // len1
-#pragma omp parallel for reduction(| : bad) reduction(max : maxq) reduction(max : maxt) schedule(static)
-    for (int k = 0; k < n; ++k) {
-        const bsw_seqpair &p = pp[k];
-        if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN ||
-            p.h0 < 0 || (int64_t)p.h0 + (int64_t)p.len2 * h->P.match > 32767)
-            bad |= 1;
-        h->key[(size_t)k] = (uint32_t)std::max(p.len2, 0);
-        h->sizes[(size_t)k] = (uint32_t)std::max(p.len1, 0);
-        maxq = std::max(maxq, p.len2);
-        maxt = std::max(maxt, p.len1);
-    }
-    if (bad) return BSW_ERR_RANGE;
-
-    // 2. order: empty pairs out, then stable sort by len1 then len2, both descending, so that a
-    //    warp holds pairs of equal query length and near-equal target length, heavy bins first.
+    h->h0s.resize((size_t)n);
     h->ord_a.resize((size_t)n);
     h->ord_b.resize((size_t)n);
-    int nd = 0;
-    for (int k = 0; k < n; ++k) {
-        if (pp[k].len1 == 0 || pp[k].len2 == 0) s.trivial.push_back((uint32_t)k);
-        else h->ord_a[(size_t)nd++] = (uint32_t)k;
-    }
-    s.n_dev = nd;
-    if (nd == 0) { s.blob_bytes = 0; return BSW_OK; }
-    counting_sort(h->sizes, h->ord_a.data(), h->ord_b.data(), nd, maxt + 1, true);
-    counting_sort(h->key, h->ord_b.data(), h->ord_a.data(), nd, maxq + 1, true);
-    const uint32_t *ord = h->ord_a.data();
-
-    // 3. launches: contiguous ranges of the sorted order sharing a query-length bin
-    {
-        int p = 0;
-        while (p < nd) {
-            const int q_hi = (int)h->key[ord[p]];
-            const int bin_lo = ((q_hi - 1) / kBinCols) * kBinCols;  // this launch takes len2 in (bin_lo, q_hi]
-            int e = p;
-            int t_hi = 0;
-            int64_t work = 0;
-            while (e < nd && (int)h->key[ord[e]] > bin_lo) {
-                t_hi = std::max(t_hi, (int)h->sizes[ord[e]]);
-                work += (int64_t)h->key[ord[e]] * h->sizes[ord[e]];
-                ++e;
+    h->chunk_off.resize((size_t)nchunks + 1);
+    const int match = h->P.match;
+#pragma omp parallel for reduction(| : bad) reduction(max : maxq) reduction(max : maxt) reduction(+ : ntriv) schedule(static)
+    for (int c = 0; c < nchunks; ++c) {
+        const int hi = std::min(n, (c + 1) * kChunk);
+        uint32_t words = 0;
+        for (int k = c * kChunk; k < hi; ++k) {
+            const bsw_seqpair &p = pp[k];
+            if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN ||
+                p.h0 < 0 || (int64_t)p.h0 + (int64_t)p.len2 * match > 32767) {
+                bad |= 1;
+                continue;
             }
-            Launch L;
-            L.first = p; L.n = e - p; L.work = work;
-            L.row_words = ((q_hi + 1) >> 1) + 1;
-            L.qs_words = (q_hi + 1) >> 1;
-            L.tg_words = (t_hi + 7) >> 3;
-            // staging: a block's narrow blobs, rounded up to 16 bytes
-            L.stage_bytes = (int)(((size_t)kBlockPairs * (seq_bytes(q_hi, false) + seq_bytes(t_hi, false)) + 15) & ~(size_t)15) + 16;
-            L.smem = smem_need(L.row_words, L.qs_words, L.tg_words, L.stage_bytes);
-            if (L.smem > kMaxSmem) L.smem = 0;  // long kernel
-            s.launches.push_back(L);
-            p = e;
+            h->key[(size_t)k] = (uint32_t)p.len2;
+            h->sizes[(size_t)k] = (uint32_t)p.len1;
+            h->h0s[(size_t)k] = (int16_t)p.h0;
+            h->ord_a[(size_t)k] = (uint32_t)k;
+            maxq = std::max(maxq, p.len2);
+            maxt = std::max(maxt, p.len1);
+            ntriv += (p.len1 == 0 || p.len2 == 0);
+            words += slot_words((uint32_t)p.len2, (uint32_t)p.len1);
         }
+        h->chunk_off[(size_t)c + 1] = words;
     }
-
-    // 4. blob offsets (narrow slots; every block of every launch starts 16-byte aligned)
-    h->offs.resize((size_t)nd + 1);
+    if (bad) return BSW_ERR_RANGE;
     {
         uint64_t run = 0;
-        for (const Launch &L : s.launches) {
-            for (int b = 0; b < L.n; ++b) {
-                if ((b % kBlockPairs) == 0) run = (run + 15) & ~(uint64_t)15;
-                const uint32_t k = ord[L.first + b];
-                h->offs[(size_t)(L.first + b)] = run;
-                run += slot_bytes(h->key[k], h->sizes[k]);
-            }
+        h->chunk_off[0] = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            run += h->chunk_off[(size_t)c + 1];
+            if (run > 0xFFFFFF00ull) return BSW_ERR_RANGE;   // slab blobs are addressed in 32-bit words
+            h->chunk_off[(size_t)c + 1] = (uint32_t)run;
         }
-        run = (run + 15) & ~(uint64_t)15;
-        h->offs[(size_t)nd] = run;
     }
-    const uint64_t narrow_bytes = h->offs[(size_t)nd];
-    // worst case every pair is wide; the overflow area follows the narrow slots. Allocate lazily:
-    // first pass assumes 1/8 of the narrow size (+ slack), grows and repacks if exceeded.
-    int T = omp_get_max_threads();
-    std::vector<std::vector<uint8_t>> wide_buf((size_t)T);
-    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> wide_idx((size_t)T);  // (sorted pos, offset in thread buf)
-
+    const uint64_t narrow_bytes = (uint64_t)h->chunk_off[(size_t)nchunks] * 4;
+    st.host_bin_ms += ms_since(t0);
+    t0 = Clock::now();
     int rc = ensure_slab(h, s, n, (size_t)narrow_bytes + 64);
     if (rc) return rc;
-    uint8_t *blob = reinterpret_cast<uint8_t *>(s.h_blob);
+    st.host_alloc_ms += ms_since(t0);
+    t0 = Clock::now();
 
+    // ---- pass B
+    int T = omp_get_max_threads();
+    std::vector<std::vector<uint8_t>> wide_buf((size_t)T);
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> wide_idx((size_t)T);  // (pair, offset in thread buf)
+    uint8_t *blob = reinterpret_cast<uint8_t *>(s.h_blob);
+    h->offs.resize((size_t)n);
+    h->flags.assign((size_t)n, 0);
 #pragma omp parallel num_threads(T)
     {
         int t = omp_get_thread_num();
         std::vector<uint8_t> &wb = wide_buf[(size_t)t];
         auto &wi = wide_idx[(size_t)t];
-#pragma omp for schedule(dynamic, 2048)
-        for (int p = 0; p < nd; ++p) {
-            const uint32_t k = ord[p];
-            const bsw_seqpair &sp = pp[k];
-            uint8_t *dst = blob + h->offs[(size_t)p];
-            const uint32_t qb = seq_bytes((uint32_t)sp.len2, false);
-            bool w1 = pack2bit(qer + sp.idq, sp.len2, dst);
-            bool w2 = pack2bit(ref + sp.idr, sp.len1, dst + qb);
-            PairMeta &m = s.h_meta[p];
-            m.off = (uint32_t)(h->offs[(size_t)p] >> 2);
-            m.id = k;
-            m.len2 = (uint16_t)sp.len2; m.len1 = (uint16_t)sp.len1;
-            m.h0 = (int16_t)sp.h0;
-            m.flags = 0;
-            if (w1 || w2) {
-                m.flags = 1;
-                const uint32_t wq = seq_bytes((uint32_t)sp.len2, true), wt = seq_bytes((uint32_t)sp.len1, true);
-                size_t o = wb.size();
-                o = (o + 3) & ~(size_t)3;
-                wb.resize(o + wq + wt);
-                pack4bit(qer + sp.idq, sp.len2, wb.data() + o);
-                pack4bit(ref + sp.idr, sp.len1, wb.data() + o + wq);
-                wi.emplace_back((uint32_t)p, (uint32_t)o);
+#pragma omp for schedule(dynamic, 4)
+        for (int c = 0; c < nchunks; ++c) {
+            const int hi = std::min(n, (c + 1) * kChunk);
+            uint32_t off = h->chunk_off[(size_t)c];
+            for (int k = c * kChunk; k < hi; ++k) {
+                const bsw_seqpair &sp = pp[k];
+                if (k + 4 < hi) {   // the records are read in order; pull the next sequences in early
+                    __builtin_prefetch(qer + pp[k + 4].idq);
+                    __builtin_prefetch(ref + pp[k + 4].idr);
+                    __builtin_prefetch(ref + pp[k + 4].idr + 64);
+                }
+                uint8_t *dst = blob + (size_t)off * 4;
+                const uint32_t qb = seq_bytes((uint32_t)sp.len2, false);
+                const uint32_t sw = slot_words((uint32_t)sp.len2, (uint32_t)sp.len1);
+                bool w1 = pack2bit(qer + sp.idq, sp.len2, dst);
+                bool w2 = pack2bit(ref + sp.idr, sp.len1, dst + qb);
+                h->offs[(size_t)k] = off;
+                if (w1 || w2) {
+                    h->flags[(size_t)k] = 1;
+                    const uint32_t wq = seq_bytes((uint32_t)sp.len2, true), wt = seq_bytes((uint32_t)sp.len1, true);
+                    size_t o = (wb.size() + 15) & ~(size_t)15;
+                    wb.resize(o + wq + wt);
+                    pack4bit(qer + sp.idq, sp.len2, wb.data() + o);
+                    pack4bit(ref + sp.idr, sp.len1, wb.data() + o + wq);
+                    wi.emplace_back((uint32_t)k, (uint32_t)o);
+                }
+                off += sw;
             }
         }
     }
-    // overflow area
+    // overflow area: per-thread buffers appended after the slots; a wide pair's slot keeps only the
+    // word offset of its 4-bit blob
     uint64_t wide_total = 0;
     std::vector<uint64_t> wbase((size_t)T);
     for (int t = 0; t < T; ++t) {
@@ -336,11 +332,10 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
         wide_total += (wide_buf[(size_t)t].size() + 15) & ~(size_t)15;
     }
     s.blob_bytes = (size_t)(narrow_bytes + wide_total + 16);
-    if (s.blob_bytes > (size_t)0xFFFFFFFFull * 4) return BSW_ERR_RANGE;
+    if (s.blob_bytes > (size_t)0xFFFFFF00ull * 4) return BSW_ERR_RANGE;
     if (wide_total) {
         if (s.blob_bytes + 64 > s.cap_blob) {
-            // grow, keeping the narrow part
-            std::vector<uint8_t> keep(blob, blob + narrow_bytes);
+            std::vector<uint8_t> keep(blob, blob + narrow_bytes);   // grow, keeping the slots
             rc = ensure_slab(h, s, n, s.blob_bytes + 64 + (s.blob_bytes >> 2));
             if (rc) return rc;
             blob = reinterpret_cast<uint8_t *>(s.h_blob);
@@ -350,57 +345,160 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             if (wide_buf[(size_t)t].empty()) continue;
             memcpy(blob + wbase[(size_t)t], wide_buf[(size_t)t].data(), wide_buf[(size_t)t].size());
             for (auto &pr : wide_idx[(size_t)t]) {
-                // a wide pair keeps its narrow slot; the slot's first word points at the wide blob
                 uint32_t woff = (uint32_t)((wbase[(size_t)t] + pr.second) >> 2);
-                memcpy(blob + h->offs[(size_t)pr.first], &woff, 4);
+                memcpy(blob + (size_t)h->offs[(size_t)pr.first] * 4, &woff, 4);
             }
         }
     }
     memset(blob + s.blob_bytes - 16, 0, 16);
+    st.host_pack_ms += ms_since(t0);
+    t0 = Clock::now();
+
+    // ---- sort (pairs with an empty sequence are answered on the host and left out)
+    int nd = n;
+    if (ntriv) {
+        nd = 0;
+        for (int k = 0; k < n; ++k) {
+            if (pp[k].len1 == 0 || pp[k].len2 == 0) s.trivial.push_back((uint32_t)k);
+            else h->ord_a[(size_t)nd++] = (uint32_t)k;
+        }
+    }
+    s.n_dev = nd;
+    if (nd == 0) return BSW_OK;
+    counting_sort(h->sizes, h->ord_a.data(), h->ord_b.data(), nd, maxt + 1, true);
+    counting_sort(h->key, h->ord_b.data(), h->ord_a.data(), nd, maxq + 1, true);
+    const uint32_t *ord = h->ord_a.data();
+    st.host_sort_ms += ms_since(t0);
+    t0 = Clock::now();
+
+    // ---- pass C + plan. The sorted order is descending in len2, so a launch = the run of positions
+    // whose len2 falls in one kBinCols-wide bin; its geometry needs the largest len2 / len1 in it.
+    h->binmax.assign((size_t)(maxq / kBinCols + 2) * 2, 0);
+    std::vector<uint32_t> &bm = h->binmax;   // per bin: [count, max len1]
+#pragma omp parallel num_threads(T)
+    {
+        std::vector<uint32_t> loc(bm.size(), 0);
+#pragma omp for schedule(static) nowait
+        for (int p = 0; p < nd; ++p) {
+            const uint32_t k = ord[p];
+            PairMeta &m = s.h_meta[p];
+            m.off = h->offs[k];
+            m.id = k;
+            m.len2 = (uint16_t)h->key[k]; m.len1 = (uint16_t)h->sizes[k];
+            m.h0 = h->h0s[k];
+            m.flags = h->flags[k];
+            const size_t b = (size_t)((h->key[k] - 1) / kBinCols) * 2;
+            loc[b] += 1;
+            loc[b + 1] = std::max(loc[b + 1], h->sizes[k]);
+        }
+#pragma omp critical
+        for (size_t i = 0; i < bm.size(); i += 2) { bm[i] += loc[i]; bm[i + 1] = std::max(bm[i + 1], loc[i + 1]); }
+    }
+    {
+        int p = 0;
+        for (int b = maxq / kBinCols + 1; b >= 0; --b) {
+            const int cnt = (int)bm[(size_t)b * 2];
+            if (!cnt) continue;
+            const int q_hi = (int)s.h_meta[p].len2, t_hi = (int)bm[(size_t)b * 2 + 1];
+            Launch L;
+            L.first = p; L.n = cnt; L.work = (int64_t)cnt * q_hi * t_hi;
+            L.row_words = ((q_hi + 1) >> 1) + 1;
+            L.qs_words = (q_hi + 1) >> 1;
+            L.tg_words = (t_hi + 7) >> 3;
+            L.stage_bytes = 0;
+            L.smem = smem_need(L.row_words, L.qs_words, L.tg_words, 0);
+            if (L.smem > kMaxSmem) L.smem = 0;  // long kernel
+            s.launches.push_back(L);
+            p += cnt;
+        }
+    }
+    st.host_plan_ms += ms_since(t0);
     return BSW_OK;
 }
 
 // ---- device side of a slab ---------------------------------------------------------------------
 
+int ensure_aux(bsw_handle *h, Device &dev) {
+    if (dev.aux[0]) return BSW_OK;
+    for (int j = 0; j < kAux; ++j) {
+        CU(cudaStreamCreateWithFlags(&dev.aux[j], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&dev.aux_ev[j], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&dev.fork_ev, cudaEventDisableTiming));
+    return BSW_OK;
+}
+
+// Enqueues every launch of the given slabs: work forks from `main` onto the device's aux streams
+// (bins of different lengths overlap; the few-block long bins no longer leave the GPU idle) and
+// joins back into `main`. Long-kernel launches share a per-slab scratch and stay on aux[0].
 template <bool M1, bool SY, bool CNT>
-int launch_all(bsw_handle *h, Slab &s) {
-    for (const Launch &L : s.launches) {
-        const int grid = (L.n + kBlockPairs - 1) / kBlockPairs;
-        if (L.smem) {
-            auto kern = bsw_short_kernel<M1, SY, CNT>;
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-            kern<<<grid, kBlockPairs, L.smem, s.stream>>>(s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K,
-                                                         L.row_words, L.qs_words, L.tg_words, L.stage_bytes);
-        } else {
-            const size_t nthreads = (size_t)grid * kBlockPairs;
-            size_t need = (size_t)8 * L.row_words * nthreads +
-                          ((((size_t)2 * L.qs_words * nthreads) + 15) & ~(size_t)15) +
-                          (size_t)4 * L.tg_words * nthreads + 256;
-            if (need > s.cap_scratch) {
-                CU(cudaStreamSynchronize(s.stream));
-                if (s.d_scratch) cudaFree(s.d_scratch);
-                s.d_scratch = nullptr; s.cap_scratch = 0;
-                CU(cudaMalloc((void **)&s.d_scratch, need));
-                s.cap_scratch = need;
-            }
-            bsw_long_kernel<M1, SY, CNT><<<grid, kBlockPairs, 0, s.stream>>>(
-                s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K, L.row_words, L.qs_words, L.tg_words,
-                s.d_scratch);
+int launch_all(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs) {
+    int rc = ensure_aux(h, dev);
+    if (rc) return rc;
+    auto kshort = bsw_short_kernel<M1, SY, CNT>;
+    if (!dev.attr_set[M1][SY][CNT]) {
+        CU(cudaFuncSetAttribute(kshort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+        dev.attr_set[M1][SY][CNT] = true;
+    }
+    // scratch for the long kernel, sized once per slab before anything is enqueued
+    for (int i = 0; i < nslabs; ++i) {
+        Slab &s = *slabs[i];
+        size_t need = 0;
+        for (const Launch &L : s.launches) {
+            if (L.smem) continue;
+            const size_t nthreads = (size_t)((L.n + kBlockPairs - 1) / kBlockPairs) * kBlockPairs;
+            need = std::max(need, (size_t)8 * L.row_words * nthreads +
+                                      ((((size_t)2 * L.qs_words * nthreads) + 15) & ~(size_t)15) +
+                                      (size_t)4 * L.tg_words * nthreads + 256);
         }
-        CU(cudaGetLastError());
-        h->stats.kernel_launches++;
-        if (L.smem) h->stats.pairs_short += L.n; else h->stats.pairs_long += L.n;
+        if (need > s.cap_scratch) {
+            CU(cudaDeviceSynchronize());
+            if (s.d_scratch) cudaFree(s.d_scratch);
+            s.d_scratch = nullptr; s.cap_scratch = 0;
+            CU(cudaMalloc((void **)&s.d_scratch, need));
+            s.cap_scratch = need;
+        }
+    }
+    CU(cudaEventRecord(dev.fork_ev, main));
+    for (int j = 0; j < kAux; ++j) CU(cudaStreamWaitEvent(dev.aux[j], dev.fork_ev, 0));
+    int rr = 0;
+    for (int i = 0; i < nslabs; ++i) {
+        Slab &s = *slabs[i];
+        for (const Launch &L : s.launches) {
+            const int grid = (L.n + kBlockPairs - 1) / kBlockPairs;
+            if (L.smem) {
+                cudaStream_t st = dev.aux[rr++ % kAux];
+                kshort<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K,
+                                                         L.row_words, L.qs_words, L.tg_words);
+            } else {
+                bsw_long_kernel<M1, SY, CNT><<<grid, kBlockPairs, 0, dev.aux[0]>>>(
+                    s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K, L.row_words, L.qs_words, L.tg_words,
+                    s.d_scratch);
+            }
+            CU(cudaGetLastError());
+            h->stats.kernel_launches++;
+            if (L.smem) h->stats.pairs_short += L.n; else h->stats.pairs_long += L.n;
+        }
+    }
+    for (int j = 0; j < kAux; ++j) {
+        CU(cudaEventRecord(dev.aux_ev[j], dev.aux[j]));
+        CU(cudaStreamWaitEvent(main, dev.aux_ev[j], 0));
     }
     return BSW_OK;
 }
 
-int launch_slab(bsw_handle *h, Slab &s, bool count = false) {
+int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs, bool count = false) {
     if (count) {
-        if (h->match1) return h->sym ? launch_all<true, true, true>(h, s) : launch_all<true, false, true>(h, s);
-        return h->sym ? launch_all<false, true, true>(h, s) : launch_all<false, false, true>(h, s);
+        if (h->match1) return h->sym ? launch_all<true, true, true>(h, dev, main, slabs, nslabs) : launch_all<true, false, true>(h, dev, main, slabs, nslabs);
+        return h->sym ? launch_all<false, true, true>(h, dev, main, slabs, nslabs) : launch_all<false, false, true>(h, dev, main, slabs, nslabs);
     }
-    if (h->match1) return h->sym ? launch_all<true, true, false>(h, s) : launch_all<true, false, false>(h, s);
-    return h->sym ? launch_all<false, true, false>(h, s) : launch_all<false, false, false>(h, s);
+    if (h->match1) return h->sym ? launch_all<true, true, false>(h, dev, main, slabs, nslabs) : launch_all<true, false, false>(h, dev, main, slabs, nslabs);
+    return h->sym ? launch_all<false, true, false>(h, dev, main, slabs, nslabs) : launch_all<false, false, false>(h, dev, main, slabs, nslabs);
+}
+
+int launch_slab(bsw_handle *h, Device &dev, Slab &s, bool count = false) {
+    Slab *one = &s;
+    return launch_slabs(h, dev, s.stream, &one, 1, count);
 }
 
 // long launches of one slab must not share the scratch concurrently: they are on one stream -> serial.
@@ -439,17 +537,29 @@ void scatter_slab(bsw_handle *h, const Slab &s, const PairOut *out, bsw_seqpair 
     (void)h;
 }
 
-// slab boundaries over [0, n): by pair count and by bases
+// slab boundaries over [0, n): by pair count and by bases, at a granularity of 64 Ki pairs
 void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts) {
+    constexpr int64_t G = 1 << 16;
+    const int64_t ng = (n + G - 1) / G;
+    std::vector<int64_t> bases((size_t)ng, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < ng; ++c) {
+        int64_t b = 0;
+        const int64_t hi = std::min(n, (c + 1) * G);
+        for (int64_t k = c * G; k < hi; ++k)
+            b += (int64_t)std::max(pairs[k].len1, 0) + std::max(pairs[k].len2, 0);
+        bases[(size_t)c] = b;
+    }
     cuts.clear();
     cuts.push_back(0);
-    int64_t bases = 0, cnt = 0;
-    for (int64_t k = 0; k < n; ++k) {
-        bases += (int64_t)std::max(pairs[k].len1, 0) + std::max(pairs[k].len2, 0);
-        ++cnt;
-        if (cnt >= kSlabPairs || bases >= kSlabBases) {
-            cuts.push_back(k + 1);
-            bases = 0; cnt = 0;
+    int64_t acc = 0, cnt = 0;
+    for (int64_t c = 0; c < ng; ++c) {
+        const int64_t hi = std::min(n, (c + 1) * G);
+        acc += bases[(size_t)c];
+        cnt += hi - c * G;
+        if (cnt >= kSlabPairs || acc >= kSlabBases) {
+            cuts.push_back(hi);
+            acc = 0; cnt = 0;
         }
     }
     if (cuts.back() != n) cuts.push_back(n);
@@ -457,7 +567,11 @@ void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts) 
 
 int finish_slab(bsw_handle *h, Slab &s, bsw_seqpair *pairs, double *kernel_ms_acc) {
     if (!s.busy) return BSW_OK;
-    CU(cudaEventSynchronize(s.ev_done));
+    {
+        auto tw = Clock::now();
+        CU(cudaEventSynchronize(s.ev_done));
+        h->stats.host_wait_ms += ms_since(tw);
+    }
     if (s.n_dev) {
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
@@ -571,6 +685,11 @@ void bsw_gpu_free(bsw_handle *h) {
         cudaSetDevice(d.id);
         for (Slab &s : d.ring) free_slab(s);
         for (Slab *s : d.staged) { free_slab(*s); delete s; }
+        for (int j = 0; j < kAux; ++j) {
+            if (d.aux[j]) cudaStreamDestroy(d.aux[j]);
+            if (d.aux_ev[j]) cudaEventDestroy(d.aux_ev[j]);
+        }
+        if (d.fork_ev) cudaEventDestroy(d.fork_ev);
     }
     delete h;
 }
@@ -590,11 +709,16 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
     st.pairs = n; st.kernel_launches = 0; st.h2d_bytes = 0; st.d2h_bytes = 0;
     st.pairs_short = 0; st.pairs_long = 0;
     st.host_bin_ms = st.host_pack_ms = st.host_scatter_ms = st.kernel_ms = 0;
+    st.host_sort_ms = st.host_plan_ms = st.host_alloc_ms = st.host_cut_ms = st.host_wait_ms = 0;
     h->K.w = w;
     if (n == 0) { st.wall_ms = 0; return BSW_OK; }
 
     std::vector<int64_t> cuts;
-    cut_slabs(pairs, n, cuts);
+    {
+        auto t0 = Clock::now();
+        cut_slabs(pairs, n, cuts);
+        st.host_cut_ms = ms_since(t0);
+    }
     const int nslabs = (int)cuts.size() - 1;
     std::vector<double> kms((size_t)ng, 0.0);
     int rc = BSW_OK;
@@ -606,14 +730,12 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
         CU(cudaSetDevice(dev.id));
         rc = finish_slab(h, s, pairs, &kms[(size_t)d]);  // ring slot still owns an older slab
         if (rc) break;
-        auto t0 = Clock::now();
         rc = prepare_slab(h, s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]));
-        st.host_pack_ms += ms_since(t0);
         if (rc) break;
         if (s.n_dev) {
             if ((rc = upload_slab(h, s))) break;
             CU(cudaEventRecord(s.ev_k0, s.stream));
-            if ((rc = launch_slab(h, s))) break;
+            if ((rc = launch_slab(h, dev, s))) break;
             CU(cudaEventRecord(s.ev_k1, s.stream));
             if ((rc = download_slab(h, s))) break;
         }
@@ -677,11 +799,10 @@ int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms) {
         CU(cudaSetDevice(dev.id));
         cudaStream_t st0 = dev.staged[0]->stream;
         CU(cudaEventRecord(dev.staged[0]->ev_k0, st0));
-        for (Slab *s : dev.staged) {
-            cudaStream_t keep = s->stream;
-            s->stream = st0;
-            int rc = s->n_dev ? launch_slab(h, *s) : BSW_OK;
-            s->stream = keep;
+        std::vector<Slab *> live;
+        for (Slab *s : dev.staged) if (s->n_dev) live.push_back(s);
+        if (!live.empty()) {
+            int rc = launch_slabs(h, dev, st0, live.data(), (int)live.size());
             if (rc) return rc;
         }
         CU(cudaEventRecord(dev.staged[0]->ev_k1, st0));
@@ -709,7 +830,7 @@ int bsw_gpu_count_staged(bsw_handle *h, int64_t *cells_visited) {
         CU(cudaSetDevice(dev.id));
         for (Slab *s : dev.staged) {
             if (!s->n_dev) continue;
-            int rc = launch_slab(h, *s, true);
+            int rc = launch_slab(h, dev, *s, true);
             if (rc) return rc;
             if ((rc = download_slab(h, *s))) return rc;
             CU(cudaStreamSynchronize(s->stream));

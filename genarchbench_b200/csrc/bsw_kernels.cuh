@@ -18,8 +18,8 @@
 //      H  = max(M, E, F)               VIMNMX3.S16x2
 //    substitution scores for both lanes come from ONE PRMT that indexes an 8-byte LUT with the
 //    per-lane (query ^ target) code (ambiguous base folded in through an OR on bit 2).
-//  * packed sequences (2-bit, or 4-bit when a pair holds an ambiguous base) are copied block-wide
-//    with coalesced 128-bit loads into shared memory and expanded there once per pair.
+//  * packed sequences (2-bit, or 4-bit when a pair holds an ambiguous base) sit in 16-byte aligned
+//    slots in the caller's order; each thread expands its own slot into shared memory once per pair.
 #pragma once
 #include <stdint.h>
 #ifdef BSW_HOST_EMUL
@@ -69,10 +69,10 @@ __host__ __device__ inline uint32_t seq_bytes(uint32_t len, bool wide) {
     return (b + 3u) & ~3u;  // each sequence padded to 4 bytes
 }
 
-// bytes a pair occupies in the (2-bit) slot area: query then target, at least 8
-__host__ __device__ inline uint32_t slot_bytes(uint32_t len2, uint32_t len1) {
+// 4-byte words a pair occupies in the (2-bit) slot area: query then target, 16-byte aligned
+__host__ __device__ inline uint32_t slot_words(uint32_t len2, uint32_t len1) {
     uint32_t b = seq_bytes(len2, false) + seq_bytes(len1, false);
-    return b < 8u ? 8u : b;
+    return ((b + 15u) & ~15u) >> 2;
 }
 
 __device__ __forceinline__ uint32_t pack2(int v) {
@@ -384,58 +384,35 @@ __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const Pa
 
 // ---------------------------------------------------------------------------------------------
 // Short pairs: rows in shared memory. Launch: grid = ceil(n / kBlockPairs), block = kBlockPairs,
-// dynamic smem = max(stage_bytes, 8*row_words*NT) + 2*qs_words*NT + 4*tg_words*NT.
-//   meta[k] for k in [first, first+n) (sorted), blob = packed sequences; the blobs of one block are
-//   contiguous and start 16-byte aligned (host guarantees), so the block copies them with uint4 loads.
+// dynamic smem = (8*row_words + 2*qs_words + 4*tg_words) * NT.
+//   meta[k] for k in [0, n): this launch's pairs in sorted (length-binned) order; blob = the slab's
+//   packed sequences. Each thread expands its own 16-byte aligned slot straight from global memory
+//   (a few dozen bytes per pair, read once; the host packs slots in the caller's order so that its
+//   own pass is a pure stream -- see DESIGN.md).
 // ---------------------------------------------------------------------------------------------
 template <bool MATCH1, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
                  PairOut *__restrict__ out, int n, KParams P, int row_words, int qs_words,
-                 int tg_words, int stage_bytes) {
+                 int tg_words) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NT = kBlockPairs;
     const int tid = threadIdx.x;
     const int k = blockIdx.x * NT + tid;
-    const bool active = k < n;
+    if (k >= n) return;
+    const PairMeta m = meta[k];
 
-    PairMeta m;
-    if (active) m = meta[k];
-    else { m.off = 0; m.id = 0; m.len2 = 0; m.len1 = 0; m.h0 = 0; m.flags = 0; }
-
-    // block-wide blob span: [first pair's off, last active pair's end)
-    __shared__ uint32_t s_span[2];
-    const int last = min(n - blockIdx.x * NT, NT) - 1;
-    if (tid == 0) s_span[0] = m.off;
-    if (tid == last) s_span[1] = m.off + (slot_bytes(m.len2, m.len1) >> 2);
-    __syncthreads();
-    const uint32_t span0 = s_span[0], span1 = s_span[1];
-    {
-        // coalesced 128-bit copy global -> shared
-        const uint4 *src = reinterpret_cast<const uint4 *>(blob + span0);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        const int nvec = (int)((span1 - span0 + 3u) >> 2);
-        for (int v = tid; v < nvec; v += NT) dst[v] = src[v];
-    }
-    __syncthreads();
-
-    const size_t rows_bytes = (size_t)8 * row_words * NT;
-    const size_t region0 = rows_bytes > (size_t)stage_bytes ? rows_bytes : (size_t)stage_bytes;
     Rows R;
     R.stride = NT;
     R.he = reinterpret_cast<uint2 *>(smem) + tid;
-    R.qs = reinterpret_cast<uint16_t *>(smem + region0) + tid;
-    R.tg = reinterpret_cast<uint32_t *>(smem + region0 + (size_t)2 * qs_words * NT) + tid;
+    R.qs = reinterpret_cast<uint16_t *>(smem + (size_t)8 * row_words * NT) + tid;
+    R.tg = reinterpret_cast<uint32_t *>(smem + (size_t)8 * row_words * NT + (size_t)2 * qs_words * NT) + tid;
+    (void)tg_words;
 
-    if (active) {
-        // narrow pairs expand from the staged copy; a wide pair's slot only holds the word offset of
-        // its 4-bit blob in the overflow area, read straight from global memory (rare)
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(smem) + (m.off - span0);
-        if (m.flags & 1) src = blob + src[0];
-        unpack_pair(src, m.len2, m.len1, m.flags & 1, R);
-    }
-    __syncthreads();  // staging (aliased by the rows) is dead from here on
-    if (!active) return;
+    // a wide pair's slot only holds the word offset of its 4-bit blob in the overflow area
+    const uint32_t *src = blob + m.off;
+    if (m.flags & 1) src = blob + src[0];
+    unpack_pair(src, m.len2, m.len1, m.flags & 1, R);
 
     PairResult r = extend_pair<MATCH1, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
     store_result(out, m.id, r);

@@ -78,13 +78,18 @@ typedef struct bsw_gpu_stats {
     int64_t d2h_bytes;          /* bytes copied device->host by the last batch / fetch */
     int64_t pairs_short;        /* pairs routed to the thread-per-pair shared-memory kernel */
     int64_t pairs_long;         /* pairs routed to the long-pair kernel */
-    double  host_bin_ms;        /* last batch: validation + length binning */
-    double  host_pack_ms;       /* last batch: 2-bit packing into pinned staging (sum over workers) */
+    double  host_bin_ms;        /* last batch: validation + key extraction */
+    double  host_pack_ms;       /* last batch: 2-bit packing into pinned staging */
     double  host_scatter_ms;    /* last batch: result scatter into SeqPair */
     double  kernel_ms;          /* last batch: sum of CUDA-event kernel time, max over GPUs */
     double  wall_ms;            /* last batch: wall time of the whole call */
     int32_t n_gpus;
     int32_t reserved;
+    double  host_sort_ms;       /* last batch: the two counting sorts + gather of sorted lengths */
+    double  host_plan_ms;       /* last batch: launch planning + slot offsets */
+    double  host_alloc_ms;      /* last batch: (re)allocation of pinned / device buffers */
+    double  host_cut_ms;        /* last batch: slab cutting */
+    double  host_wait_ms;       /* last batch: host blocked on the GPU (ring slot not yet drained) */
 } bsw_gpu_stats;
 int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out);
 
