@@ -73,6 +73,7 @@ struct Slab {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     bool busy = false;
+    bool fastm = false;      // every score of the slab times (match+1) fits int16: one-instruction M
     bool pinned = true;      // false for staged slabs (host side borrowed)
 };
 
@@ -233,7 +234,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
 
     // ---- pass A
     const int nchunks = (n + kChunk - 1) / kChunk;
-    int bad = 0, maxq = 0, maxt = 0, ntriv = 0;
+    int bad = 0, maxq = 0, maxt = 0, ntriv = 0, maxsc = 0;
     h->key.resize((size_t)n);      // len2
     h->sizes.resize((size_t)n);    // len1
     h->h0s.resize((size_t)n);
@@ -241,7 +242,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     h->ord_b.resize((size_t)n);
     h->chunk_off.resize((size_t)nchunks + 1);
     const int match = h->P.match;
-#pragma omp parallel for reduction(| : bad) reduction(max : maxq) reduction(max : maxt) reduction(+ : ntriv) schedule(static)
+#pragma omp parallel for reduction(| : bad) reduction(max : maxq) reduction(max : maxt) reduction(max : maxsc) reduction(+ : ntriv) schedule(static)
     for (int c = 0; c < nchunks; ++c) {
         const int hi = std::min(n, (c + 1) * kChunk);
         uint32_t words = 0;
@@ -258,12 +259,14 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             h->ord_a[(size_t)k] = (uint32_t)k;
             maxq = std::max(maxq, p.len2);
             maxt = std::max(maxt, p.len1);
+            maxsc = std::max(maxsc, p.h0 + p.len2 * match);
             ntriv += (p.len1 == 0 || p.len2 == 0);
             words += slot_words((uint32_t)p.len2, (uint32_t)p.len1);
         }
         h->chunk_off[(size_t)c + 1] = words;
     }
     if (bad) return BSW_ERR_RANGE;
+    s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
     {
         uint64_t run = 0;
         h->chunk_off[0] = 0;
@@ -487,13 +490,23 @@ int launch_all(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs
     return BSW_OK;
 }
 
+template <bool CNT>
+int launch_slabs_t(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs, bool fastm) {
+    if (fastm) return h->sym ? launch_all<true, true, CNT>(h, dev, main, slabs, nslabs) : launch_all<true, false, CNT>(h, dev, main, slabs, nslabs);
+    return h->sym ? launch_all<false, true, CNT>(h, dev, main, slabs, nslabs) : launch_all<false, false, CNT>(h, dev, main, slabs, nslabs);
+}
+
+// slabs are grouped by their `fastm` flag (it selects the kernel instantiation)
 int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs, bool count = false) {
-    if (count) {
-        if (h->match1) return h->sym ? launch_all<true, true, true>(h, dev, main, slabs, nslabs) : launch_all<true, false, true>(h, dev, main, slabs, nslabs);
-        return h->sym ? launch_all<false, true, true>(h, dev, main, slabs, nslabs) : launch_all<false, false, true>(h, dev, main, slabs, nslabs);
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<Slab *> sel;
+        for (int i = 0; i < nslabs; ++i) if (slabs[i]->fastm == (pass == 0)) sel.push_back(slabs[i]);
+        if (sel.empty()) continue;
+        int rc = count ? launch_slabs_t<true>(h, dev, main, sel.data(), (int)sel.size(), pass == 0)
+                       : launch_slabs_t<false>(h, dev, main, sel.data(), (int)sel.size(), pass == 0);
+        if (rc) return rc;
     }
-    if (h->match1) return h->sym ? launch_all<true, true, false>(h, dev, main, slabs, nslabs) : launch_all<true, false, false>(h, dev, main, slabs, nslabs);
-    return h->sym ? launch_all<false, true, false>(h, dev, main, slabs, nslabs) : launch_all<false, false, false>(h, dev, main, slabs, nslabs);
+    return BSW_OK;
 }
 
 int launch_slab(bsw_handle *h, Device &dev, Slab &s, bool count = false) {
@@ -657,7 +670,7 @@ int bsw_gpu_init_devices(const bsw_params *params, int n_devices, const int *dev
     if (!h) return BSW_ERR_NOMEM;
     h->P = p;
     h->K = KParams{p.o_del, p.e_del, p.o_ins, p.e_ins, p.zdrop, p.end_bonus, p.match, p.mismatch, p.ambig, 0,
-                   max_score_of(p.match, p.mismatch, p.ambig)};
+                   max_score_of(p.match, p.mismatch, p.ambig), 65536u, (uint32_t)(p.match + 1)};
     h->match1 = (p.match == 1);
     h->sym = (p.o_del == p.o_ins && p.e_del == p.e_ins);
     memset(&h->stats, 0, sizeof h->stats);

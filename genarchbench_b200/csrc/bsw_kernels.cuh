@@ -40,6 +40,10 @@ struct KParams {
     // Computed on the HOST: ptxas 12.9 (sm_100a) fuses max(max(max(match, -mismatch), ambig), 0)
     // into one VIMNMX3.RELU and drops the negation (seen on B200: band came out as w).
     int max_score;
+    // Multipliers read from the parameter bank at run time, so that ptxas keeps the lane shifts
+    // below as IMAD / IMAD.HI on the FMA pipe instead of folding them into ALU-pipe shifts (the
+    // ALU pipe is what bounds this kernel): k16 = 65536, km = match + 1.
+    uint32_t k16, km;
 };
 __host__ __device__ inline int max_score_of(int match, int mismatch, int ambig) {
     int mx = 0;
@@ -102,6 +106,16 @@ struct Rows {
     __device__ __forceinline__ uint32_t getE16(int j) const {
         const uint32_t w = he[(size_t)(j >> 1) * stride].y;
         return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+    }
+    // Hs[j] = 0, E[j] = 0 with two 16-bit stores (no read-modify-write latency in front of the row).
+    // Issued as asm with a memory clobber so the packed 64-bit accesses are not moved across them.
+    __device__ __forceinline__ void zeroHE16(int j) const {
+#ifdef BSW_HOST_EMUL
+        setHE16(j, 0u, 0u);
+#else
+        unsigned char *p = reinterpret_cast<unsigned char *>(&he[(size_t)(j >> 1) * stride]) + 2 * (j & 1);
+        asm volatile("st.u16 [%0], %2;\n\tst.u16 [%1], %2;" ::"l"(p), "l"(p + 4), "h"((unsigned short)0) : "memory");
+#endif
     }
     // sets Hs[j] = hv and E[j] = ev, leaving the other half of the word pair untouched
     __device__ __forceinline__ void setHE16(int j, uint32_t hv, uint32_t ev) const {
@@ -201,12 +215,15 @@ __device__ __forceinline__ int pair_band(const KParams &P, int qlen) {
 }
 
 // The DP of one pair over row storage R (already holding qs[] and tg[]).
-//   MATCH1: match score == 1 (M = Hd + min(s, Hd) needs no multiply)
+//   FASTM : every score of the launch satisfies score * (match + 1) <= 32767, so the reference's
+//           M = Hd ? Hd + s : 0 is ONE instruction, min(Hd + s, Hd * (match + 1)) (the product on the
+//           FMA pipe): for Hd >= 1 the second term is >= Hd + match >= Hd + s, for Hd == 0 it caps M
+//           at 0 -- and any M <= 0 behaves like 0 in max(M, E, F) and in max(M - oe, 0).
 //   SYM   : o_del == o_ins && e_del == e_ins (one T for both gap kinds)
 //   COUNT : also track the reference's exact leading trim and count the cells its scalar loop would
 //           visit (bandedSWA.cpp:191-216; the commented SW_cells++ at :215) -- the unit of work of
 //           the GCUPS metric. Used once per input outside any timed region.
-template <bool MATCH1, bool SYM, bool COUNT>
+template <bool FASTM, bool SYM, bool COUNT>
 __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int h0, const KParams &P) {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
@@ -235,11 +252,13 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
 
     const int band = pair_band(P, qlen);
     const int budget = min(qlen + band, tlen);
+    const uint32_t K16 = P.k16, KM = P.km;
 
     int best = h0, best_i = -1, best_j = -1, g_i = -1, gsc = -1, off = 0;
     int beg = 0, end = qlen;
     uint32_t tword = 0;
-    int xbeg = 0;            // COUNT: the reference's exact beg (ours lags it by whole words)
+    int hcol = h0 - P.o_del;  // first column: H(i,-1) = max(h0 - o_del - e_del*(i+1), 0)
+    int xbeg = 0;             // COUNT: the reference's exact beg (ours lags it by whole words)
     uint32_t cells = 0;
 
     for (int i = 0; i < budget; ++i) {
@@ -252,16 +271,16 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         }
 
         if ((i & 7) == 0) tword = R.TG(i >> 3);
-        const uint32_t tcode = (tword >> (4 * (i & 7))) & 0x7u;
-        const uint32_t tsel = (base_pat(tcode) | 0x80u) * 0x0101u;
+        const uint32_t tsel = (tword & 7u) * 0x1111u + 0x8080u;   // (code * 0x11 | 0x80) in both bytes
+        tword >>= 4;
 
-        int hleft = 0;
-        if (beg == 0) hleft = max(h0 - (P.o_del + P.e_del * (i + 1)), 0);
+        hcol -= P.e_del;
+        const int hleft = beg == 0 ? max(hcol, 0) : 0;
 
         // Lanes outside [beg, end) of the first / last word must see zero inputs: clear the stale
         // (never read again) entries instead of masking inside the loop.
-        if (beg & 1) R.setHE16(beg - 1, 0u, 0u);
-        if (end & 1) R.setHE16(end, 0u, 0u);
+        if (beg & 1) R.zeroHE16(beg - 1);
+        if (end & 1) R.zeroHE16(end);
 
         const int g0 = beg >> 1, g1 = (end - 1) >> 1;
         uint32_t hprev = (uint32_t)hleft << 16;  // .hi = H(i, 2*g0 - 1)
@@ -270,32 +289,60 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         int mjlo = -1, mjhi = -1;
         uint32_t h = 0, En = 0, Hst = 0;
 
-        for (int g = g0; g <= g1; ++g) {
-            const uint2 he = R.HE(g);
+        // One group = columns (2g, 2g+1). Only the F scan is serial along the row; the scores, M, T
+        // and E' of different groups are independent. With 2-3 resident warps per scheduler the
+        // kernel is bound by dependency latency, so groups are processed four at a time: all loads
+        // first, then the independent parts of the four groups (interleavable), then the F chain.
+        auto front = [&](const uint2 he, const uint32_t qsel, uint32_t &M, uint32_t &Tins, uint32_t &Enew) {
             const uint32_t Hd = he.x, Ev = he.y;
-            const uint32_t qsel = R.QS(g);
             // k = q ^ t on bits 0-1 (and the sign-replicate bit), q | t on bit 2 (ambiguous)
             const uint32_t sel = sel_combine(qsel, tsel, 0x4444u);
             const uint32_t s = prmt_sx(LUT_LO, LUT_HI, sel);
-            uint32_t sm;
-            if (MATCH1) sm = __vmins2(s, Hd);
-            else sm = __vmins2(s, __vmins2(Hd, 0x00010001u) * (uint32_t)P.match);
-            const uint32_t M = __vadd2(Hd, sm);
+            if (FASTM) {
+                M = __viaddmin_s16x2(Hd, s, Hd * KM);
+            } else {
+                const uint32_t sm = __vmins2(s, __vmins2(Hd, 0x00010001u) * (uint32_t)P.match);
+                M = __vadd2(Hd, sm);
+            }
             const uint32_t Tdel = __viaddmax_s16x2_relu(M, NEG_OE_DEL, NEG_OE_DEL);
-            const uint32_t Tins = SYM ? Tdel : __viaddmax_s16x2_relu(M, NEG_OE_INS, NEG_OE_INS);
-            En = __viaddmax_s16x2(Ev, NEG_E_DEL, Tdel);
+            Tins = SYM ? Tdel : __viaddmax_s16x2_relu(M, NEG_OE_INS, NEG_OE_INS);
+            Enew = __viaddmax_s16x2(Ev, NEG_E_DEL, Tdel);
+        };
+        auto back = [&](const int g, const uint32_t Ev, const uint32_t M, const uint32_t Tins, const uint32_t Enew) {
             const uint32_t W1 = __viaddmax_s16x2(A, NEG_E_INS, Tins);   // .lo = F(i, 2g+1)
-            const uint32_t B = W1 * 65536u + A;                          // { F(2g), F(2g+1) }
+            const uint32_t B = W1 * K16 + A;                             // { F(2g), F(2g+1) }  (IMAD)
             h = __vimax3_s16x2(M, Ev, B);
             const uint32_t W2 = __viaddmax_s16x2(B, NEG_E_INS, Tins);   // .hi = F(i, 2g+2)
-            A = W2 >> 16;
-            Hst = __funnelshift_r(hprev, h, 16);                         // { H(i,2g-1), H(i,2g) }
+            A = __umulhi(W2, K16);                                       // W2 >> 16           (IMAD.HI)
+            Hst = __umulhi(hprev, K16) + h * K16;                        // { H(i,2g-1), H(i,2g) }
+            En = Enew;
             R.HE(g) = make_uint2(Hst, En);
             hprev = h;
             bool phi, plo;
             rm = __vibmax_s16x2(h, rm, &phi, &plo);
             if (plo) mjlo = g;
             if (phi) mjhi = g;
+        };
+        int g = g0;
+        for (; g + 3 <= g1; g += 4) {
+            const uint2 he0 = R.HE(g), he1 = R.HE(g + 1), he2 = R.HE(g + 2), he3 = R.HE(g + 3);
+            const uint32_t q0 = R.QS(g), q1 = R.QS(g + 1), q2 = R.QS(g + 2), q3 = R.QS(g + 3);
+            uint32_t M0, M1, M2, M3, T0, T1, T2, T3, E0, E1, E2, E3;
+            front(he0, q0, M0, T0, E0);
+            front(he1, q1, M1, T1, E1);
+            front(he2, q2, M2, T2, E2);
+            front(he3, q3, M3, T3, E3);
+            back(g, he0.y, M0, T0, E0);
+            back(g + 1, he1.y, M1, T1, E1);
+            back(g + 2, he2.y, M2, T2, E2);
+            back(g + 3, he3.y, M3, T3, E3);
+        }
+        for (; g <= g1; ++g) {
+            const uint2 he0 = R.HE(g);
+            const uint32_t q0 = R.QS(g);
+            uint32_t M0, T0, E0;
+            front(he0, q0, M0, T0, E0);
+            back(g, he0.y, M0, T0, E0);
         }
 
         // last computed column's H, and the reference's eh[end] = { h1, 0 }
@@ -332,26 +379,21 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             while (j < end && R.getH16(j) == 0 && R.getE16(j) == 0) ++j;
             xbeg = j;
         }
-        // leading trim (not semantic: skipped cells are all-zero; done lazily, one word per row)
-        {
+        // leading trim (not semantic: skipped cells are all-zero; done lazily, one word every 4th row)
+        if ((i & 3) == 3) {
             const uint2 z = R.HE(g0);
             if ((z.x | z.y) == 0u && 2 * (g0 + 1) > beg) beg = 2 * (g0 + 1);
         }
-        // trailing trim (semantic): j* = last j in [beg,end] with Hs[j] | E[j] != 0; m > 0
-        // guarantees one exists
-        {
+        // trailing trim (semantic): j* = last j in [beg,end] with Hs[j] | E[j] != 0 (m > 0
+        // guarantees one exists); the new end is min(j* + 2, qlen). Hs[end] = H(i,end-1) is almost
+        // always non-zero, so that case is tested first.
+        if (hlast) {
+            end = min(end + 2, qlen);
+        } else {
             int jstar;
             const uint32_t Wt = Hst | En;
-            if (end & 1) {
-                if (Wt >> 16) jstar = end;
-                else if (Wt & 0xFFFFu) jstar = end - 1;
-                else jstar = -1;
-            } else {
-                if (hlast) jstar = end;
-                else if (Wt >> 16) jstar = end - 1;
-                else if (Wt & 0xFFFFu) jstar = end - 2;
-                else jstar = -1;
-            }
+            if (end & 1) jstar = (Wt & 0xFFFFu) ? end - 1 : -1;
+            else jstar = (Wt >> 16) ? end - 1 : ((Wt & 0xFFFFu) ? end - 2 : -1);
             if (jstar < 0) {
                 int g = g1 - 1;
                 uint32_t wz = 0;
@@ -390,7 +432,7 @@ __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const Pa
 //   (a few dozen bytes per pair, read once; the host packs slots in the caller's order so that its
 //   own pass is a pure stream -- see DESIGN.md).
 // ---------------------------------------------------------------------------------------------
-template <bool MATCH1, bool SYM, bool COUNT>
+template <bool FASTM, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
                  PairOut *__restrict__ out, int n, KParams P, int row_words, int qs_words,
@@ -414,7 +456,7 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     if (m.flags & 1) src = blob + src[0];
     unpack_pair(src, m.len2, m.len1, m.flags & 1, R);
 
-    PairResult r = extend_pair<MATCH1, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
+    PairResult r = extend_pair<FASTM, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
     store_result(out, m.id, r);
 }
 
@@ -424,7 +466,7 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
 //   scratch layout: he[row_words][nthreads] (uint2) | qs[qs_words][nthreads] (u16, padded to 4 B)
 //                   | tg[tg_words][nthreads] (u32)
 // ---------------------------------------------------------------------------------------------
-template <bool MATCH1, bool SYM, bool COUNT>
+template <bool FASTM, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
                 PairOut *__restrict__ out, int n, KParams P, int row_words, int qs_words,
@@ -442,7 +484,7 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     p += (((size_t)2 * qs_words * nthreads) + 15) & ~(size_t)15;
     R.tg = reinterpret_cast<uint32_t *>(p) + k;
     unpack_pair((m.flags & 1) ? blob + blob[m.off] : blob + m.off, m.len2, m.len1, m.flags & 1, R);
-    PairResult r = extend_pair<MATCH1, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
+    PairResult r = extend_pair<FASTM, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
     store_result(out, m.id, r);
 }
 

@@ -41,6 +41,12 @@ static inline uint32_t __viaddmax_s16x2_relu(uint32_t a, uint32_t b, uint32_t c)
     int h = std::max(std::max(emul::wrap16(emul::hi(a) + emul::hi(b)), (int)emul::hi(c)), 0);
     return emul::pk(l, h);
 }
+static inline uint32_t __viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c) {
+    int l = std::min(emul::wrap16(emul::lo(a) + emul::lo(b)), (int)emul::lo(c));
+    int h = std::min(emul::wrap16(emul::hi(a) + emul::hi(b)), (int)emul::hi(c));
+    return emul::pk(l, h);
+}
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline uint32_t __vimax3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
     return emul::pk(std::max({emul::lo(a), emul::lo(b), emul::lo(c)}),
                     std::max({emul::hi(a), emul::hi(b), emul::hi(c)}));

@@ -13,8 +13,8 @@ using namespace bswk;
 extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
                               const uint8_t *qer, int64_t n, int32_t w) {
     KParams K{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w,
-              max_score_of(p->match, p->mismatch, p->ambig)};
-    const bool m1 = p->match == 1, sym = p->o_del == p->o_ins && p->e_del == p->e_ins;
+              max_score_of(p->match, p->mismatch, p->ambig), 65536u, (uint32_t)(p->match + 1)};
+    const bool sym = p->o_del == p->o_ins && p->e_del == p->e_ins;
 #pragma omp parallel
     {
         std::vector<uint2> he;
@@ -27,8 +27,8 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
                 sp.score = sp.h0; sp.qle = sp.tle = sp.gtle = 0; sp.gscore = -1; sp.max_off = 0;
                 continue;
             }
-            he.assign((size_t)((sp.len2 + 1) / 2 + 2), uint2{0xDEADBEEFu, 0xDEADBEEFu});
-            qs.assign((size_t)((sp.len2 + 1) / 2 + 1), 0xDEAD);
+            he.assign((size_t)((sp.len2 + 1) / 2 + 6), uint2{0xDEADBEEFu, 0xDEADBEEFu});
+            qs.assign((size_t)((sp.len2 + 1) / 2 + 6), 0xDEAD);
             tg.assign((size_t)((sp.len1 + 7) / 8 + 1), 0xDEADBEEFu);
             blob.assign((size_t)(seq_bytes(sp.len2, true) + seq_bytes(sp.len1, true)) / 4 + 4, 0);
             uint8_t *b = reinterpret_cast<uint8_t *>(blob.data());
@@ -41,6 +41,7 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
             Rows R{he.data(), qs.data(), tg.data(), 1};
             unpack_pair(blob.data(), sp.len2, sp.len1, wide, R);
             PairResult r;
+            const bool m1 = (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767 && !getenv("BSW_EMUL_SLOWM");
             if (m1) r = sym ? extend_pair<true, true, true>(R, sp.len2, sp.len1, sp.h0, K)
                             : extend_pair<true, false, true>(R, sp.len2, sp.len1, sp.h0, K);
             else r = sym ? extend_pair<false, true, true>(R, sp.len2, sp.len1, sp.h0, K)
