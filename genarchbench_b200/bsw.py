@@ -18,7 +18,8 @@ import numpy as np
 from .pairio import PairBatch, SEQPAIR_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbsw_gpu.so")
+# BSW_GPU_LIB: developer override used by scripts/ to A/B kernel builds; the product loads lib/libbsw_gpu.so
+LIB_PATH = os.environ.get("BSW_GPU_LIB") or os.path.join(_HERE, "lib", "libbsw_gpu.so")
 
 DEFAULT_AMBIG = -1          # bandedSWA.h:61
 DEFAULT_W = 100             # main_banded.cpp:268

@@ -43,8 +43,9 @@ inline double ms_since(Clock::time_point t0) {
 
 struct Launch {
     int first;       // first sorted position
-    int n;           // pairs
-    int row_words, qs_words, tg_words, stage_bytes;
+    int n;           // pairs (the n_wide pairs holding an ambiguous base come first)
+    int n_wide;
+    int row_el, qs_words, tg_words;   // per pair: uint4 row elements, u32 selector words, u32 target words
     size_t smem;     // 0 => long kernel
     int64_t work;    // sum len1*len2, for ordering
 };
@@ -86,7 +87,7 @@ struct Device {
     cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t aux_ev[kAux] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr;
-    bool attr_set[2][2][2] = {{{false, false}, {false, false}}, {{false, false}, {false, false}}};
+    bool attr_set[8] = {false, false, false, false, false, false, false, false};
 };
 
 }  // namespace
@@ -178,10 +179,8 @@ int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
 
 // ---- host: per-slab preparation ----------------------------------------------------------------
 
-inline size_t smem_need(int row_words, int qs_words, int tg_words, int stage_bytes) {
-    size_t rows = (size_t)8 * row_words * kBlockPairs;
-    size_t r0 = std::max(rows, (size_t)stage_bytes);
-    return r0 + (size_t)2 * qs_words * kBlockPairs + (size_t)4 * tg_words * kBlockPairs;
+inline size_t smem_need(int row_el, int qs_words, int tg_words) {
+    return ((size_t)16 * row_el + (size_t)4 * qs_words + (size_t)4 * tg_words) * kBlockPairs;
 }
 
 // Stable parallel counting sort of `in` (indices) by key[in[.]] < nkeys into `out`.
@@ -354,6 +353,18 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
         }
     }
     memset(blob + s.blob_bytes - 16, 0, 16);
+    // inside a launch bin the pairs holding an ambiguous base come first (whole warps of them run
+    // the LOP3-selector code): sort key = len2 - 1 with the wide flag inserted above the bin's low bits
+    static_assert(kBinCols == 16, "sort key layout");
+    auto bin_key = [](uint32_t len2, uint32_t wide) {
+        const uint32_t v = len2 - 1;   // len2 >= 1 for every sorted pair
+        return ((v & ~15u) << 1) | (wide << 4) | (v & 15u);
+    };
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < n; ++k) {
+        const uint32_t l2 = h->key[(size_t)k];
+        h->key[(size_t)k] = l2 ? bin_key(l2, h->flags[(size_t)k]) : 0u;
+    }
     st.host_pack_ms += ms_since(t0);
     t0 = Clock::now();
 
@@ -369,15 +380,17 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     s.n_dev = nd;
     if (nd == 0) return BSW_OK;
     counting_sort(h->sizes, h->ord_a.data(), h->ord_b.data(), nd, maxt + 1, true);
-    counting_sort(h->key, h->ord_b.data(), h->ord_a.data(), nd, maxq + 1, true);
+    counting_sort(h->key, h->ord_b.data(), h->ord_a.data(), nd, (int)bin_key((uint32_t)std::max(maxq, 1), 1u) + 1, true);
     const uint32_t *ord = h->ord_a.data();
     st.host_sort_ms += ms_since(t0);
     t0 = Clock::now();
 
-    // ---- pass C + plan. The sorted order is descending in len2, so a launch = the run of positions
-    // whose len2 falls in one kBinCols-wide bin; its geometry needs the largest len2 / len1 in it.
-    h->binmax.assign((size_t)(maxq / kBinCols + 2) * 2, 0);
-    std::vector<uint32_t> &bm = h->binmax;   // per bin: [count, max len1]
+    // ---- pass C + plan. The sorted order is descending in len2 bin, wide pairs first inside a bin, so
+    // a launch = the run of positions whose len2 falls in one kBinCols-wide bin; its geometry needs
+    // the largest len2 / len1 in it.
+    const int nbins = maxq / kBinCols + 2;
+    h->binmax.assign((size_t)nbins * 4, 0);
+    std::vector<uint32_t> &bm = h->binmax;   // per (wide, bin): [count, max len1]
 #pragma omp parallel num_threads(T)
     {
         std::vector<uint32_t> loc(bm.size(), 0);
@@ -385,12 +398,15 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
         for (int p = 0; p < nd; ++p) {
             const uint32_t k = ord[p];
             PairMeta &m = s.h_meta[p];
+            const uint32_t fl = h->flags[k];
+            const uint32_t kk = h->key[k];
+            const uint32_t l2 = (((kk >> 1) & ~15u) | (kk & 15u)) + 1;
             m.off = h->offs[k];
             m.id = k;
-            m.len2 = (uint16_t)h->key[k]; m.len1 = (uint16_t)h->sizes[k];
+            m.len2 = (uint16_t)l2; m.len1 = (uint16_t)h->sizes[k];
             m.h0 = h->h0s[k];
-            m.flags = h->flags[k];
-            const size_t b = (size_t)((h->key[k] - 1) / kBinCols) * 2;
+            m.flags = (uint16_t)fl;
+            const size_t b = ((size_t)fl * nbins + (size_t)((l2 - 1) / kBinCols)) * 2;
             loc[b] += 1;
             loc[b + 1] = std::max(loc[b + 1], h->sizes[k]);
         }
@@ -399,20 +415,23 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     }
     {
         int p = 0;
-        for (int b = maxq / kBinCols + 1; b >= 0; --b) {
-            const int cnt = (int)bm[(size_t)b * 2];
-            if (!cnt) continue;
-            const int q_hi = (int)s.h_meta[p].len2, t_hi = (int)bm[(size_t)b * 2 + 1];
+        for (int b = nbins - 1; b >= 0; --b) {
+            const size_t bw = ((size_t)nbins + (size_t)b) * 2, bn = (size_t)b * 2;
+            const int nw = (int)bm[bw], nn = (int)bm[bn];
+            if (nw + nn == 0) continue;
+            int q_hi = 0;
+            if (nw) q_hi = std::max(q_hi, (int)s.h_meta[p].len2);
+            if (nn) q_hi = std::max(q_hi, (int)s.h_meta[p + nw].len2);
+            const int t_hi = (int)std::max(bm[bw + 1], bm[bn + 1]);
             Launch L;
-            L.first = p; L.n = cnt; L.work = (int64_t)cnt * q_hi * t_hi;
-            L.row_words = ((q_hi + 1) >> 1) + 1;
-            L.qs_words = (q_hi + 1) >> 1;
+            L.first = p; L.n = nw + nn; L.n_wide = nw; L.work = (int64_t)(nw + nn) * q_hi * t_hi;
+            L.row_el = row_elems(q_hi);
+            L.qs_words = sel_words(q_hi);
             L.tg_words = (t_hi + 7) >> 3;
-            L.stage_bytes = 0;
-            L.smem = smem_need(L.row_words, L.qs_words, L.tg_words, 0);
+            L.smem = smem_need(L.row_el, L.qs_words, L.tg_words);
             if (L.smem > kMaxSmem) L.smem = 0;  // long kernel
             s.launches.push_back(L);
-            p += cnt;
+            p += nw + nn;
         }
     }
     st.host_plan_ms += ms_since(t0);
@@ -431,28 +450,39 @@ int ensure_aux(bsw_handle *h, Device &dev) {
     return BSW_OK;
 }
 
+// The kernel instantiations, indexed [fastm][sym][count].
+typedef void (*ShortFn)(const PairMeta *, const uint32_t *, PairOut *, int, int, KParams, int, int, int);
+typedef void (*LongFn)(const PairMeta *, const uint32_t *, PairOut *, int, int, KParams, int, int, int, unsigned char *);
+template <int I> struct KernelTable {
+    static void fill(ShortFn *sf, LongFn *lf) {
+        sf[I] = bsw_short_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
+        lf[I] = bsw_long_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
+        KernelTable<I - 1>::fill(sf, lf);
+    }
+};
+template <> struct KernelTable<-1> { static void fill(ShortFn *, LongFn *) {} };
+inline int kernel_index(bool fastm, bool sym, bool count) {
+    return (fastm ? 4 : 0) | (sym ? 2 : 0) | (count ? 1 : 0);
+}
+
 // Enqueues every launch of the given slabs: work forks from `main` onto the device's aux streams
 // (bins of different lengths overlap; the few-block long bins no longer leave the GPU idle) and
 // joins back into `main`. Long-kernel launches share a per-slab scratch and stay on aux[0].
-template <bool M1, bool SY, bool CNT>
-int launch_all(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs) {
+int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs, bool count = false) {
+    static ShortFn short_fn[8];
+    static LongFn long_fn[8];
+    static bool filled = false;
+    if (!filled) { KernelTable<7>::fill(short_fn, long_fn); filled = true; }
     int rc = ensure_aux(h, dev);
     if (rc) return rc;
-    auto kshort = bsw_short_kernel<M1, SY, CNT>;
-    if (!dev.attr_set[M1][SY][CNT]) {
-        CU(cudaFuncSetAttribute(kshort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-        dev.attr_set[M1][SY][CNT] = true;
-    }
     // scratch for the long kernel, sized once per slab before anything is enqueued
     for (int i = 0; i < nslabs; ++i) {
         Slab &s = *slabs[i];
         size_t need = 0;
         for (const Launch &L : s.launches) {
             if (L.smem) continue;
-            const size_t nthreads = (size_t)((L.n + kBlockPairs - 1) / kBlockPairs) * kBlockPairs;
-            need = std::max(need, (size_t)8 * L.row_words * nthreads +
-                                      ((((size_t)2 * L.qs_words * nthreads) + 15) & ~(size_t)15) +
-                                      (size_t)4 * L.tg_words * nthreads + 256);
+            const size_t nthreads = (size_t)((launch_threads(L.n_wide, L.n - L.n_wide) + kBlockPairs - 1) / kBlockPairs) * kBlockPairs;
+            need = std::max(need, ((size_t)16 * L.row_el + (size_t)4 * L.qs_words + (size_t)4 * L.tg_words) * nthreads + 256);
         }
         if (need > s.cap_scratch) {
             CU(cudaDeviceSynchronize());
@@ -468,15 +498,20 @@ int launch_all(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs
     for (int i = 0; i < nslabs; ++i) {
         Slab &s = *slabs[i];
         for (const Launch &L : s.launches) {
-            const int grid = (L.n + kBlockPairs - 1) / kBlockPairs;
+            const int grid = (launch_threads(L.n_wide, L.n - L.n_wide) + kBlockPairs - 1) / kBlockPairs;
+            const int ki = kernel_index(s.fastm, h->sym, count);
             if (L.smem) {
+                if (!dev.attr_set[ki]) {
+                    CU(cudaFuncSetAttribute(short_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                    dev.attr_set[ki] = true;
+                }
                 cudaStream_t st = dev.aux[rr++ % kAux];
-                kshort<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K,
-                                                         L.row_words, L.qs_words, L.tg_words);
+                short_fn[ki]<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta + L.first, s.d_blob, s.d_out, L.n_wide,
+                                                                L.n - L.n_wide, h->K, L.row_el, L.qs_words, L.tg_words);
             } else {
-                bsw_long_kernel<M1, SY, CNT><<<grid, kBlockPairs, 0, dev.aux[0]>>>(
-                    s.d_meta + L.first, s.d_blob, s.d_out, L.n, h->K, L.row_words, L.qs_words, L.tg_words,
-                    s.d_scratch);
+                long_fn[ki]<<<grid, kBlockPairs, 0, dev.aux[0]>>>(
+                    s.d_meta + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.row_el, L.qs_words,
+                    L.tg_words, s.d_scratch);
             }
             CU(cudaGetLastError());
             h->stats.kernel_launches++;
@@ -486,25 +521,6 @@ int launch_all(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs
     for (int j = 0; j < kAux; ++j) {
         CU(cudaEventRecord(dev.aux_ev[j], dev.aux[j]));
         CU(cudaStreamWaitEvent(main, dev.aux_ev[j], 0));
-    }
-    return BSW_OK;
-}
-
-template <bool CNT>
-int launch_slabs_t(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs, bool fastm) {
-    if (fastm) return h->sym ? launch_all<true, true, CNT>(h, dev, main, slabs, nslabs) : launch_all<true, false, CNT>(h, dev, main, slabs, nslabs);
-    return h->sym ? launch_all<false, true, CNT>(h, dev, main, slabs, nslabs) : launch_all<false, false, CNT>(h, dev, main, slabs, nslabs);
-}
-
-// slabs are grouped by their `fastm` flag (it selects the kernel instantiation)
-int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs, bool count = false) {
-    for (int pass = 0; pass < 2; ++pass) {
-        std::vector<Slab *> sel;
-        for (int i = 0; i < nslabs; ++i) if (slabs[i]->fastm == (pass == 0)) sel.push_back(slabs[i]);
-        if (sel.empty()) continue;
-        int rc = count ? launch_slabs_t<true>(h, dev, main, sel.data(), (int)sel.size(), pass == 0)
-                       : launch_slabs_t<false>(h, dev, main, sel.data(), (int)sel.size(), pass == 0);
-        if (rc) return rc;
     }
     return BSW_OK;
 }
@@ -670,7 +686,7 @@ int bsw_gpu_init_devices(const bsw_params *params, int n_devices, const int *dev
     if (!h) return BSW_ERR_NOMEM;
     h->P = p;
     h->K = KParams{p.o_del, p.e_del, p.o_ins, p.e_ins, p.zdrop, p.end_bonus, p.match, p.mismatch, p.ambig, 0,
-                   max_score_of(p.match, p.mismatch, p.ambig), 65536u, (uint32_t)(p.match + 1)};
+                   max_score_of(p.match, p.mismatch, p.ambig), 65536u, (uint32_t)(p.match + 1), 1u};
     h->match1 = (p.match == 1);
     h->sym = (p.o_del == p.o_ins && p.e_del == p.e_ins);
     memset(&h->stats, 0, sizeof h->stats);

@@ -22,6 +22,18 @@
 //    slots in the caller's order; each thread expands its own slot into shared memory once per pair.
 #pragma once
 #include <stdint.h>
+#ifndef BSW_HIER_ARGMAX
+#define BSW_HIER_ARGMAX 0
+#endif
+#ifndef BSW_SEL_LOP3      // experiment: LOP3 selector for narrow pairs too
+#define BSW_SEL_LOP3 0
+#endif
+#ifndef BSW_TRIM_EVERY    // leading trim every N-th row (power of two)
+#define BSW_TRIM_EVERY 1
+#endif
+#ifndef BSW_ST_SHARED     // 16-bit row stores through st.shared (short kernel only)
+#define BSW_ST_SHARED 0
+#endif
 #ifdef BSW_HOST_EMUL
 // tests/host_emul compiles the per-pair code below with g++ against an emulation of the few CUDA
 // intrinsics it uses, so the algorithm can be checked against the oracle without a GPU.
@@ -42,8 +54,8 @@ struct KParams {
     int max_score;
     // Multipliers read from the parameter bank at run time, so that ptxas keeps the lane shifts
     // below as IMAD / IMAD.HI on the FMA pipe instead of folding them into ALU-pipe shifts (the
-    // ALU pipe is what bounds this kernel): k16 = 65536, km = match + 1.
-    uint32_t k16, km;
+    // ALU pipe is what bounds this kernel): k16 = 65536, km = match + 1, k1 = 1.
+    uint32_t k16, km, k1;
 };
 __host__ __device__ inline int max_score_of(int match, int mismatch, int ambig) {
     int mx = 0;
@@ -85,53 +97,69 @@ __device__ __forceinline__ uint32_t pack2(int v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row storage. Words are interleaved by thread: word w of thread t lives at base[w * stride + t].
-//   he[g]  : .x = { Hs[2g], Hs[2g+1] }  with Hs[j] = H(i-1, j-1)  (the reference's eh[j].h)
-//            .y = { E[2g],  E[2g+1]  }  with E[j]  = E(i, j)       (the reference's eh[j].e)
-//   qs[g]  : 16-bit PRMT selector seed of query columns (2g, 2g+1)
-//   tg[w]  : target bases, 4 bits each, 8 per word
+// Row storage. Everything is interleaved by thread so that a warp's accesses are conflict free
+// whatever column each thread is at:
+//   he4[k] : uint4 = the reference's eh[] for FOUR adjacent columns 4k .. 4k+3 (two "groups"):
+//              .x = { Hs[4k],   Hs[4k+1] }   .y = { E[4k],   E[4k+1] }
+//              .z = { Hs[4k+2], Hs[4k+3] }   .w = { E[4k+2], E[4k+3] }
+//            with Hs[j] = H(i-1, j-1) (eh[j].h) and E[j] = E(i, j) (eh[j].e), int16 each;
+//            element k of this thread lives at he4[k * stride]                      (LDS/STS.128)
+//   qs[k]  : u32 = the PRMT selector seeds of query columns 4k .. 4k+3 (16 bits per group)
+//   tg[w]  : target bases, 4 bits each, 8 per word (narrow pairs store 4 - code, see unpack_pair)
 // ---------------------------------------------------------------------------------------------
 struct Rows {
-    uint2 *he;
-    uint16_t *qs;
+    uint4 *he4;
+    uint32_t *qs;
     uint32_t *tg;
     int stride;  // threads sharing the arrays (blockDim for shared memory, grid-wide for global)
-    __device__ __forceinline__ uint2 &HE(int g) const { return he[(size_t)g * stride]; }
+    __device__ __forceinline__ uint4 &HE4(int k) const { return he4[(size_t)k * stride]; }
+    // group g = columns (2g, 2g+1): the .xy or .zw half of element g >> 1
+    __device__ __forceinline__ uint2 &HE(int g) const {
+        return reinterpret_cast<uint2 *>(he4 + (size_t)(g >> 1) * stride)[g & 1];
+    }
     // 16-bit views of the rows. They go through the SAME 32-bit words the packed loop reads and
-    // writes (no differently-typed aliases the compiler could reorder around the uint2 accesses).
+    // writes (no differently-typed aliases the compiler could reorder around the packed accesses).
     __device__ __forceinline__ uint32_t getH16(int j) const {
-        const uint32_t w = he[(size_t)(j >> 1) * stride].x;
+        const uint32_t w = HE(j >> 1).x;
         return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
     }
     __device__ __forceinline__ uint32_t getE16(int j) const {
-        const uint32_t w = he[(size_t)(j >> 1) * stride].y;
+        const uint32_t w = HE(j >> 1).y;
         return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
     }
-    // Hs[j] = 0, E[j] = 0 with two 16-bit stores (no read-modify-write latency in front of the row).
-    // Issued as asm with a memory clobber so the packed 64-bit accesses are not moved across them.
-    __device__ __forceinline__ void zeroHE16(int j) const {
-#ifdef BSW_HOST_EMUL
-        setHE16(j, 0u, 0u);
-#else
-        unsigned char *p = reinterpret_cast<unsigned char *>(&he[(size_t)(j >> 1) * stride]) + 2 * (j & 1);
-        asm volatile("st.u16 [%0], %2;\n\tst.u16 [%1], %2;" ::"l"(p), "l"(p + 4), "h"((unsigned short)0) : "memory");
-#endif
-    }
-    // sets Hs[j] = hv and E[j] = ev, leaving the other half of the word pair untouched
+    // Hs[j] = hv, E[j] = ev with two 16-bit stores (no read-modify-write latency in front of the
+    // row). Issued as asm with a memory clobber so the packed accesses are not moved across them.
     __device__ __forceinline__ void setHE16(int j, uint32_t hv, uint32_t ev) const {
-        uint2 &p = he[(size_t)(j >> 1) * stride];
+#ifdef BSW_HOST_EMUL
+        uint2 &p = HE(j >> 1);
         uint2 v = p;
         if (j & 1) { v.x = (v.x & 0xFFFFu) | (hv << 16); v.y = (v.y & 0xFFFFu) | (ev << 16); }
         else { v.x = (v.x & 0xFFFF0000u) | hv; v.y = (v.y & 0xFFFF0000u) | ev; }
         p = v;
+#else
+        unsigned char *p = reinterpret_cast<unsigned char *>(&HE(j >> 1)) + 2 * (j & 1);
+#if BSW_ST_SHARED
+        const uint32_t sp = (uint32_t)__cvta_generic_to_shared(p);
+        asm volatile("st.shared.u16 [%0], %1;\n\tst.shared.u16 [%0+4], %2;" ::"r"(sp), "h"((unsigned short)hv),
+                     "h"((unsigned short)ev) : "memory");
+#else
+        asm volatile("st.u16 [%0], %2;\n\tst.u16 [%1], %3;" ::"l"(p), "l"(p + 4), "h"((unsigned short)hv),
+                     "h"((unsigned short)ev) : "memory");
+#endif
+#endif
     }
-    __device__ __forceinline__ uint16_t &QS(int g) const { return qs[(size_t)g * stride]; }
+    __device__ __forceinline__ uint32_t &QS2(int k) const { return qs[(size_t)k * stride]; }
+    __device__ __forceinline__ uint32_t QS(int g) const {   // 16-bit seed of one group
+        const uint32_t w = QS2(g >> 1);
+        return (g & 1) ? (w >> 16) : (w & 0xFFFFu);
+    }
     __device__ __forceinline__ uint32_t &TG(int w) const { return tg[(size_t)w * stride]; }
 };
 
 // PTX prmt.b32 (default mode): byte i of the result = byte (nibble_i & 7) of {b:a}; nibble bit 3 set
-// => that byte's SIGN replicated instead. (__byte_perm() masks the selector with 0x7777 and loses
-// the sign mode, so the instruction is issued directly.)
+// => that byte's SIGN replicated instead. Only the low 16 bits of the selector are used.
+// (__byte_perm() masks the selector with 0x7777 and loses the sign mode, so the instruction is
+// issued directly.)
 __device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) {
 #ifdef BSW_HOST_EMUL
     return emul::prmt(a, b, sel);
@@ -152,47 +180,70 @@ __device__ __forceinline__ uint32_t sel_combine(uint32_t q, uint32_t t, uint32_t
 #endif
 }
 
-// selector nibble pattern of one base code (0..4): both nibbles carry the code
-__device__ __forceinline__ uint32_t base_pat(uint32_t code) { return code * 0x11u; }
+// Substitution scores come from ONE PRMT per group: an 8-byte look-up table indexed, per 16-bit
+// lane, by a 3-bit code in the selector nibbles (value byte: the code; sign byte: code | 8).
+//   narrow pairs (bases 0..3): code = q + (4 - t) in 1..7, == 4 iff q == t. The selector is a plain
+//     ADD of the query seed (nibbles q) and the row's target seed (nibbles 4 - t, sign nibbles + 8):
+//     no nibble ever carries, and the add is issued as IMAD on the FMA pipe (see KParams::k1).
+//     LUT: byte 4 = match, every other byte = -mismatch.
+//   wide pairs (a base may be 4 = ambiguous): code = (q ^ t) on bits 0-1 | (q | t) on bit 2, one LOP3.
+//     LUT: byte 0 = match, 1..3 = -mismatch, 4..7 = ambiguous.
+template <bool WIDE>
+__device__ __forceinline__ void score_lut(const KParams &P, uint32_t &lo, uint32_t &hi) {
+    const uint32_t mm = (uint32_t)(-P.mismatch) & 0xFFu, ma = (uint32_t)P.match & 0xFFu;
+    if (WIDE || BSW_SEL_LOP3) {
+        lo = ma | (mm * 0x01010100u);
+        hi = ((uint32_t)P.ambig & 0xFFu) * 0x01010101u;
+    } else {
+        lo = mm * 0x01010101u;
+        hi = ma | (mm * 0x01010100u);
+    }
+}
 
-// Expands this thread's packed blob (already visible at `blob`, 4-byte words) into qs[] / tg[].
-__device__ inline void unpack_pair(const uint32_t *blob, int qlen, int tlen, bool wide, const Rows &R) {
-    const int ngroups = (qlen + 1) >> 1;
-    if (!wide) {
-        // query: 16 bases per word -> 8 selector seeds
-        for (int w = 0, g = 0; g < ngroups; ++w) {
-            uint32_t x = blob[w];
+// Expands this thread's packed blob (4-byte words: query then target, each padded to 4 bytes) into
+// qs[] / tg[]. Narrow blobs hold 2 bits per base, wide blobs 4 bits per base.
+template <bool WIDE>
+__device__ inline void unpack_pair(const uint32_t *blob, int qlen, int tlen, const Rows &R) {
+    const int nsel = (((qlen + 1) >> 1) + 1) >> 1;   // selector words: two groups each (== sel_words)
+    const int twords = (tlen + 7) >> 3;
+    if (!WIDE) {
+        // 16 bases per word -> 8 groups -> 4 selector words; a base b becomes the byte b * 0x11
+        for (int w = 0, k = 0; k < nsel; ++w) {
+            const uint32_t x = blob[w];
 #pragma unroll
-            for (int k = 0; k < 8; ++k, ++g) {
-                if (g < ngroups) {
-                    uint32_t two = (x >> (4 * k)) & 0xFu;
-                    R.QS(g) = (uint16_t)(base_pat(two & 3u) | (base_pat(two >> 2) << 8));
+            for (int u = 0; u < 4; ++u, ++k) {
+                if (k < nsel) {
+                    uint32_t v = (x >> (8 * u)) & 0xFFu;          // 4 bases
+                    v = (v | (v << 12)) & 0x000F000Fu;
+                    v = (v | (v << 6)) & 0x03030303u;             // one base per byte
+                    R.QS2(k) = v * 0x11u;
                 }
             }
         }
         const uint32_t *tb = blob + (seq_bytes(qlen, false) >> 2);
-        const int twords = (tlen + 7) >> 3;
         for (int w = 0; w < twords; ++w) {
             uint32_t x = tb[w >> 1];
             x = (w & 1) ? (x >> 16) : (x & 0xFFFFu);   // 8 bases, 2 bits each
             x = (x | (x << 8)) & 0x00FF00FFu;
             x = (x | (x << 4)) & 0x0F0F0F0Fu;
             x = (x | (x << 2)) & 0x33333333u;           // -> 8 nibbles
-            R.TG(w) = x;
+            R.TG(w) = BSW_SEL_LOP3 ? x : 0x44444444u - x;   // nibble = 4 - code (never borrows)
         }
     } else {
-        for (int w = 0, g = 0; g < ngroups; ++w) {
-            uint32_t x = blob[w];
+        // 8 bases per word -> 4 groups -> 2 selector words
+        for (int w = 0, k = 0; k < nsel; ++w) {
+            const uint32_t x = blob[w];
 #pragma unroll
-            for (int k = 0; k < 4; ++k, ++g) {
-                if (g < ngroups) {
-                    uint32_t two = (x >> (8 * k)) & 0xFFu;
-                    R.QS(g) = (uint16_t)(base_pat(two & 0xFu) | (base_pat(two >> 4) << 8));
+            for (int u = 0; u < 2; ++u, ++k) {
+                if (k < nsel) {
+                    uint32_t v = (x >> (16 * u)) & 0xFFFFu;       // 4 bases, 4 bits each
+                    v = (v | (v << 8)) & 0x00FF00FFu;
+                    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+                    R.QS2(k) = v * 0x11u;
                 }
             }
         }
         const uint32_t *tb = blob + (seq_bytes(qlen, true) >> 2);
-        const int twords = (tlen + 7) >> 3;
         for (int w = 0; w < twords; ++w) R.TG(w) = tb[w];
     }
 }
@@ -214,6 +265,12 @@ __device__ __forceinline__ int pair_band(const KParams &P, int qlen) {
     return band;
 }
 
+// number of he4 elements (4 columns each) a pair with qlen query bases needs: columns 0 .. qlen
+// (one spare so that the hi lane of the last group is always initialised), rounded up
+__host__ __device__ inline int row_elems(int qlen) { return (qlen + 4) >> 2; }
+// number of qs words (selector seeds of two groups = 4 columns each) for qlen query bases
+__host__ __device__ inline int sel_words(int qlen) { return (((qlen + 1) >> 1) + 1) >> 1; }
+
 // The DP of one pair over row storage R (already holding qs[] and tg[]).
 //   FASTM : every score of the launch satisfies score * (match + 1) <= 32767, so the reference's
 //           M = Hd ? Hd + s : 0 is ONE instruction, min(Hd + s, Hd * (match + 1)) (the product on the
@@ -223,42 +280,47 @@ __device__ __forceinline__ int pair_band(const KParams &P, int qlen) {
 //   COUNT : also track the reference's exact leading trim and count the cells its scalar loop would
 //           visit (bandedSWA.cpp:191-216; the commented SW_cells++ at :215) -- the unit of work of
 //           the GCUPS metric. Used once per input outside any timed region.
-template <bool FASTM, bool SYM, bool COUNT>
+//   WIDE  : the pair may hold ambiguous bases (4-bit blob, LOP3 selector; see score_lut)
+template <bool FASTM, bool SYM, bool COUNT, bool WIDE>
 __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int h0, const KParams &P) {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
     const uint32_t NEG_E_DEL = pack2(-P.e_del), NEG_E_INS = pack2(-P.e_ins);
-    // PRMT look-up table: index 0 match, 1..3 mismatch, 4..7 ambiguous (low byte of the score; PRMT
-    // replicates its sign into the high byte of each lane)
-    const uint32_t LUT_LO = ((uint32_t)P.match & 0xFFu) | (((uint32_t)(-P.mismatch) & 0xFFu) * 0x01010100u);
-    const uint32_t LUT_HI = ((uint32_t)P.ambig & 0xFFu) * 0x01010101u;
+    uint32_t LUT_LO, LUT_HI;
+    score_lut<WIDE>(P, LUT_LO, LUT_HI);
 
-    // row "-1" (bandedSWA.cpp:159-161) and zeroed E; one spare column so the hi lane of the last
-    // word is always initialised
+    // row "-1" (bandedSWA.cpp:159-161) and zeroed E, over every element the row loop may touch
     {
-        const int nwords = ((qlen + 1) >> 1) + 1;
+        const int nel = row_elems(qlen);
         int hv = h0;
-        for (int g = 0; g < nwords; ++g) {
-            int a = hv;                                   // Hs[2g]
-            if (g == 0) hv = h0 > oe_ins ? h0 - oe_ins : 0;
-            else hv = max(hv - P.e_ins, 0);
-            int b = hv;                                   // Hs[2g+1]
-            hv = max(hv - P.e_ins, 0);
-            if (2 * g > qlen) a = 0;                      // the reference's calloc'ed tail
-            if (2 * g + 1 > qlen) b = 0;
-            R.HE(g) = make_uint2((uint32_t)a | ((uint32_t)b << 16), 0u);
+        for (int k = 0; k < nel; ++k) {
+            uint32_t w[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int g = 2 * k + u;
+                int a = hv;                                   // Hs[2g]
+                if (g == 0) hv = h0 > oe_ins ? h0 - oe_ins : 0;
+                else hv = max(hv - P.e_ins, 0);
+                int b = hv;                                   // Hs[2g+1]
+                hv = max(hv - P.e_ins, 0);
+                if (2 * g > qlen) a = 0;                      // the reference's calloc'ed tail
+                if (2 * g + 1 > qlen) b = 0;
+                w[u] = (uint32_t)a | ((uint32_t)b << 16);
+            }
+            uint4 v; v.x = w[0]; v.y = 0u; v.z = w[1]; v.w = 0u;
+            R.HE4(k) = v;
         }
     }
 
     const int band = pair_band(P, qlen);
     const int budget = min(qlen + band, tlen);
-    const uint32_t K16 = P.k16, KM = P.km;
+    const uint32_t K16 = P.k16, KM = P.km, K1 = P.k1;
 
     int best = h0, best_i = -1, best_j = -1, g_i = -1, gsc = -1, off = 0;
     int beg = 0, end = qlen;
     uint32_t tword = 0;
     int hcol = h0 - P.o_del;  // first column: H(i,-1) = max(h0 - o_del - e_del*(i+1), 0)
-    int xbeg = 0;             // COUNT: the reference's exact beg (ours lags it by whole words)
+    int xbeg = 0;             // COUNT: the reference's exact beg (ours lags it by up to 3 columns)
     uint32_t cells = 0;
 
     for (int i = 0; i < budget; ++i) {
@@ -271,32 +333,34 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         }
 
         if ((i & 7) == 0) tword = R.TG(i >> 3);
-        const uint32_t tsel = (tword & 7u) * 0x1111u + 0x8080u;   // (code * 0x11 | 0x80) in both bytes
+        // the row's target seed in both halves: nibbles c, c | 8 with c = 4 - code (narrow) / code (wide)
+        const uint32_t tsel = (tword & 7u) * 0x11111111u + 0x80808080u;
         tword >>= 4;
 
         hcol -= P.e_del;
         const int hleft = beg == 0 ? max(hcol, 0) : 0;
 
-        // Lanes outside [beg, end) of the first / last word must see zero inputs: clear the stale
-        // (never read again) entries instead of masking inside the loop.
-        if (beg & 1) R.zeroHE16(beg - 1);
-        if (end & 1) R.zeroHE16(end);
+        // The row is computed over whole groups starting at a 4-column boundary. Lanes outside
+        // [beg, end) must see zero inputs: instead of masking inside the loop, the stale (never read
+        // again) entry just left of beg is cleared -- everything further left, down to the boundary, is
+        // already zero (cleared by earlier rows while the band clamp moved beg one column per row, or
+        // zero when the leading trim moved beg, which it only does in steps of 4) -- and so is the
+        // entry at `end` when it shares a group with column end - 1.
+        if (beg & 3) R.setHE16(beg - 1, 0u, 0u);
+        if (end & 1) R.setHE16(end, 0u, 0u);
 
-        const int g0 = beg >> 1, g1 = (end - 1) >> 1;
+        const int g0 = (beg >> 2) << 1, g1 = (end - 1) >> 1;
         uint32_t hprev = (uint32_t)hleft << 16;  // .hi = H(i, 2*g0 - 1)
         uint32_t A = 0;                          // { F(i, 2g), 0 }
         uint32_t rm = 0;                         // running max per lane (even / odd columns)
-        int mjlo = -1, mjhi = -1;
+        int ilo = g0, ihi = g0;                  // last group of the block where a lane last reached rm
         uint32_t h = 0, En = 0, Hst = 0;
 
         // One group = columns (2g, 2g+1). Only the F scan is serial along the row; the scores, M, T
-        // and E' of different groups are independent. With 2-3 resident warps per scheduler the
-        // kernel is bound by dependency latency, so groups are processed four at a time: all loads
-        // first, then the independent parts of the four groups (interleavable), then the F chain.
-        auto front = [&](const uint2 he, const uint32_t qsel, uint32_t &M, uint32_t &Tins, uint32_t &Enew) {
-            const uint32_t Hd = he.x, Ev = he.y;
-            // k = q ^ t on bits 0-1 (and the sign-replicate bit), q | t on bit 2 (ambiguous)
-            const uint32_t sel = sel_combine(qsel, tsel, 0x4444u);
+        // and E' of different groups are independent. Groups are processed four at a time: loads
+        // first (2 x LDS.128 + 1 x LDS.64), then the independent parts, then the F chain.
+        auto front = [&](const uint32_t Hd, const uint32_t Ev, const uint32_t sel, uint32_t &M, uint32_t &Tins,
+                         uint32_t &Enew) {
             const uint32_t s = prmt_sx(LUT_LO, LUT_HI, sel);
             if (FASTM) {
                 M = __viaddmin_s16x2(Hd, s, Hd * KM);
@@ -308,41 +372,74 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             Tins = SYM ? Tdel : __viaddmax_s16x2_relu(M, NEG_OE_INS, NEG_OE_INS);
             Enew = __viaddmax_s16x2(Ev, NEG_E_DEL, Tdel);
         };
-        auto back = [&](const int g, const uint32_t Ev, const uint32_t M, const uint32_t Tins, const uint32_t Enew) {
+        // F scan of one group and its H; returns the word { H(i,2g-1), H(i,2g) } to store
+        auto back = [&](const uint32_t Ev, const uint32_t M, const uint32_t Tins) -> uint32_t {
             const uint32_t W1 = __viaddmax_s16x2(A, NEG_E_INS, Tins);   // .lo = F(i, 2g+1)
             const uint32_t B = W1 * K16 + A;                             // { F(2g), F(2g+1) }  (IMAD)
             h = __vimax3_s16x2(M, Ev, B);
             const uint32_t W2 = __viaddmax_s16x2(B, NEG_E_INS, Tins);   // .hi = F(i, 2g+2)
             A = __umulhi(W2, K16);                                       // W2 >> 16           (IMAD.HI)
-            Hst = __umulhi(hprev, K16) + h * K16;                        // { H(i,2g-1), H(i,2g) }
-            En = Enew;
-            R.HE(g) = make_uint2(Hst, En);
+            const uint32_t st = __umulhi(hprev, K16) + h * K16;          // { H(i,2g-1), H(i,2g) }
             hprev = h;
-            bool phi, plo;
-            rm = __vibmax_s16x2(h, rm, &phi, &plo);
-            if (plo) mjlo = g;
-            if (phi) mjhi = g;
+            return st;
         };
         int g = g0;
         for (; g + 3 <= g1; g += 4) {
-            const uint2 he0 = R.HE(g), he1 = R.HE(g + 1), he2 = R.HE(g + 2), he3 = R.HE(g + 3);
-            const uint32_t q0 = R.QS(g), q1 = R.QS(g + 1), q2 = R.QS(g + 2), q3 = R.QS(g + 3);
+            const int k = g >> 1;
+            const uint4 a = R.HE4(k), b = R.HE4(k + 1);
+            const uint32_t q01 = R.QS2(k), q23 = R.QS2(k + 1);
+            uint32_t s0, s1, s2, s3;
+            if (WIDE || BSW_SEL_LOP3) {
+                s0 = sel_combine(q01, tsel, 0x44444444u); s1 = __umulhi(s0, K16);
+                s2 = sel_combine(q23, tsel, 0x44444444u); s3 = __umulhi(s2, K16);
+            } else {
+                // tsel carries the row's seed in both halves: the upper half of the sum is group 1's selector
+                s0 = q01 * K1 + tsel; s1 = __umulhi(s0, K16);
+                s2 = q23 * K1 + tsel; s3 = __umulhi(s2, K16);
+            }
             uint32_t M0, M1, M2, M3, T0, T1, T2, T3, E0, E1, E2, E3;
-            front(he0, q0, M0, T0, E0);
-            front(he1, q1, M1, T1, E1);
-            front(he2, q2, M2, T2, E2);
-            front(he3, q3, M3, T3, E3);
-            back(g, he0.y, M0, T0, E0);
-            back(g + 1, he1.y, M1, T1, E1);
-            back(g + 2, he2.y, M2, T2, E2);
-            back(g + 3, he3.y, M3, T3, E3);
+            front(a.x, a.y, s0, M0, T0, E0);
+            front(a.z, a.w, s1, M1, T1, E1);
+            front(b.x, b.y, s2, M2, T2, E2);
+            front(b.z, b.w, s3, M3, T3, E3);
+            uint4 oa, ob;
+            oa.x = back(a.y, M0, T0); const uint32_t h0v = h;
+            oa.z = back(a.w, M1, T1); const uint32_t h1v = h;
+            ob.x = back(b.y, M2, T2); const uint32_t h2v = h;
+            ob.z = back(b.w, M3, T3);
+            oa.y = E0; oa.w = E1; ob.y = E2; ob.w = E3;
+            R.HE4(k) = oa;
+            R.HE4(k + 1) = ob;
+            Hst = ob.z; En = E3;
+#if BSW_HIER_ARGMAX
+            // row max per lane; only the block where a lane last reached it is recorded, the column
+            // is recovered after the row (see below)
+            const uint32_t bm = __vimax3_s16x2(h0v, h1v, __vmaxs2(h2v, h));
+            bool phi, plo;
+            rm = __vibmax_s16x2(bm, rm, &phi, &plo);
+            if (plo) ilo = g + 3;
+            if (phi) ihi = g + 3;
+#else
+            bool phi, plo;
+            rm = __vibmax_s16x2(h0v, rm, &phi, &plo); if (plo) ilo = g;     if (phi) ihi = g;
+            rm = __vibmax_s16x2(h1v, rm, &phi, &plo); if (plo) ilo = g + 1; if (phi) ihi = g + 1;
+            rm = __vibmax_s16x2(h2v, rm, &phi, &plo); if (plo) ilo = g + 2; if (phi) ihi = g + 2;
+            rm = __vibmax_s16x2(h, rm, &phi, &plo);   if (plo) ilo = g + 3; if (phi) ihi = g + 3;
+#endif
         }
         for (; g <= g1; ++g) {
             const uint2 he0 = R.HE(g);
-            const uint32_t q0 = R.QS(g);
+            const uint32_t q = R.QS(g);
+            const uint32_t s0 = (WIDE || BSW_SEL_LOP3) ? sel_combine(q, tsel, 0x44444444u) : q * K1 + tsel;
             uint32_t M0, T0, E0;
-            front(he0, q0, M0, T0, E0);
-            back(g, he0.y, M0, T0, E0);
+            front(he0.x, he0.y, s0, M0, T0, E0);
+            Hst = back(he0.y, M0, T0);
+            En = E0;
+            R.HE(g) = make_uint2(Hst, En);
+            bool phi, plo;
+            rm = __vibmax_s16x2(h, rm, &phi, &plo);
+            if (plo) ilo = g;
+            if (phi) ihi = g;
         }
 
         // last computed column's H, and the reference's eh[end] = { h1, 0 }
@@ -360,11 +457,31 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         const int mlo = (int)(short)(rm & 0xFFFFu), mhi = (int)(short)(rm >> 16);
         const int m = max(mlo, mhi);
         if (m == 0) break;
+        // LAST column reaching m
         int mj;
-        {
-            const int jlo = 2 * mjlo, jhi = 2 * mjhi + 1;
-            mj = mlo > mhi ? jlo : (mhi > mlo ? jhi : max(jlo, jhi));   // LAST column reaching m
+#if BSW_HIER_ARGMAX
+        // H(i, j) now sits in Hs[j + 1]; the lane's last >= event happened in the (at most four)
+        // groups ending at ilo / ihi, so the scan below stops within them.
+        // (the hi lane of the last group is column `end` when end is odd: never a candidate)
+        mj = -1;
+        if (mlo >= mhi) {
+            int gg = ilo;
+#pragma unroll 1
+            for (int t = 0; t < 3 && R.getH16(2 * gg + 1) != (uint32_t)mlo; ++t) --gg;
+            mj = 2 * gg;
         }
+        if (mhi >= mlo) {
+            int gg = min(ihi, (end - 2) >> 1);
+#pragma unroll 1
+            for (int t = 0; t < 3 && R.getH16(2 * gg + 2) != (uint32_t)mhi; ++t) --gg;
+            mj = max(mj, 2 * gg + 1);
+        }
+#else
+        {
+            const int jlo = 2 * ilo, jhi = 2 * ihi + 1;
+            mj = mlo > mhi ? jlo : (mhi > mlo ? jhi : max(jlo, jhi));
+        }
+#endif
         if (m > best) {
             best = m; best_i = i; best_j = mj;
             off = max(off, abs(mj - i));
@@ -379,10 +496,10 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             while (j < end && R.getH16(j) == 0 && R.getE16(j) == 0) ++j;
             xbeg = j;
         }
-        // leading trim (not semantic: skipped cells are all-zero; done lazily, one word every 4th row)
-        if ((i & 3) == 3) {
-            const uint2 z = R.HE(g0);
-            if ((z.x | z.y) == 0u && 2 * (g0 + 1) > beg) beg = 2 * (g0 + 1);
+        // leading trim (not semantic: skipped cells are all-zero; done lazily, four columns at a time)
+        if ((i & (BSW_TRIM_EVERY - 1)) == BSW_TRIM_EVERY - 1) {
+            const uint4 z = R.HE4(g0 >> 1);
+            if ((z.x | z.y | z.z | z.w) == 0u && 2 * g0 + 4 > beg) beg = 2 * g0 + 4;
         }
         // trailing trim (semantic): j* = last j in [beg,end] with Hs[j] | E[j] != 0 (m > 0
         // guarantees one exists); the new end is min(j* + 2, qlen). Hs[end] = H(i,end-1) is almost
@@ -395,14 +512,14 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             if (end & 1) jstar = (Wt & 0xFFFFu) ? end - 1 : -1;
             else jstar = (Wt >> 16) ? end - 1 : ((Wt & 0xFFFFu) ? end - 2 : -1);
             if (jstar < 0) {
-                int g = g1 - 1;
+                int gz = g1 - 1;
                 uint32_t wz = 0;
-                for (; g >= 0; --g) {
-                    const uint2 z = R.HE(g);
+                for (; gz >= 0; --gz) {
+                    const uint2 z = R.HE(gz);
                     wz = z.x | z.y;
                     if (wz) break;
                 }
-                jstar = (wz >> 16) ? 2 * g + 1 : 2 * g;
+                jstar = (wz >> 16) ? 2 * gz + 1 : 2 * gz;
             }
             end = min(jstar + 2, qlen);
         }
@@ -425,66 +542,89 @@ __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const Pa
 }
 
 // ---------------------------------------------------------------------------------------------
-// Short pairs: rows in shared memory. Launch: grid = ceil(n / kBlockPairs), block = kBlockPairs,
-// dynamic smem = (8*row_words + 2*qs_words + 4*tg_words) * NT.
-//   meta[k] for k in [0, n): this launch's pairs in sorted (length-binned) order; blob = the slab's
-//   packed sequences. Each thread expands its own 16-byte aligned slot straight from global memory
-//   (a few dozen bytes per pair, read once; the host packs slots in the caller's order so that its
-//   own pass is a pure stream -- see DESIGN.md).
+// Short pairs: rows in shared memory. Launch: block = kBlockPairs threads, dynamic smem =
+// (16*row_el + 4*qs_words + 4*tg_words) * NT.
+//   meta[0 .. n_wide + n_narrow): this launch's pairs in sorted (length-binned) order, the n_wide pairs
+//   holding an ambiguous base first. Threads [0, roundup32(n_wide)) take the wide pairs, the threads
+//   after them the narrow ones, so every WARP runs one instantiation of the DP (no divergence between
+//   the LOP3-selector and the add-selector code). blob = the slab's packed sequences: each thread
+//   expands its own 16-byte aligned slot straight from global memory (a few dozen bytes per pair, read
+//   once; the host packs slots in the caller's order so that its own pass is a pure stream -- see
+//   DESIGN.md). A wide pair's slot holds the word offset of its 4-bit blob in the slab's overflow area.
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int launch_threads(int n_wide, int n_narrow) { return ((n_wide + 31) & ~31) + n_narrow; }
+
 template <bool FASTM, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
-                 PairOut *__restrict__ out, int n, KParams P, int row_words, int qs_words,
+                 PairOut *__restrict__ out, int n_wide, int n_narrow, KParams P, int row_el, int qs_words,
                  int tg_words) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NT = kBlockPairs;
     const int tid = threadIdx.x;
-    const int k = blockIdx.x * NT + tid;
-    if (k >= n) return;
+    const int t = blockIdx.x * NT + tid;
+    const int nwr = (n_wide + 31) & ~31;
+    const bool wide = t < nwr;                       // warp-uniform
+    const int k = wide ? t : t - nwr + n_wide;
+    if (wide ? t >= n_wide : k >= n_wide + n_narrow) return;
     const PairMeta m = meta[k];
 
     Rows R;
     R.stride = NT;
-    R.he = reinterpret_cast<uint2 *>(smem) + tid;
-    R.qs = reinterpret_cast<uint16_t *>(smem + (size_t)8 * row_words * NT) + tid;
-    R.tg = reinterpret_cast<uint32_t *>(smem + (size_t)8 * row_words * NT + (size_t)2 * qs_words * NT) + tid;
+    R.he4 = reinterpret_cast<uint4 *>(smem) + tid;
+    R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)16 * row_el * NT) + tid;
+    R.tg = reinterpret_cast<uint32_t *>(smem + (size_t)16 * row_el * NT + (size_t)4 * qs_words * NT) + tid;
     (void)tg_words;
 
-    // a wide pair's slot only holds the word offset of its 4-bit blob in the overflow area
     const uint32_t *src = blob + m.off;
-    if (m.flags & 1) src = blob + src[0];
-    unpack_pair(src, m.len2, m.len1, m.flags & 1, R);
-
-    PairResult r = extend_pair<FASTM, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
+    PairResult r;
+    if (wide) {
+        src = blob + src[0];
+        unpack_pair<true>(src, m.len2, m.len1, R);
+        r = extend_pair<FASTM, SYM, COUNT, true>(R, m.len2, m.len1, m.h0, P);
+    } else {
+        unpack_pair<false>(src, m.len2, m.len1, R);
+        r = extend_pair<FASTM, SYM, COUNT, false>(R, m.len2, m.len1, m.h0, P);
+    }
     store_result(out, m.id, r);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Long pairs (rows do not fit the shared-memory bins): same per-pair code over a global scratch,
 // interleaved by thread across the whole grid so neighbouring threads touch neighbouring words.
-//   scratch layout: he[row_words][nthreads] (uint2) | qs[qs_words][nthreads] (u16, padded to 4 B)
-//                   | tg[tg_words][nthreads] (u32)
+//   scratch layout: he4[row_el][nthreads] (uint4) | qs[qs_words][nthreads] (u32) | tg[tg_words][nthreads] (u32)
 // ---------------------------------------------------------------------------------------------
 template <bool FASTM, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
-                PairOut *__restrict__ out, int n, KParams P, int row_words, int qs_words,
+                PairOut *__restrict__ out, int n_wide, int n_narrow, KParams P, int row_el, int qs_words,
                 int tg_words, unsigned char *__restrict__ scratch) {
     const int nthreads = gridDim.x * blockDim.x;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nwr = (n_wide + 31) & ~31;
+    const bool wide = t < nwr;
+    const int k = wide ? t : t - nwr + n_wide;
+    if (wide ? t >= n_wide : k >= n_wide + n_narrow) return;
     const PairMeta m = meta[k];
     Rows R;
     R.stride = nthreads;
     unsigned char *p = scratch;
-    R.he = reinterpret_cast<uint2 *>(p) + k;
-    p += (size_t)8 * row_words * nthreads;
-    R.qs = reinterpret_cast<uint16_t *>(p) + k;
-    p += (((size_t)2 * qs_words * nthreads) + 15) & ~(size_t)15;
-    R.tg = reinterpret_cast<uint32_t *>(p) + k;
-    unpack_pair((m.flags & 1) ? blob + blob[m.off] : blob + m.off, m.len2, m.len1, m.flags & 1, R);
-    PairResult r = extend_pair<FASTM, SYM, COUNT>(R, m.len2, m.len1, m.h0, P);
+    R.he4 = reinterpret_cast<uint4 *>(p) + t;
+    p += (size_t)16 * row_el * nthreads;
+    R.qs = reinterpret_cast<uint32_t *>(p) + t;
+    p += (size_t)4 * qs_words * nthreads;
+    R.tg = reinterpret_cast<uint32_t *>(p) + t;
+    (void)tg_words;
+    const uint32_t *src = blob + m.off;
+    PairResult r;
+    if (wide) {
+        src = blob + src[0];
+        unpack_pair<true>(src, m.len2, m.len1, R);
+        r = extend_pair<FASTM, SYM, COUNT, true>(R, m.len2, m.len1, m.h0, P);
+    } else {
+        unpack_pair<false>(src, m.len2, m.len1, R);
+        r = extend_pair<FASTM, SYM, COUNT, false>(R, m.len2, m.len1, m.h0, P);
+    }
     store_result(out, m.id, r);
 }
 

@@ -28,6 +28,9 @@ static inline int wrap16(int v) { return (int16_t)(uint16_t)v; }
 static inline uint32_t __vmins2(uint32_t a, uint32_t b) {
     return emul::pk(std::min(emul::lo(a), emul::lo(b)), std::min(emul::hi(a), emul::hi(b)));
 }
+static inline uint32_t __vmaxs2(uint32_t a, uint32_t b) {
+    return emul::pk(std::max(emul::lo(a), emul::lo(b)), std::max(emul::hi(a), emul::hi(b)));
+}
 static inline uint32_t __vadd2(uint32_t a, uint32_t b) {  // per-halfword wrapping add
     return emul::pk(emul::lo(a) + emul::lo(b), emul::hi(a) + emul::hi(b));
 }

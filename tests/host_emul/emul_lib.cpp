@@ -13,13 +13,12 @@ using namespace bswk;
 extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
                               const uint8_t *qer, int64_t n, int32_t w) {
     KParams K{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w,
-              max_score_of(p->match, p->mismatch, p->ambig), 65536u, (uint32_t)(p->match + 1)};
+              max_score_of(p->match, p->mismatch, p->ambig), 65536u, (uint32_t)(p->match + 1), 1u};
     const bool sym = p->o_del == p->o_ins && p->e_del == p->e_ins;
 #pragma omp parallel
     {
-        std::vector<uint2> he;
-        std::vector<uint16_t> qs;
-        std::vector<uint32_t> tg, blob;
+        std::vector<uint4> he;
+        std::vector<uint32_t> qs, tg, blob;
 #pragma omp for schedule(dynamic, 256)
         for (int64_t k = 0; k < n; ++k) {
             bsw_seqpair &sp = pairs[k];
@@ -27,8 +26,8 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
                 sp.score = sp.h0; sp.qle = sp.tle = sp.gtle = 0; sp.gscore = -1; sp.max_off = 0;
                 continue;
             }
-            he.assign((size_t)((sp.len2 + 1) / 2 + 6), uint2{0xDEADBEEFu, 0xDEADBEEFu});
-            qs.assign((size_t)((sp.len2 + 1) / 2 + 6), 0xDEAD);
+            he.assign((size_t)row_elems(sp.len2), uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+            qs.assign((size_t)sel_words(sp.len2), 0xDEADBEEFu);
             tg.assign((size_t)((sp.len1 + 7) / 8 + 1), 0xDEADBEEFu);
             blob.assign((size_t)(seq_bytes(sp.len2, true) + seq_bytes(sp.len1, true)) / 4 + 4, 0);
             uint8_t *b = reinterpret_cast<uint8_t *>(blob.data());
@@ -39,13 +38,15 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
                 pack4bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, true));
             }
             Rows R{he.data(), qs.data(), tg.data(), 1};
-            unpack_pair(blob.data(), sp.len2, sp.len1, wide, R);
+            if (wide) unpack_pair<true>(blob.data(), sp.len2, sp.len1, R);
+            else unpack_pair<false>(blob.data(), sp.len2, sp.len1, R);
             PairResult r;
             const bool m1 = (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767 && !getenv("BSW_EMUL_SLOWM");
-            if (m1) r = sym ? extend_pair<true, true, true>(R, sp.len2, sp.len1, sp.h0, K)
-                            : extend_pair<true, false, true>(R, sp.len2, sp.len1, sp.h0, K);
-            else r = sym ? extend_pair<false, true, true>(R, sp.len2, sp.len1, sp.h0, K)
-                         : extend_pair<false, false, true>(R, sp.len2, sp.len1, sp.h0, K);
+#define EP(F, S) (wide ? extend_pair<F, S, true, true>(R, sp.len2, sp.len1, sp.h0, K) \
+                  : extend_pair<F, S, true, false>(R, sp.len2, sp.len1, sp.h0, K))
+            if (m1) r = sym ? EP(true, true) : EP(true, false);
+            else r = sym ? EP(false, true) : EP(false, false);
+#undef EP
             sp.score = r.score; sp.qle = r.qle; sp.tle = r.tle; sp.gtle = r.gtle;
             sp.gscore = r.gscore; sp.max_off = r.max_off;
             sp.seqid = (int32_t)r.cells;   // test hook: cell count of the COUNT variant
