@@ -45,7 +45,7 @@ struct Launch {
     int first;       // first sorted position
     int n;           // pairs (the n_wide pairs holding an ambiguous base come first)
     int n_wide;
-    int row_el, qs_words, tg_words;   // per pair: uint4 row elements, u32 selector words, u32 target words
+    int row_el, qs_words;   // per pair: uint4 row elements, u32 selector words
     size_t smem;     // 0 => long kernel
     int64_t work;    // sum len1*len2, for ordering
 };
@@ -179,8 +179,8 @@ int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
 
 // ---- host: per-slab preparation ----------------------------------------------------------------
 
-inline size_t smem_need(int row_el, int qs_words, int tg_words) {
-    return ((size_t)16 * row_el + (size_t)4 * qs_words + (size_t)4 * tg_words) * kBlockPairs;
+inline size_t smem_need(int row_el, int qs_words) {
+    return ((size_t)16 * row_el + (size_t)4 * qs_words) * kBlockPairs;
 }
 
 // Stable parallel counting sort of `in` (indices) by key[in[.]] < nkeys into `out`.
@@ -427,8 +427,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             L.first = p; L.n = nw + nn; L.n_wide = nw; L.work = (int64_t)(nw + nn) * q_hi * t_hi;
             L.row_el = row_elems(q_hi);
             L.qs_words = sel_words(q_hi);
-            L.tg_words = (t_hi + 7) >> 3;
-            L.smem = smem_need(L.row_el, L.qs_words, L.tg_words);
+            L.smem = smem_need(L.row_el, L.qs_words);
             if (L.smem > kMaxSmem) L.smem = 0;  // long kernel
             s.launches.push_back(L);
             p += nw + nn;
@@ -451,8 +450,8 @@ int ensure_aux(bsw_handle *h, Device &dev) {
 }
 
 // The kernel instantiations, indexed [fastm][sym][count].
-typedef void (*ShortFn)(const PairMeta *, const uint32_t *, PairOut *, int, int, KParams, int, int, int);
-typedef void (*LongFn)(const PairMeta *, const uint32_t *, PairOut *, int, int, KParams, int, int, int, unsigned char *);
+typedef void (*ShortFn)(const PairMeta *, const uint32_t *, PairOut *, int, int, KParams, int, int);
+typedef void (*LongFn)(const PairMeta *, const uint32_t *, PairOut *, int, int, KParams, int, int, unsigned char *);
 template <int I> struct KernelTable {
     static void fill(ShortFn *sf, LongFn *lf) {
         sf[I] = bsw_short_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
@@ -482,7 +481,7 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
         for (const Launch &L : s.launches) {
             if (L.smem) continue;
             const size_t nthreads = (size_t)((launch_threads(L.n_wide, L.n - L.n_wide) + kBlockPairs - 1) / kBlockPairs) * kBlockPairs;
-            need = std::max(need, ((size_t)16 * L.row_el + (size_t)4 * L.qs_words + (size_t)4 * L.tg_words) * nthreads + 256);
+            need = std::max(need, ((size_t)16 * L.row_el + (size_t)4 * L.qs_words) * nthreads + 256);
         }
         if (need > s.cap_scratch) {
             CU(cudaDeviceSynchronize());
@@ -507,11 +506,11 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                 }
                 cudaStream_t st = dev.aux[rr++ % kAux];
                 short_fn[ki]<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta + L.first, s.d_blob, s.d_out, L.n_wide,
-                                                                L.n - L.n_wide, h->K, L.row_el, L.qs_words, L.tg_words);
+                                                                L.n - L.n_wide, h->K, L.row_el, L.qs_words);
             } else {
                 long_fn[ki]<<<grid, kBlockPairs, 0, dev.aux[0]>>>(
                     s.d_meta + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.row_el, L.qs_words,
-                    L.tg_words, s.d_scratch);
+                    s.d_scratch);
             }
             CU(cudaGetLastError());
             h->stats.kernel_launches++;

@@ -31,6 +31,12 @@
 #ifndef BSW_TRIM_EVERY    // leading trim every N-th row (power of two)
 #define BSW_TRIM_EVERY 1
 #endif
+#ifndef BSW_SCALAR_F      // F chain as two scalar VIADDMNMX per group (T lanes split on the FMA pipe)
+#define BSW_SCALAR_F 0
+#endif
+#ifndef BSW_PREFETCH      // issue the next block's loads before computing the current block
+#define BSW_PREFETCH 1
+#endif
 #ifndef BSW_ST_SHARED     // 16-bit row stores through st.shared (short kernel only)
 #define BSW_ST_SHARED 0
 #endif
@@ -105,12 +111,12 @@ __device__ __forceinline__ uint32_t pack2(int v) {
 //            with Hs[j] = H(i-1, j-1) (eh[j].h) and E[j] = E(i, j) (eh[j].e), int16 each;
 //            element k of this thread lives at he4[k * stride]                      (LDS/STS.128)
 //   qs[k]  : u32 = the PRMT selector seeds of query columns 4k .. 4k+3 (16 bits per group)
-//   tg[w]  : target bases, 4 bits each, 8 per word (narrow pairs store 4 - code, see unpack_pair)
+//   tb     : the pair's PACKED target in the slab blob (global memory, read 8 rows at a time)
 // ---------------------------------------------------------------------------------------------
 struct Rows {
     uint4 *he4;
     uint32_t *qs;
-    uint32_t *tg;
+    const uint32_t *tb;
     int stride;  // threads sharing the arrays (blockDim for shared memory, grid-wide for global)
     __device__ __forceinline__ uint4 &HE4(int k) const { return he4[(size_t)k * stride]; }
     // group g = columns (2g, 2g+1): the .xy or .zw half of element g >> 1
@@ -153,7 +159,18 @@ struct Rows {
         const uint32_t w = QS2(g >> 1);
         return (g & 1) ? (w >> 16) : (w & 0xFFFFu);
     }
-    __device__ __forceinline__ uint32_t &TG(int w) const { return tg[(size_t)w * stride]; }
+    // target bases of rows 8w .. 8w+7 as 8 nibbles: 4 - code for narrow pairs (see score_lut), the
+    // code itself for wide pairs
+    template <bool WIDE>
+    __device__ __forceinline__ uint32_t TG(int w) const {
+        if (WIDE) return tb[w];
+        uint32_t x = tb[w >> 1];
+        x = (w & 1) ? (x >> 16) : (x & 0xFFFFu);   // 8 bases, 2 bits each
+        x = (x | (x << 8)) & 0x00FF00FFu;
+        x = (x | (x << 4)) & 0x0F0F0F0Fu;
+        x = (x | (x << 2)) & 0x33333333u;           // -> 8 nibbles
+        return BSW_SEL_LOP3 ? x : 0x44444444u - x;  // never borrows
+    }
 };
 
 // PTX prmt.b32 (default mode): byte i of the result = byte (nibble_i & 7) of {b:a}; nibble bit 3 set
@@ -200,12 +217,12 @@ __device__ __forceinline__ void score_lut(const KParams &P, uint32_t &lo, uint32
     }
 }
 
-// Expands this thread's packed blob (4-byte words: query then target, each padded to 4 bytes) into
-// qs[] / tg[]. Narrow blobs hold 2 bits per base, wide blobs 4 bits per base.
+// Expands the query of this thread's packed blob (4-byte words: query then target, each padded to 4
+// bytes) into qs[] and points R.tb at the target. Narrow blobs hold 2 bits per base, wide blobs 4.
 template <bool WIDE>
-__device__ inline void unpack_pair(const uint32_t *blob, int qlen, int tlen, const Rows &R) {
+__device__ inline void unpack_pair(const uint32_t *blob, int qlen, Rows &R) {
+    R.tb = blob + (seq_bytes((uint32_t)qlen, WIDE) >> 2);
     const int nsel = (((qlen + 1) >> 1) + 1) >> 1;   // selector words: two groups each (== sel_words)
-    const int twords = (tlen + 7) >> 3;
     if (!WIDE) {
         // 16 bases per word -> 8 groups -> 4 selector words; a base b becomes the byte b * 0x11
         for (int w = 0, k = 0; k < nsel; ++w) {
@@ -219,15 +236,6 @@ __device__ inline void unpack_pair(const uint32_t *blob, int qlen, int tlen, con
                     R.QS2(k) = v * 0x11u;
                 }
             }
-        }
-        const uint32_t *tb = blob + (seq_bytes(qlen, false) >> 2);
-        for (int w = 0; w < twords; ++w) {
-            uint32_t x = tb[w >> 1];
-            x = (w & 1) ? (x >> 16) : (x & 0xFFFFu);   // 8 bases, 2 bits each
-            x = (x | (x << 8)) & 0x00FF00FFu;
-            x = (x | (x << 4)) & 0x0F0F0F0Fu;
-            x = (x | (x << 2)) & 0x33333333u;           // -> 8 nibbles
-            R.TG(w) = BSW_SEL_LOP3 ? x : 0x44444444u - x;   // nibble = 4 - code (never borrows)
         }
     } else {
         // 8 bases per word -> 4 groups -> 2 selector words
@@ -243,8 +251,6 @@ __device__ inline void unpack_pair(const uint32_t *blob, int qlen, int tlen, con
                 }
             }
         }
-        const uint32_t *tb = blob + (seq_bytes(qlen, true) >> 2);
-        for (int w = 0; w < twords; ++w) R.TG(w) = tb[w];
     }
 }
 
@@ -285,7 +291,9 @@ template <bool FASTM, bool SYM, bool COUNT, bool WIDE>
 __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int h0, const KParams &P) {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
-    const uint32_t NEG_E_DEL = pack2(-P.e_del), NEG_E_INS = pack2(-P.e_ins);
+    const uint32_t NEG_E_DEL = pack2(-P.e_del);
+    const int NEG_E_INS_S = -P.e_ins;
+    const uint32_t NEG_E_INS = pack2(-P.e_ins);
     uint32_t LUT_LO, LUT_HI;
     score_lut<WIDE>(P, LUT_LO, LUT_HI);
 
@@ -332,7 +340,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             cells += (uint32_t)(end - xbeg);
         }
 
-        if ((i & 7) == 0) tword = R.TG(i >> 3);
+        if ((i & 7) == 0) tword = R.template TG<WIDE>(i >> 3);
         // the row's target seed in both halves: nibbles c, c | 8 with c = 4 - code (narrow) / code (wide)
         const uint32_t tsel = (tword & 7u) * 0x11111111u + 0x80808080u;
         tword >>= 4;
@@ -351,14 +359,15 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
 
         const int g0 = (beg >> 2) << 1, g1 = (end - 1) >> 1;
         uint32_t hprev = (uint32_t)hleft << 16;  // .hi = H(i, 2*g0 - 1)
-        uint32_t A = 0;                          // { F(i, 2g), 0 }
+        int F = 0;                               // F(i, 2g), a plain int: the only serial chain of the row
         uint32_t rm = 0;                         // running max per lane (even / odd columns)
-        int ilo = g0, ihi = g0;                  // last group of the block where a lane last reached rm
+        int ilo = g0, ihi = g0;                  // last group where a lane reached rm
         uint32_t h = 0, En = 0, Hst = 0;
 
-        // One group = columns (2g, 2g+1). Only the F scan is serial along the row; the scores, M, T
-        // and E' of different groups are independent. Groups are processed four at a time: loads
-        // first (2 x LDS.128 + 1 x LDS.64), then the independent parts, then the F chain.
+        // One group = columns (2g, 2g+1). The scores, M, T and E' of different groups are independent;
+        // only F runs along the row, as TWO dependent scalar VIADDMNMX per group (the T lanes are split
+        // off the chain on the FMA pipe). Groups are processed four at a time; the loads of the next
+        // four (2 x LDS.128 + 2 x LDS.32) are issued before the current four are computed.
         auto front = [&](const uint32_t Hd, const uint32_t Ev, const uint32_t sel, uint32_t &M, uint32_t &Tins,
                          uint32_t &Enew) {
             const uint32_t s = prmt_sx(LUT_LO, LUT_HI, sel);
@@ -374,58 +383,73 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         };
         // F scan of one group and its H; returns the word { H(i,2g-1), H(i,2g) } to store
         auto back = [&](const uint32_t Ev, const uint32_t M, const uint32_t Tins) -> uint32_t {
+#if BSW_SCALAR_F
+            const int tlo = (int)__umulhi(Tins * K16, K16);              // T(2g)   (T >= 0; two IMADs)
+            const int thi = (int)__umulhi(Tins, K16);                    // T(2g+1)
+            const int F1 = __viaddmax_s32(F, NEG_E_INS_S, tlo);          // F(i, 2g+1)
+            const uint32_t B = (uint32_t)F1 * K16 + (uint32_t)F;         // { F(2g), F(2g+1) }  (IMAD)
+            F = __viaddmax_s32(F1, NEG_E_INS_S, thi);                    // F(i, 2g+2)
+#else
+            const uint32_t A = (uint32_t)F;                              // { F(2g), 0 }
             const uint32_t W1 = __viaddmax_s16x2(A, NEG_E_INS, Tins);   // .lo = F(i, 2g+1)
             const uint32_t B = W1 * K16 + A;                             // { F(2g), F(2g+1) }  (IMAD)
-            h = __vimax3_s16x2(M, Ev, B);
             const uint32_t W2 = __viaddmax_s16x2(B, NEG_E_INS, Tins);   // .hi = F(i, 2g+2)
-            A = __umulhi(W2, K16);                                       // W2 >> 16           (IMAD.HI)
+            F = (int)__umulhi(W2, K16);                                  // W2 >> 16           (IMAD.HI)
+#endif
+            h = __vimax3_s16x2(M, Ev, B);
             const uint32_t st = __umulhi(hprev, K16) + h * K16;          // { H(i,2g-1), H(i,2g) }
             hprev = h;
             return st;
         };
         int g = g0;
-        for (; g + 3 <= g1; g += 4) {
-            const int k = g >> 1;
-            const uint4 a = R.HE4(k), b = R.HE4(k + 1);
-            const uint32_t q01 = R.QS2(k), q23 = R.QS2(k + 1);
-            uint32_t s0, s1, s2, s3;
-            if (WIDE || BSW_SEL_LOP3) {
-                s0 = sel_combine(q01, tsel, 0x44444444u); s1 = __umulhi(s0, K16);
-                s2 = sel_combine(q23, tsel, 0x44444444u); s3 = __umulhi(s2, K16);
-            } else {
-                // tsel carries the row's seed in both halves: the upper half of the sum is group 1's selector
-                s0 = q01 * K1 + tsel; s1 = __umulhi(s0, K16);
-                s2 = q23 * K1 + tsel; s3 = __umulhi(s2, K16);
-            }
-            uint32_t M0, M1, M2, M3, T0, T1, T2, T3, E0, E1, E2, E3;
-            front(a.x, a.y, s0, M0, T0, E0);
-            front(a.z, a.w, s1, M1, T1, E1);
-            front(b.x, b.y, s2, M2, T2, E2);
-            front(b.z, b.w, s3, M3, T3, E3);
-            uint4 oa, ob;
-            oa.x = back(a.y, M0, T0); const uint32_t h0v = h;
-            oa.z = back(a.w, M1, T1); const uint32_t h1v = h;
-            ob.x = back(b.y, M2, T2); const uint32_t h2v = h;
-            ob.z = back(b.w, M3, T3);
-            oa.y = E0; oa.w = E1; ob.y = E2; ob.w = E3;
-            R.HE4(k) = oa;
-            R.HE4(k + 1) = ob;
-            Hst = ob.z; En = E3;
-#if BSW_HIER_ARGMAX
-            // row max per lane; only the block where a lane last reached it is recorded, the column
-            // is recovered after the row (see below)
-            const uint32_t bm = __vimax3_s16x2(h0v, h1v, __vmaxs2(h2v, h));
-            bool phi, plo;
-            rm = __vibmax_s16x2(bm, rm, &phi, &plo);
-            if (plo) ilo = g + 3;
-            if (phi) ihi = g + 3;
-#else
-            bool phi, plo;
-            rm = __vibmax_s16x2(h0v, rm, &phi, &plo); if (plo) ilo = g;     if (phi) ihi = g;
-            rm = __vibmax_s16x2(h1v, rm, &phi, &plo); if (plo) ilo = g + 1; if (phi) ihi = g + 1;
-            rm = __vibmax_s16x2(h2v, rm, &phi, &plo); if (plo) ilo = g + 2; if (phi) ihi = g + 2;
-            rm = __vibmax_s16x2(h, rm, &phi, &plo);   if (plo) ilo = g + 3; if (phi) ihi = g + 3;
-#endif
+        if (g + 3 <= g1) {
+            uint4 a = R.HE4(g >> 1), b = R.HE4((g >> 1) + 1);
+            uint32_t q01 = R.QS2(g >> 1), q23 = R.QS2((g >> 1) + 1);
+            bool more;
+            do {
+                const int k = g >> 1;
+                more = g + 7 <= g1;
+                uint4 na = a, nb = b;
+                uint32_t nq01 = q01, nq23 = q23;
+                if (BSW_PREFETCH && more) {
+                    na = R.HE4(k + 2); nb = R.HE4(k + 3);
+                    nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
+                }
+                uint32_t s0, s1, s2, s3;
+                if (WIDE || BSW_SEL_LOP3) {
+                    s0 = sel_combine(q01, tsel, 0x44444444u); s1 = __umulhi(s0, K16);
+                    s2 = sel_combine(q23, tsel, 0x44444444u); s3 = __umulhi(s2, K16);
+                } else {
+                    // tsel carries the row's seed in both halves: the upper half of the sum is group 1's selector
+                    s0 = q01 * K1 + tsel; s1 = __umulhi(s0, K16);
+                    s2 = q23 * K1 + tsel; s3 = __umulhi(s2, K16);
+                }
+                uint32_t M0, M1, M2, M3, T0, T1, T2, T3, E0, E1, E2, E3;
+                front(a.x, a.y, s0, M0, T0, E0);
+                front(a.z, a.w, s1, M1, T1, E1);
+                front(b.x, b.y, s2, M2, T2, E2);
+                front(b.z, b.w, s3, M3, T3, E3);
+                uint4 oa, ob;
+                oa.x = back(a.y, M0, T0); const uint32_t h0v = h;
+                oa.z = back(a.w, M1, T1); const uint32_t h1v = h;
+                ob.x = back(b.y, M2, T2); const uint32_t h2v = h;
+                ob.z = back(b.w, M3, T3);
+                oa.y = E0; oa.w = E1; ob.y = E2; ob.w = E3;
+                R.HE4(k) = oa;
+                R.HE4(k + 1) = ob;
+                Hst = ob.z; En = E3;
+                bool phi, plo;
+                rm = __vibmax_s16x2(h0v, rm, &phi, &plo); if (plo) ilo = g;     if (phi) ihi = g;
+                rm = __vibmax_s16x2(h1v, rm, &phi, &plo); if (plo) ilo = g + 1; if (phi) ihi = g + 1;
+                rm = __vibmax_s16x2(h2v, rm, &phi, &plo); if (plo) ilo = g + 2; if (phi) ihi = g + 2;
+                rm = __vibmax_s16x2(h, rm, &phi, &plo);   if (plo) ilo = g + 3; if (phi) ihi = g + 3;
+                if (!BSW_PREFETCH && more) {
+                    na = R.HE4(k + 2); nb = R.HE4(k + 3);
+                    nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
+                }
+                a = na; b = nb; q01 = nq01; q23 = nq23;
+                g += 4;
+            } while (more);
         }
         for (; g <= g1; ++g) {
             const uint2 he0 = R.HE(g);
@@ -543,7 +567,7 @@ __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const Pa
 
 // ---------------------------------------------------------------------------------------------
 // Short pairs: rows in shared memory. Launch: block = kBlockPairs threads, dynamic smem =
-// (16*row_el + 4*qs_words + 4*tg_words) * NT.
+// (16*row_el + 4*qs_words) * NT.
 //   meta[0 .. n_wide + n_narrow): this launch's pairs in sorted (length-binned) order, the n_wide pairs
 //   holding an ambiguous base first. Threads [0, roundup32(n_wide)) take the wide pairs, the threads
 //   after them the narrow ones, so every WARP runs one instantiation of the DP (no divergence between
@@ -557,8 +581,7 @@ __host__ __device__ inline int launch_threads(int n_wide, int n_narrow) { return
 template <bool FASTM, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
-                 PairOut *__restrict__ out, int n_wide, int n_narrow, KParams P, int row_el, int qs_words,
-                 int tg_words) {
+                 PairOut *__restrict__ out, int n_wide, int n_narrow, KParams P, int row_el, int qs_words) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NT = kBlockPairs;
     const int tid = threadIdx.x;
@@ -573,17 +596,16 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     R.stride = NT;
     R.he4 = reinterpret_cast<uint4 *>(smem) + tid;
     R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)16 * row_el * NT) + tid;
-    R.tg = reinterpret_cast<uint32_t *>(smem + (size_t)16 * row_el * NT + (size_t)4 * qs_words * NT) + tid;
-    (void)tg_words;
+    (void)qs_words;
 
     const uint32_t *src = blob + m.off;
     PairResult r;
     if (wide) {
         src = blob + src[0];
-        unpack_pair<true>(src, m.len2, m.len1, R);
+        unpack_pair<true>(src, m.len2, R);
         r = extend_pair<FASTM, SYM, COUNT, true>(R, m.len2, m.len1, m.h0, P);
     } else {
-        unpack_pair<false>(src, m.len2, m.len1, R);
+        unpack_pair<false>(src, m.len2, R);
         r = extend_pair<FASTM, SYM, COUNT, false>(R, m.len2, m.len1, m.h0, P);
     }
     store_result(out, m.id, r);
@@ -592,13 +614,13 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
 // ---------------------------------------------------------------------------------------------
 // Long pairs (rows do not fit the shared-memory bins): same per-pair code over a global scratch,
 // interleaved by thread across the whole grid so neighbouring threads touch neighbouring words.
-//   scratch layout: he4[row_el][nthreads] (uint4) | qs[qs_words][nthreads] (u32) | tg[tg_words][nthreads] (u32)
+//   scratch layout: he4[row_el][nthreads] (uint4) | qs[qs_words][nthreads] (u32)
 // ---------------------------------------------------------------------------------------------
 template <bool FASTM, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
                 PairOut *__restrict__ out, int n_wide, int n_narrow, KParams P, int row_el, int qs_words,
-                int tg_words, unsigned char *__restrict__ scratch) {
+                unsigned char *__restrict__ scratch) {
     const int nthreads = gridDim.x * blockDim.x;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nwr = (n_wide + 31) & ~31;
@@ -612,17 +634,15 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     R.he4 = reinterpret_cast<uint4 *>(p) + t;
     p += (size_t)16 * row_el * nthreads;
     R.qs = reinterpret_cast<uint32_t *>(p) + t;
-    p += (size_t)4 * qs_words * nthreads;
-    R.tg = reinterpret_cast<uint32_t *>(p) + t;
-    (void)tg_words;
+    (void)qs_words;
     const uint32_t *src = blob + m.off;
     PairResult r;
     if (wide) {
         src = blob + src[0];
-        unpack_pair<true>(src, m.len2, m.len1, R);
+        unpack_pair<true>(src, m.len2, R);
         r = extend_pair<FASTM, SYM, COUNT, true>(R, m.len2, m.len1, m.h0, P);
     } else {
-        unpack_pair<false>(src, m.len2, m.len1, R);
+        unpack_pair<false>(src, m.len2, R);
         r = extend_pair<FASTM, SYM, COUNT, false>(R, m.len2, m.len1, m.h0, P);
     }
     store_result(out, m.id, r);

@@ -49,6 +49,7 @@ static inline uint32_t __viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c) {
     int h = std::min(emul::wrap16(emul::hi(a) + emul::hi(b)), (int)emul::hi(c));
     return emul::pk(l, h);
 }
+static inline int __viaddmax_s32(int a, int b, int c) { return std::max((int)((uint32_t)a + (uint32_t)b), c); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline uint32_t __vimax3_s16x2(uint32_t a, uint32_t b, uint32_t c) {
     return emul::pk(std::max({emul::lo(a), emul::lo(b), emul::lo(c)}),

@@ -18,7 +18,7 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
 #pragma omp parallel
     {
         std::vector<uint4> he;
-        std::vector<uint32_t> qs, tg, blob;
+        std::vector<uint32_t> qs, blob;
 #pragma omp for schedule(dynamic, 256)
         for (int64_t k = 0; k < n; ++k) {
             bsw_seqpair &sp = pairs[k];
@@ -28,7 +28,6 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
             }
             he.assign((size_t)row_elems(sp.len2), uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
             qs.assign((size_t)sel_words(sp.len2), 0xDEADBEEFu);
-            tg.assign((size_t)((sp.len1 + 7) / 8 + 1), 0xDEADBEEFu);
             blob.assign((size_t)(seq_bytes(sp.len2, true) + seq_bytes(sp.len1, true)) / 4 + 4, 0);
             uint8_t *b = reinterpret_cast<uint8_t *>(blob.data());
             bool wide = pack2bit(qer + sp.idq, sp.len2, b);
@@ -37,9 +36,9 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
                 pack4bit(qer + sp.idq, sp.len2, b);
                 pack4bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, true));
             }
-            Rows R{he.data(), qs.data(), tg.data(), 1};
-            if (wide) unpack_pair<true>(blob.data(), sp.len2, sp.len1, R);
-            else unpack_pair<false>(blob.data(), sp.len2, sp.len1, R);
+            Rows R{he.data(), qs.data(), nullptr, 1};
+            if (wide) unpack_pair<true>(blob.data(), sp.len2, R);
+            else unpack_pair<false>(blob.data(), sp.len2, R);
             PairResult r;
             const bool m1 = (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767 && !getenv("BSW_EMUL_SLOWM");
 #define EP(F, S) (wide ? extend_pair<F, S, true, true>(R, sp.len2, sp.len1, sp.h0, K) \
