@@ -5,10 +5,12 @@
 // (main_banded.cpp:338-350). Where the reference pads, counting-sorts by len1, transposes AoS->SoA
 // per 32 lanes and unsorts (bandedSWA.cpp:2726-2761, 2811-2880, 2940-2960), this library
 //   1. cuts the caller's pair array into slabs,
-//   2. per slab: validates, length-bins (stable counting sort by len2 then len1), packs the bases
-//      2 bits each (4 bits for pairs holding an ambiguous base) into pinned memory -- all host cores,
-//   3. streams slabs through a ring of buffers per GPU: H2D, one kernel launch per length bin,
-//      D2H of 16-byte result records already in the caller's order,
+//   2. per slab, in ONE pass over the caller's data on all host cores: validates, packs the bases
+//      2 bits each (4 bits for pairs holding an ambiguous base) into pinned memory, writes a 16-byte
+//      record per pair in the caller's order and histograms the query lengths (= the launch plan),
+//   3. streams slabs through a ring of buffers per GPU: H2D, length binning ON THE DEVICE (a key
+//      kernel + a radix sort of pair indices), one DP launch per length bin, D2H of 16-byte result
+//      records already in the caller's order,
 //   4. scatters the six outputs into the caller's SeqPair array.
 // There is NO CPU implementation of the DP in here: without a CUDA device init fails.
 #include "bsw_gpu.h"
@@ -16,6 +18,9 @@
 #include "bsw_pack.h"
 
 #include <omp.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <atomic>
 
 #include <algorithm>
 #include <chrono>
@@ -34,7 +39,11 @@ constexpr int64_t kSlabPairs = 1 << 20;        // pairs per slab (upper bound)
 constexpr int64_t kSlabBases = 512ll << 20;    // bases per slab (upper bound)
 constexpr size_t kMaxSmem = 227 * 1024 - 64;   // opt-in shared memory per block on sm_100, minus the kernel's static bytes
 constexpr int kBinCols = 16;                   // query-length granularity of a launch bin
-constexpr int kVersion = 1;
+constexpr int kVersion = 2;
+// device sort key of a pair, descending order = launch order:
+//   [30:20] launch bin (len2 - 1) / 16   [19] holds an ambiguous base   [18:15] (len2 - 1) % 16   [14:0] len1
+constexpr int kKeyBits = 31;
+constexpr int kMaxBins = BSW_MAX_SEQ_LEN / kBinCols + 2;
 
 using Clock = std::chrono::steady_clock;
 inline double ms_since(Clock::time_point t0) {
@@ -60,10 +69,14 @@ struct Slab {
     uint32_t *h_blob = nullptr;
     PairOut *h_out = nullptr;
     // device
-    PairMeta *d_meta = nullptr;
+    PairMeta *d_meta = nullptr;      // caller order
     uint32_t *d_blob = nullptr;
     PairOut *d_out = nullptr;
     unsigned char *d_scratch = nullptr;
+    uint32_t *d_keys = nullptr;      // [2][cap_pairs] sort keys (in / out)
+    uint32_t *d_ord = nullptr;       // [2][cap_pairs] pair indices (in / out): out = the binned order
+    void *d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
     // current contents
     int64_t lo = 0;          // first pair (caller order) of the slab
     int n = 0;               // pairs in the slab
@@ -102,13 +115,8 @@ struct bsw_handle {
     // staged state
     int64_t staged_n = -1;
     int32_t staged_w = 0;
-    // host scratch reused across slabs
-    std::vector<uint32_t> key, ord_a, ord_b;
-    std::vector<uint32_t> sizes;
-    std::vector<uint32_t> offs;      // slot offsets of the sorted pairs, in 4-byte words
-    std::vector<int16_t> h0s;
-    std::vector<uint8_t> flags;
-    std::vector<uint32_t> chunk_off, binmax;
+    // host scratch reused across slabs: per-thread (wide, bin) histograms
+    std::vector<uint32_t> hist;
 };
 
 namespace {
@@ -132,6 +140,9 @@ void free_slab(Slab &s) {
     if (s.d_blob) cudaFree(s.d_blob);
     if (s.d_out) cudaFree(s.d_out);
     if (s.d_scratch) cudaFree(s.d_scratch);
+    if (s.d_keys) cudaFree(s.d_keys);
+    if (s.d_ord) cudaFree(s.d_ord);
+    if (s.d_sort_tmp) cudaFree(s.d_sort_tmp);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -160,6 +171,16 @@ int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
         s.d_meta = nullptr; s.d_out = nullptr;
         CU(cudaMalloc((void **)&s.d_meta, sizeof(PairMeta) * cap));
         CU(cudaMalloc((void **)&s.d_out, sizeof(PairOut) * cap));
+        if (s.d_keys) cudaFree(s.d_keys);
+        if (s.d_ord) cudaFree(s.d_ord);
+        if (s.d_sort_tmp) cudaFree(s.d_sort_tmp);
+        s.d_keys = s.d_ord = nullptr; s.d_sort_tmp = nullptr;
+        CU(cudaMalloc((void **)&s.d_keys, sizeof(uint32_t) * 2 * cap));
+        CU(cudaMalloc((void **)&s.d_ord, sizeof(uint32_t) * 2 * cap));
+        s.sort_tmp_bytes = 0;
+        CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, s.sort_tmp_bytes, s.d_keys, s.d_keys + cap, s.d_ord,
+                                                     s.d_ord + cap, (int)cap, 0, kKeyBits));
+        CU(cudaMalloc(&s.d_sort_tmp, s.sort_tmp_bytes + 16));
         s.cap_pairs = cap;
     }
     if (blob_bytes > s.cap_blob) {
@@ -183,47 +204,21 @@ inline size_t smem_need(int row_el, int qs_words) {
     return ((size_t)16 * row_el + (size_t)4 * qs_words) * kBlockPairs;
 }
 
-// Stable parallel counting sort of `in` (indices) by key[in[.]] < nkeys into `out`.
-void counting_sort(const std::vector<uint32_t> &key_of, const uint32_t *in, uint32_t *out, int n,
-                   int nkeys, bool descending) {
-    int T = omp_get_max_threads();
-    if (n < (1 << 16)) T = 1;
-    std::vector<uint32_t> hist((size_t)T * nkeys, 0);
-#pragma omp parallel num_threads(T)
-    {
-        int t = omp_get_thread_num();
-        int lo = (int)((int64_t)n * t / T), hi = (int)((int64_t)n * (t + 1) / T);
-        uint32_t *hh = hist.data() + (size_t)t * nkeys;
-        for (int i = lo; i < hi; ++i) hh[key_of[in[i]]]++;
-#pragma omp barrier
-#pragma omp single
-        {
-            uint32_t run = 0;
-            for (int kk = 0; kk < nkeys; ++kk) {
-                int k = descending ? nkeys - 1 - kk : kk;
-                for (int tt = 0; tt < T; ++tt) {
-                    uint32_t c = hist[(size_t)tt * nkeys + k];
-                    hist[(size_t)tt * nkeys + k] = run;
-                    run += c;
-                }
-            }
-        }
-        for (int i = lo; i < hi; ++i) out[hh[key_of[in[i]]]++] = in[i];
-    }
-}
+// Validates and packs slab [lo, lo+n) of the caller's arrays into s (host side), in one parallel pass
+// over chunks of kChunk pairs:
+//   loop A  (the chunk's SeqPair records, 72 B each): validate, size the chunk's blob;
+//   reserve the chunk's words in the pinned blob with one atomic add (chunks land in any order);
+//   loop B  (records now in cache): 2-bit pack query and target of each pair into a 16-byte aligned slot,
+//           4-bit pack the pair again into an extra reservation if it holds an ambiguous base (the slot's
+//           first word then holds that offset), write the pair's 16-byte PairMeta in the CALLER's order,
+//           count it in the thread's (wide, len2 bin) histogram.
+// The histogram is the launch plan: the device sorts pair indices by (bin, wide, len2, len1) itself.
+// Returns BSW_OK, an error, or kRetry with s.blob_bytes = the capacity the slab really needs.
+constexpr int kRetry = -1;
 
-// Validates, packs, bins and sorts slab [lo, lo+n) of the caller's arrays into s (host side).
-//   pass A  (parallel, reads the SeqPair records once): validate, pull out len2 / len1 / h0, size
-//           every chunk of kChunk pairs;
-//   pass B  (parallel over chunks, streaming): 2-bit pack each pair's query and target, in the
-//           CALLER's order, into a 16-byte aligned slot of the pinned blob; pairs holding an ambiguous
-//           base are also packed 4 bits per base into a per-thread overflow buffer;
-//   sort    two stable counting sorts of the pair indices (len1, then len2, descending);
-//   pass C  (parallel, sorted order): gather the 16-byte PairMeta records;
-//   plan    one launch per query-length bin, from the len2 histogram.
 int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t *ref,
                  const uint8_t *qer, int64_t lo, int n) {
-    constexpr int kChunk = 4096;
+    constexpr int kChunk = 2048;
     const bsw_seqpair *pp = pairs + lo;
     bsw_gpu_stats &st = h->stats;
     s.lo = lo; s.n = n;
@@ -231,77 +226,43 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     s.trivial.clear();
     auto t0 = Clock::now();
 
-    // ---- pass A
     const int nchunks = (n + kChunk - 1) / kChunk;
-    int bad = 0, maxq = 0, maxt = 0, ntriv = 0, maxsc = 0;
-    h->key.resize((size_t)n);      // len2
-    h->sizes.resize((size_t)n);    // len1
-    h->h0s.resize((size_t)n);
-    h->ord_a.resize((size_t)n);
-    h->ord_b.resize((size_t)n);
-    h->chunk_off.resize((size_t)nchunks + 1);
+    const int T = omp_get_max_threads();
     const int match = h->P.match;
-#pragma omp parallel for reduction(| : bad) reduction(max : maxq) reduction(max : maxt) reduction(max : maxsc) reduction(+ : ntriv) schedule(static)
-    for (int c = 0; c < nchunks; ++c) {
-        const int hi = std::min(n, (c + 1) * kChunk);
-        uint32_t words = 0;
-        for (int k = c * kChunk; k < hi; ++k) {
-            const bsw_seqpair &p = pp[k];
-            if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN ||
-                p.h0 < 0 || (int64_t)p.h0 + (int64_t)p.len2 * match > 32767) {
-                bad |= 1;
-                continue;
-            }
-            h->key[(size_t)k] = (uint32_t)p.len2;
-            h->sizes[(size_t)k] = (uint32_t)p.len1;
-            h->h0s[(size_t)k] = (int16_t)p.h0;
-            h->ord_a[(size_t)k] = (uint32_t)k;
-            maxq = std::max(maxq, p.len2);
-            maxt = std::max(maxt, p.len1);
-            maxsc = std::max(maxsc, p.h0 + p.len2 * match);
-            ntriv += (p.len1 == 0 || p.len2 == 0);
-            words += slot_words((uint32_t)p.len2, (uint32_t)p.len1);
-        }
-        h->chunk_off[(size_t)c + 1] = words;
-    }
-    if (bad) return BSW_ERR_RANGE;
-    s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
-    {
-        uint64_t run = 0;
-        h->chunk_off[0] = 0;
-        for (int c = 0; c < nchunks; ++c) {
-            run += h->chunk_off[(size_t)c + 1];
-            if (run > 0xFFFFFF00ull) return BSW_ERR_RANGE;   // slab blobs are addressed in 32-bit words
-            h->chunk_off[(size_t)c + 1] = (uint32_t)run;
-        }
-    }
-    const uint64_t narrow_bytes = (uint64_t)h->chunk_off[(size_t)nchunks] * 4;
-    st.host_bin_ms += ms_since(t0);
-    t0 = Clock::now();
-    int rc = ensure_slab(h, s, n, (size_t)narrow_bytes + 64);
-    if (rc) return rc;
-    st.host_alloc_ms += ms_since(t0);
-    t0 = Clock::now();
-
-    // ---- pass B
-    int T = omp_get_max_threads();
-    std::vector<std::vector<uint8_t>> wide_buf((size_t)T);
-    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> wide_idx((size_t)T);  // (pair, offset in thread buf)
+    const size_t cap_words = s.cap_blob / 4 > 16 ? s.cap_blob / 4 - 16 : 0;
     uint8_t *blob = reinterpret_cast<uint8_t *>(s.h_blob);
-    h->offs.resize((size_t)n);
-    h->flags.assign((size_t)n, 0);
-#pragma omp parallel num_threads(T)
+    std::atomic<uint64_t> cursor{0};
+    int bad = 0, maxq = 0, maxsc = 0, overflow = 0;
+    h->hist.assign((size_t)T * 2 * kMaxBins, 0);
+    std::vector<std::vector<uint32_t>> triv((size_t)T);
+    const bool have_pext = pack_have_pext();
+
+#pragma omp parallel num_threads(T) reduction(| : bad) reduction(| : overflow) reduction(max : maxq) reduction(max : maxsc)
     {
-        int t = omp_get_thread_num();
-        std::vector<uint8_t> &wb = wide_buf[(size_t)t];
-        auto &wi = wide_idx[(size_t)t];
-#pragma omp for schedule(dynamic, 4)
+        const int t = omp_get_thread_num();
+        uint32_t *hist = h->hist.data() + (size_t)t * 2 * kMaxBins;
+#pragma omp for schedule(dynamic, 2)
         for (int c = 0; c < nchunks; ++c) {
-            const int hi = std::min(n, (c + 1) * kChunk);
-            uint32_t off = h->chunk_off[(size_t)c];
-            for (int k = c * kChunk; k < hi; ++k) {
+            const int k0 = c * kChunk, k1 = std::min(n, k0 + kChunk);
+            // ---- loop A
+            uint64_t words = 0;
+            int cbad = 0;
+            for (int k = k0; k < k1; ++k) {
+                const bsw_seqpair &p = pp[k];
+                if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN ||
+                    p.h0 < 0 || (int64_t)p.h0 + (int64_t)p.len2 * match > 32767) {
+                    cbad = 1;
+                    break;
+                }
+                words += slot_words((uint32_t)p.len2, (uint32_t)p.len1);
+            }
+            if (cbad) { bad |= 1; continue; }
+            uint64_t off = cursor.fetch_add(words, std::memory_order_relaxed);
+            if (off + words > cap_words) { overflow |= 1; continue; }
+            // ---- loop B
+            for (int k = k0; k < k1; ++k) {
                 const bsw_seqpair &sp = pp[k];
-                if (k + 4 < hi) {   // the records are read in order; pull the next sequences in early
+                if (k + 4 < k1) {   // the records are read in order; pull the next sequences in early
                     __builtin_prefetch(qer + pp[k + 4].idq);
                     __builtin_prefetch(ref + pp[k + 4].idr);
                     __builtin_prefetch(ref + pp[k + 4].idr + 64);
@@ -309,122 +270,74 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                 uint8_t *dst = blob + (size_t)off * 4;
                 const uint32_t qb = seq_bytes((uint32_t)sp.len2, false);
                 const uint32_t sw = slot_words((uint32_t)sp.len2, (uint32_t)sp.len1);
-                bool w1 = pack2bit(qer + sp.idq, sp.len2, dst);
-                bool w2 = pack2bit(ref + sp.idr, sp.len1, dst + qb);
-                h->offs[(size_t)k] = off;
+                bool w1, w2;
+                if (have_pext) {
+                    w1 = pack2bit_pext(qer + sp.idq, sp.len2, dst);
+                    w2 = pack2bit_pext(ref + sp.idr, sp.len1, dst + qb);
+                } else {
+                    w1 = pack2bit(qer + sp.idq, sp.len2, dst);
+                    w2 = pack2bit(ref + sp.idr, sp.len1, dst + qb);
+                }
+                uint32_t wide = 0;
                 if (w1 || w2) {
-                    h->flags[(size_t)k] = 1;
+                    wide = 1;
                     const uint32_t wq = seq_bytes((uint32_t)sp.len2, true), wt = seq_bytes((uint32_t)sp.len1, true);
-                    size_t o = (wb.size() + 15) & ~(size_t)15;
-                    wb.resize(o + wq + wt);
-                    pack4bit(qer + sp.idq, sp.len2, wb.data() + o);
-                    pack4bit(ref + sp.idr, sp.len1, wb.data() + o + wq);
-                    wi.emplace_back((uint32_t)k, (uint32_t)o);
+                    const uint64_t ww = ((uint64_t)wq + wt + 15) / 16 * 4;
+                    const uint64_t woff = cursor.fetch_add(ww, std::memory_order_relaxed);
+                    if (woff + ww > cap_words) {
+                        overflow |= 1;
+                    } else {
+                        uint8_t *wd = blob + (size_t)woff * 4;
+                        pack4bit(qer + sp.idq, sp.len2, wd);
+                        pack4bit(ref + sp.idr, sp.len1, wd + wq);
+                        const uint32_t w32 = (uint32_t)woff;
+                        memcpy(dst, &w32, 4);
+                    }
+                }
+                PairMeta &m = s.h_meta[k];
+                m.off = (uint32_t)off;
+                m.id = (uint32_t)k;
+                m.len2 = (uint16_t)sp.len2; m.len1 = (uint16_t)sp.len1;
+                m.h0 = (int16_t)sp.h0;
+                m.flags = (uint16_t)wide;
+                if (sp.len1 == 0 || sp.len2 == 0) {
+                    triv[(size_t)t].push_back((uint32_t)k);
+                } else {
+                    hist[wide * kMaxBins + (uint32_t)(sp.len2 - 1) / kBinCols] += 1;
+                    maxq = std::max(maxq, sp.len2);
+                    maxsc = std::max(maxsc, sp.h0 + sp.len2 * match);
                 }
                 off += sw;
             }
         }
     }
-    // overflow area: per-thread buffers appended after the slots; a wide pair's slot keeps only the
-    // word offset of its 4-bit blob
-    uint64_t wide_total = 0;
-    std::vector<uint64_t> wbase((size_t)T);
-    for (int t = 0; t < T; ++t) {
-        wbase[(size_t)t] = narrow_bytes + wide_total;
-        wide_total += (wide_buf[(size_t)t].size() + 15) & ~(size_t)15;
-    }
-    s.blob_bytes = (size_t)(narrow_bytes + wide_total + 16);
-    if (s.blob_bytes > (size_t)0xFFFFFF00ull * 4) return BSW_ERR_RANGE;
-    if (wide_total) {
-        if (s.blob_bytes + 64 > s.cap_blob) {
-            std::vector<uint8_t> keep(blob, blob + narrow_bytes);   // grow, keeping the slots
-            rc = ensure_slab(h, s, n, s.blob_bytes + 64 + (s.blob_bytes >> 2));
-            if (rc) return rc;
-            blob = reinterpret_cast<uint8_t *>(s.h_blob);
-            memcpy(blob, keep.data(), (size_t)narrow_bytes);
-        }
-        for (int t = 0; t < T; ++t) {
-            if (wide_buf[(size_t)t].empty()) continue;
-            memcpy(blob + wbase[(size_t)t], wide_buf[(size_t)t].data(), wide_buf[(size_t)t].size());
-            for (auto &pr : wide_idx[(size_t)t]) {
-                uint32_t woff = (uint32_t)((wbase[(size_t)t] + pr.second) >> 2);
-                memcpy(blob + (size_t)h->offs[(size_t)pr.first] * 4, &woff, 4);
-            }
-        }
-    }
-    memset(blob + s.blob_bytes - 16, 0, 16);
-    // inside a launch bin the pairs holding an ambiguous base come first (whole warps of them run
-    // the LOP3-selector code): sort key = len2 - 1 with the wide flag inserted above the bin's low bits
-    static_assert(kBinCols == 16, "sort key layout");
-    auto bin_key = [](uint32_t len2, uint32_t wide) {
-        const uint32_t v = len2 - 1;   // len2 >= 1 for every sorted pair
-        return ((v & ~15u) << 1) | (wide << 4) | (v & 15u);
-    };
-#pragma omp parallel for schedule(static)
-    for (int k = 0; k < n; ++k) {
-        const uint32_t l2 = h->key[(size_t)k];
-        h->key[(size_t)k] = l2 ? bin_key(l2, h->flags[(size_t)k]) : 0u;
-    }
+    if (bad) return BSW_ERR_RANGE;
+    const uint64_t total_words = cursor.load();
+    if (total_words > 0xFFFFFF00ull) return BSW_ERR_RANGE;   // slab blobs are addressed in 32-bit words
+    s.blob_bytes = (size_t)total_words * 4 + 16;
+    if (overflow) return kRetry;
+    memset(blob + (size_t)total_words * 4, 0, 16);
+    s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
+    for (int t = 0; t < T; ++t) s.trivial.insert(s.trivial.end(), triv[(size_t)t].begin(), triv[(size_t)t].end());
+    s.n_dev = n - (int)s.trivial.size();
     st.host_pack_ms += ms_since(t0);
     t0 = Clock::now();
 
-    // ---- sort (pairs with an empty sequence are answered on the host and left out)
-    int nd = n;
-    if (ntriv) {
-        nd = 0;
-        for (int k = 0; k < n; ++k) {
-            if (pp[k].len1 == 0 || pp[k].len2 == 0) s.trivial.push_back((uint32_t)k);
-            else h->ord_a[(size_t)nd++] = (uint32_t)k;
-        }
-    }
-    s.n_dev = nd;
-    if (nd == 0) return BSW_OK;
-    counting_sort(h->sizes, h->ord_a.data(), h->ord_b.data(), nd, maxt + 1, true);
-    counting_sort(h->key, h->ord_b.data(), h->ord_a.data(), nd, (int)bin_key((uint32_t)std::max(maxq, 1), 1u) + 1, true);
-    const uint32_t *ord = h->ord_a.data();
-    st.host_sort_ms += ms_since(t0);
-    t0 = Clock::now();
-
-    // ---- pass C + plan. The sorted order is descending in len2 bin, wide pairs first inside a bin, so
-    // a launch = the run of positions whose len2 falls in one kBinCols-wide bin; its geometry needs
-    // the largest len2 / len1 in it.
-    const int nbins = maxq / kBinCols + 2;
-    h->binmax.assign((size_t)nbins * 4, 0);
-    std::vector<uint32_t> &bm = h->binmax;   // per (wide, bin): [count, max len1]
-#pragma omp parallel num_threads(T)
-    {
-        std::vector<uint32_t> loc(bm.size(), 0);
-#pragma omp for schedule(static) nowait
-        for (int p = 0; p < nd; ++p) {
-            const uint32_t k = ord[p];
-            PairMeta &m = s.h_meta[p];
-            const uint32_t fl = h->flags[k];
-            const uint32_t kk = h->key[k];
-            const uint32_t l2 = (((kk >> 1) & ~15u) | (kk & 15u)) + 1;
-            m.off = h->offs[k];
-            m.id = k;
-            m.len2 = (uint16_t)l2; m.len1 = (uint16_t)h->sizes[k];
-            m.h0 = h->h0s[k];
-            m.flags = (uint16_t)fl;
-            const size_t b = ((size_t)fl * nbins + (size_t)((l2 - 1) / kBinCols)) * 2;
-            loc[b] += 1;
-            loc[b + 1] = std::max(loc[b + 1], h->sizes[k]);
-        }
-#pragma omp critical
-        for (size_t i = 0; i < bm.size(); i += 2) { bm[i] += loc[i]; bm[i + 1] = std::max(bm[i + 1], loc[i + 1]); }
-    }
-    {
+    // ---- plan: one launch per query-length bin, longest first, the wide pairs of a bin in front
+    // (== the device sort order: key descending)
+    if (s.n_dev > 0) {
+        const int nbins = maxq / kBinCols + 1;
         int p = 0;
         for (int b = nbins - 1; b >= 0; --b) {
-            const size_t bw = ((size_t)nbins + (size_t)b) * 2, bn = (size_t)b * 2;
-            const int nw = (int)bm[bw], nn = (int)bm[bn];
+            int nw = 0, nn = 0;
+            for (int t = 0; t < T; ++t) {
+                nn += (int)h->hist[(size_t)t * 2 * kMaxBins + (size_t)b];
+                nw += (int)h->hist[(size_t)t * 2 * kMaxBins + kMaxBins + (size_t)b];
+            }
             if (nw + nn == 0) continue;
-            int q_hi = 0;
-            if (nw) q_hi = std::max(q_hi, (int)s.h_meta[p].len2);
-            if (nn) q_hi = std::max(q_hi, (int)s.h_meta[p + nw].len2);
-            const int t_hi = (int)std::max(bm[bw + 1], bm[bn + 1]);
+            const int q_hi = std::min(maxq, (b + 1) * kBinCols);
             Launch L;
-            L.first = p; L.n = nw + nn; L.n_wide = nw; L.work = (int64_t)(nw + nn) * q_hi * t_hi;
+            L.first = p; L.n = nw + nn; L.n_wide = nw; L.work = (int64_t)(nw + nn) * q_hi * q_hi;
             L.row_el = row_elems(q_hi);
             L.qs_words = sel_words(q_hi);
             L.smem = smem_need(L.row_el, L.qs_words);
@@ -435,6 +348,25 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     }
     st.host_plan_ms += ms_since(t0);
     return BSW_OK;
+}
+
+// prepare_slab with the (rare) capacity retry: the first pass over a slab whose blob does not fit the
+// ring slot reports the exact size, the slot grows, the pass runs again.
+int prepare_slab_fit(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                     int64_t lo, int n, size_t blob_guess) {
+    auto t0 = Clock::now();
+    int rc = ensure_slab(h, s, n, blob_guess);
+    h->stats.host_alloc_ms += ms_since(t0);
+    if (rc) return rc;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        rc = prepare_slab(h, s, pairs, ref, qer, lo, n);
+        if (rc != kRetry) return rc;
+        t0 = Clock::now();
+        rc = ensure_slab(h, s, n, s.blob_bytes + (s.blob_bytes >> 3) + 4096);
+        h->stats.host_alloc_ms += ms_since(t0);
+        if (rc) return rc;
+    }
+    return BSW_ERR_NOMEM;
 }
 
 // ---- device side of a slab ---------------------------------------------------------------------
@@ -450,8 +382,8 @@ int ensure_aux(bsw_handle *h, Device &dev) {
 }
 
 // The kernel instantiations, indexed [fastm][sym][count].
-typedef void (*ShortFn)(const PairMeta *, const uint32_t *, PairOut *, int, int, KParams, int, int);
-typedef void (*LongFn)(const PairMeta *, const uint32_t *, PairOut *, int, int, KParams, int, int, unsigned char *);
+typedef void (*ShortFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
+typedef void (*LongFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int, unsigned char *);
 template <int I> struct KernelTable {
     static void fill(ShortFn *sf, LongFn *lf) {
         sf[I] = bsw_short_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
@@ -505,12 +437,13 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                     dev.attr_set[ki] = true;
                 }
                 cudaStream_t st = dev.aux[rr++ % kAux];
-                short_fn[ki]<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta + L.first, s.d_blob, s.d_out, L.n_wide,
-                                                                L.n - L.n_wide, h->K, L.row_el, L.qs_words);
+                short_fn[ki]<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
+                                                                s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.row_el,
+                                                                L.qs_words);
             } else {
                 long_fn[ki]<<<grid, kBlockPairs, 0, dev.aux[0]>>>(
-                    s.d_meta + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.row_el, L.qs_words,
-                    s.d_scratch);
+                    s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, h->K,
+                    L.row_el, L.qs_words, s.d_scratch);
             }
             CU(cudaGetLastError());
             h->stats.kernel_launches++;
@@ -524,6 +457,19 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
     return BSW_OK;
 }
 
+// Length binning of a slab on its device: keys + identity, then the radix sort (descending).
+int bin_slab(bsw_handle *h, Slab &s, cudaStream_t st) {
+    if (s.n_dev == 0) return BSW_OK;
+    const int n = s.n;
+    bsw_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_meta, n, s.d_keys, s.d_ord);
+    CU(cudaGetLastError());
+    h->stats.kernel_launches++;
+    size_t tmp = s.sort_tmp_bytes;
+    CU(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_keys, s.d_keys + s.cap_pairs, s.d_ord,
+                                                 s.d_ord + s.cap_pairs, n, 0, kKeyBits, st));
+    return BSW_OK;
+}
+
 int launch_slab(bsw_handle *h, Device &dev, Slab &s, bool count = false) {
     Slab *one = &s;
     return launch_slabs(h, dev, s.stream, &one, 1, count);
@@ -533,9 +479,9 @@ int launch_slab(bsw_handle *h, Device &dev, Slab &s, bool count = false) {
 
 int upload_slab(bsw_handle *h, Slab &s) {
     if (s.n_dev == 0) return BSW_OK;
-    CU(cudaMemcpyAsync(s.d_meta, s.h_meta, sizeof(PairMeta) * (size_t)s.n_dev, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.d_meta, s.h_meta, sizeof(PairMeta) * (size_t)s.n, cudaMemcpyHostToDevice, s.stream));
     CU(cudaMemcpyAsync(s.d_blob, s.h_blob, s.blob_bytes, cudaMemcpyHostToDevice, s.stream));
-    h->stats.h2d_bytes += (int64_t)(sizeof(PairMeta) * (size_t)s.n_dev + s.blob_bytes);
+    h->stats.h2d_bytes += (int64_t)(sizeof(PairMeta) * (size_t)s.n + s.blob_bytes);
     return BSW_OK;
 }
 
@@ -565,32 +511,42 @@ void scatter_slab(bsw_handle *h, const Slab &s, const PairOut *out, bsw_seqpair 
     (void)h;
 }
 
-// slab boundaries over [0, n): by pair count and by bases, at a granularity of 64 Ki pairs
-void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts) {
-    constexpr int64_t G = 1 << 16;
+// Slab boundaries over [0, n): by pair count and by (estimated) bases, at a granularity of 64 Ki
+// pairs. The lengths are SAMPLED (every 64th record: one cache line in 72 instead of a sweep over the
+// whole array); blob_guess[i] is the pinned-blob capacity to try first for slab i -- prepare_slab
+// reports the exact need if the estimate was short.
+void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts, std::vector<size_t> &blob_guess) {
+    constexpr int64_t G = 1 << 16, S = 64;
     const int64_t ng = (n + G - 1) / G;
     std::vector<int64_t> bases((size_t)ng, 0);
 #pragma omp parallel for schedule(static)
     for (int64_t c = 0; c < ng; ++c) {
-        int64_t b = 0;
+        int64_t b = 0, cnt = 0;
         const int64_t hi = std::min(n, (c + 1) * G);
-        for (int64_t k = c * G; k < hi; ++k)
-            b += (int64_t)std::max(pairs[k].len1, 0) + std::max(pairs[k].len2, 0);
-        bases[(size_t)c] = b;
+        for (int64_t k = c * G; k < hi; k += S, ++cnt) {
+            const int64_t l1 = pairs[k].len1, l2 = pairs[k].len2;
+            b += std::min<int64_t>(std::max<int64_t>(l1, 0), BSW_MAX_SEQ_LEN) +
+                 std::min<int64_t>(std::max<int64_t>(l2, 0), BSW_MAX_SEQ_LEN);
+        }
+        bases[(size_t)c] = cnt ? b * (hi - c * G) / cnt : 0;
     }
     cuts.clear();
+    blob_guess.clear();
     cuts.push_back(0);
     int64_t acc = 0, cnt = 0;
+    auto close = [&](int64_t hi) {
+        cuts.push_back(hi);
+        // 2 bits per base + up to 19 bytes of padding per pair + 15 % for sampling error and wide pairs
+        blob_guess.push_back((size_t)((acc / 4 + 20 * cnt) * 115 / 100) + 65536);
+        acc = 0; cnt = 0;
+    };
     for (int64_t c = 0; c < ng; ++c) {
         const int64_t hi = std::min(n, (c + 1) * G);
         acc += bases[(size_t)c];
         cnt += hi - c * G;
-        if (cnt >= kSlabPairs || acc >= kSlabBases) {
-            cuts.push_back(hi);
-            acc = 0; cnt = 0;
-        }
+        if (cnt >= kSlabPairs || acc >= kSlabBases) close(hi);
     }
-    if (cuts.back() != n) cuts.push_back(n);
+    if (cuts.back() != n) close(n);
 }
 
 int finish_slab(bsw_handle *h, Slab &s, bsw_seqpair *pairs, double *kernel_ms_acc) {
@@ -742,9 +698,10 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
     if (n == 0) { st.wall_ms = 0; return BSW_OK; }
 
     std::vector<int64_t> cuts;
+    std::vector<size_t> guess;
     {
         auto t0 = Clock::now();
-        cut_slabs(pairs, n, cuts);
+        cut_slabs(pairs, n, cuts, guess);
         st.host_cut_ms = ms_since(t0);
     }
     const int nslabs = (int)cuts.size() - 1;
@@ -758,11 +715,13 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
         CU(cudaSetDevice(dev.id));
         rc = finish_slab(h, s, pairs, &kms[(size_t)d]);  // ring slot still owns an older slab
         if (rc) break;
-        rc = prepare_slab(h, s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]));
+        rc = prepare_slab_fit(h, s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]),
+                              guess[(size_t)sidx]);
         if (rc) break;
         if (s.n_dev) {
             if ((rc = upload_slab(h, s))) break;
             CU(cudaEventRecord(s.ev_k0, s.stream));
+            if ((rc = bin_slab(h, s, s.stream))) break;
             if ((rc = launch_slab(h, dev, s))) break;
             CU(cudaEventRecord(s.ev_k1, s.stream));
             if ((rc = download_slab(h, s))) break;
@@ -798,7 +757,8 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
     h->K.w = w;
     const int ng = (int)h->devs.size();
     std::vector<int64_t> cuts;
-    cut_slabs(pairs, n, cuts);
+    std::vector<size_t> guess;
+    cut_slabs(pairs, n, cuts, guess);
     const int nslabs = (int)cuts.size() - 1;
     for (int sidx = 0; sidx < nslabs; ++sidx) {
         Device &dev = h->devs[(size_t)(sidx % ng)];
@@ -806,7 +766,8 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
         Slab *s = new (std::nothrow) Slab();
         if (!s) return BSW_ERR_NOMEM;
         dev.staged.push_back(s);
-        int rc = prepare_slab(h, *s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]));
+        int rc = prepare_slab_fit(h, *s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]),
+                                  guess[(size_t)sidx]);
         if (rc) { drop_staged(h); return rc; }
         if ((rc = upload_slab(h, *s))) { drop_staged(h); return rc; }
         CU(cudaStreamSynchronize(s->stream));
@@ -830,7 +791,9 @@ int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms) {
         std::vector<Slab *> live;
         for (Slab *s : dev.staged) if (s->n_dev) live.push_back(s);
         if (!live.empty()) {
-            int rc = launch_slabs(h, dev, st0, live.data(), (int)live.size());
+            int rc = BSW_OK;
+            for (Slab *s : live) if ((rc = bin_slab(h, *s, st0))) return rc;   // binning is part of the path
+            rc = launch_slabs(h, dev, st0, live.data(), (int)live.size());
             if (rc) return rc;
         }
         CU(cudaEventRecord(dev.staged[0]->ev_k1, st0));
@@ -858,8 +821,9 @@ int bsw_gpu_count_staged(bsw_handle *h, int64_t *cells_visited) {
         CU(cudaSetDevice(dev.id));
         for (Slab *s : dev.staged) {
             if (!s->n_dev) continue;
-            int rc = launch_slab(h, dev, *s, true);
+            int rc = bin_slab(h, *s, s->stream);
             if (rc) return rc;
+            if ((rc = launch_slab(h, dev, *s, true))) return rc;
             if ((rc = download_slab(h, *s))) return rc;
             CU(cudaStreamSynchronize(s->stream));
             int64_t sum = 0;

@@ -568,8 +568,9 @@ __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const Pa
 // ---------------------------------------------------------------------------------------------
 // Short pairs: rows in shared memory. Launch: block = kBlockPairs threads, dynamic smem =
 // (16*row_el + 4*qs_words) * NT.
-//   meta[0 .. n_wide + n_narrow): this launch's pairs in sorted (length-binned) order, the n_wide pairs
-//   holding an ambiguous base first. Threads [0, roundup32(n_wide)) take the wide pairs, the threads
+//   meta[]: the slab's pairs in the caller's order; ord[0 .. n_wide + n_narrow): this launch's pairs
+//   (indices into meta) in the device-sorted, length-binned order, the n_wide pairs holding an
+//   ambiguous base first. Threads [0, roundup32(n_wide)) take the wide pairs, the threads
 //   after them the narrow ones, so every WARP runs one instantiation of the DP (no divergence between
 //   the LOP3-selector and the add-selector code). blob = the slab's packed sequences: each thread
 //   expands its own 16-byte aligned slot straight from global memory (a few dozen bytes per pair, read
@@ -580,8 +581,9 @@ __host__ __device__ inline int launch_threads(int n_wide, int n_narrow) { return
 
 template <bool FASTM, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
-bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
-                 PairOut *__restrict__ out, int n_wide, int n_narrow, KParams P, int row_el, int qs_words) {
+bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
+                 const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
+                 KParams P, int row_el, int qs_words) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NT = kBlockPairs;
     const int tid = threadIdx.x;
@@ -590,7 +592,7 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     const bool wide = t < nwr;                       // warp-uniform
     const int k = wide ? t : t - nwr + n_wide;
     if (wide ? t >= n_wide : k >= n_wide + n_narrow) return;
-    const PairMeta m = meta[k];
+    const PairMeta m = meta[ord[k]];
 
     Rows R;
     R.stride = NT;
@@ -618,16 +620,16 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
 // ---------------------------------------------------------------------------------------------
 template <bool FASTM, bool SYM, bool COUNT>
 __global__ void __launch_bounds__(kBlockPairs)
-bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ blob,
-                PairOut *__restrict__ out, int n_wide, int n_narrow, KParams P, int row_el, int qs_words,
-                unsigned char *__restrict__ scratch) {
+bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
+                const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
+                KParams P, int row_el, int qs_words, unsigned char *__restrict__ scratch) {
     const int nthreads = gridDim.x * blockDim.x;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nwr = (n_wide + 31) & ~31;
     const bool wide = t < nwr;
     const int k = wide ? t : t - nwr + n_wide;
     if (wide ? t >= n_wide : k >= n_wide + n_narrow) return;
-    const PairMeta m = meta[k];
+    const PairMeta m = meta[ord[k]];
     Rows R;
     R.stride = nthreads;
     unsigned char *p = scratch;
@@ -647,6 +649,28 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     }
     store_result(out, m.id, r);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Length binning on the device: sort key of every pair of a slab (descending order = launch order) and
+// the identity permutation; cub's radix sort then yields ord[]. Pairs with an empty sequence (answered
+// on the host) get key 0 and sort behind everything that is launched.
+//   key = bin << 20 | wide << 19 | (len2 - 1) % 16 << 15 | len1,  bin = (len2 - 1) / 16
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t sort_key(uint32_t len2, uint32_t len1, uint32_t wide) {
+    if (len2 == 0 || len1 == 0) return 0u;
+    const uint32_t v = len2 - 1;
+    return ((v >> 4) << 20) | (wide << 19) | ((v & 15u) << 15) | len1;
+}
+#ifndef BSW_HOST_EMUL
+__global__ void bsw_key_kernel(const PairMeta *__restrict__ meta, int n, uint32_t *__restrict__ keys,
+                               uint32_t *__restrict__ idx) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const PairMeta m = meta[k];
+    keys[k] = sort_key(m.len2, m.len1, m.flags & 1u);
+    idx[k] = (uint32_t)k;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Integer-pipe microbenchmark: `iters` x 8 independent chains of one instruction kind per thread.
