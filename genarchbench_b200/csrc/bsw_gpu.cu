@@ -235,7 +235,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     int bad = 0, maxq = 0, maxsc = 0, overflow = 0;
     h->hist.assign((size_t)T * 2 * kMaxBins, 0);
     std::vector<std::vector<uint32_t>> triv((size_t)T);
-    const bool have_pext = pack_have_pext();
+    const int packer = pack_have_avx2() ? 2 : (pack_have_pext() ? 1 : 0);
 
 #pragma omp parallel num_threads(T) reduction(| : bad) reduction(| : overflow) reduction(max : maxq) reduction(max : maxsc)
     {
@@ -271,7 +271,10 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                 const uint32_t qb = seq_bytes((uint32_t)sp.len2, false);
                 const uint32_t sw = slot_words((uint32_t)sp.len2, (uint32_t)sp.len1);
                 bool w1, w2;
-                if (have_pext) {
+                if (packer == 2) {
+                    w1 = pack2bit_avx2(qer + sp.idq, sp.len2, dst);
+                    w2 = pack2bit_avx2(ref + sp.idr, sp.len1, dst + qb);
+                } else if (packer == 1) {
                     w1 = pack2bit_pext(qer + sp.idq, sp.len2, dst);
                     w2 = pack2bit_pext(ref + sp.idr, sp.len1, dst + qb);
                 } else {

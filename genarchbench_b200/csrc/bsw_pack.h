@@ -83,6 +83,62 @@ inline bool pack2bit_pext(const uint8_t *src, int len, uint8_t *dst) {
 inline bool pack2bit_pext(const uint8_t *src, int len, uint8_t *dst) { return pack2bit(src, len, dst); }
 #endif
 
+// AVX2 variant: 32 bases per step. maddubs folds base pairs (b0 + 4*b1), madd folds those again
+// (+ 16*(b2 + 4*b3)), two saturating packs bring the eight 32-bit results down to eight bytes. The tail
+// is loaded in one piece when that cannot cross a page, through a bounce buffer otherwise.
+inline bool pack_have_avx2() {
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool v = __builtin_cpu_supports("avx2");
+    return v;
+#else
+    return false;
+#endif
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+}  // namespace bswk
+#include <immintrin.h>
+namespace bswk {
+__attribute__((target("avx2")))
+inline uint64_t pack_fold32(__m256i v, __m256i &bad) {
+    const __m256i w8 = _mm256_set1_epi16(0x0401), w16 = _mm256_set1_epi32(0x00100001);
+    bad = _mm256_or_si256(bad, v);
+    const __m256i u = _mm256_madd_epi16(_mm256_maddubs_epi16(v, w8), w16);
+    const __m128i p16 = _mm_packus_epi32(_mm256_castsi256_si128(u), _mm256_extracti128_si256(u, 1));
+    return (uint64_t)_mm_cvtsi128_si64(_mm_packus_epi16(p16, p16));
+}
+__attribute__((target("avx2")))
+inline bool pack2bit_avx2(const uint8_t *src, int len, uint8_t *dst) {
+    const int nbytes = (int)seq_bytes((uint32_t)len, false);
+    __m256i bad = _mm256_setzero_si256();
+    int i = 0, o = 0;
+    for (; i + 32 <= len; i += 32, o += 8) {
+        const uint64_t r = pack_fold32(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)), bad);
+        memcpy(dst + o, &r, 8);
+    }
+    if (i < len) {
+        const int rem = len - i;
+        __m256i v;
+        if (((uintptr_t)(src + i) & 4095u) <= 4096u - 32u) {
+            const __m256i iota = _mm256_setr_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19,
+                                                  20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31);
+            const __m256i keep = _mm256_cmpgt_epi8(_mm256_set1_epi8((char)rem), iota);
+            v = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)), keep);
+        } else {
+            alignas(32) uint8_t tmp[32] = {0};
+            memcpy(tmp, src + i, (size_t)rem);
+            v = _mm256_load_si256(reinterpret_cast<const __m256i *>(tmp));
+        }
+        const uint64_t r = pack_fold32(v, bad);
+        if (nbytes - o >= 8) { memcpy(dst + o, &r, 8); o += 8; }
+        else { const uint32_t r4 = (uint32_t)r; memcpy(dst + o, &r4, 4); o += 4; }
+    }
+    for (; o < nbytes; ++o) dst[o] = 0;
+    return !_mm256_testz_si256(bad, _mm256_set1_epi8((char)0xFC));
+}
+#else
+inline bool pack2bit_avx2(const uint8_t *src, int len, uint8_t *dst) { return pack2bit(src, len, dst); }
+#endif
+
 inline void pack4bit(const uint8_t *src, int len, uint8_t *dst) {
     const int nbytes = (int)seq_bytes((uint32_t)len, true);
     int o = 0;
