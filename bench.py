@@ -41,8 +41,25 @@ RANK = int(os.environ.get("RANK", 0))
 LOCAL_RANK = int(os.environ.get("LOCAL_RANK", 0))
 WORLD = int(os.environ.get("WORLD_SIZE", 1))
 NCORES = os.cpu_count() or 1
-# host packing threads: share the box's cores between the ranks (set before OpenMP loads)
-os.environ.setdefault("OMP_NUM_THREADS", str(max(1, NCORES // max(WORLD, 1))))
+# host packing threads: share the box's cores between the ranks (set before OpenMP loads).
+# torchrun exports OMP_NUM_THREADS=1 to every rank by default, which is not a user's choice here:
+# BSW_HOST_THREADS is the explicit override, otherwise each rank gets cores / world.
+if "BSW_HOST_THREADS" in os.environ or WORLD > 1 or "OMP_NUM_THREADS" not in os.environ:
+    os.environ["OMP_NUM_THREADS"] = os.environ.get("BSW_HOST_THREADS", str(max(1, NCORES // max(WORLD, 1))))
+# rank 0 prints ONE JSON line on stdout: everything else that libraries write to fd 1 (NCCL's version
+# banner, for one) is sent to stderr; the line itself goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+# same placement policy as the reference's regression scripts (bsw/scripts/regression_small.sh:52):
+# threads stay on their cores (without it the host pass is bimodal, 29 vs 54 ms per 10 M pairs).
+# Under torchrun the ranks share the box, so binding is left to the launcher there.
+if WORLD == 1:
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 import numpy as np  # noqa: E402
 
@@ -180,7 +197,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -243,6 +260,7 @@ def main():
 
     if rank != 0:
         g.close()
+        bdist.shutdown()
         return
 
     peaks = measured_peaks()
@@ -291,8 +309,9 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     g.close()
+    bdist.shutdown()
 
 
 if __name__ == "__main__":

@@ -29,7 +29,10 @@ def init_process_group(backend: str | None = None):
             os.environ.setdefault("MASTER_PORT", "29500")
             if backend == "nccl":
                 torch.cuda.set_device(local_rank)
-            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+                dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                        device_id=torch.device("cuda", local_rank))
+            else:
+                dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, local_rank, world
 
 
@@ -60,6 +63,12 @@ def barrier() -> None:
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
+
+
+def shutdown() -> None:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def reduce_stats(sums: Sequence[float], maxes: Sequence[float], device=None) -> Tuple[list, list]:
