@@ -101,6 +101,7 @@ struct Device {
     cudaEvent_t aux_ev[kAux] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t fork_ev = nullptr;
     bool attr_set[8] = {false, false, false, false, false, false, false, false};
+    bool attr_set_long[8] = {false, false, false, false, false, false, false, false};
 };
 
 }  // namespace
@@ -386,7 +387,7 @@ int ensure_aux(bsw_handle *h, Device &dev) {
 
 // The kernel instantiations, indexed [fastm][sym][count].
 typedef void (*ShortFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
-typedef void (*LongFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int, unsigned char *);
+typedef void (*LongFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
 template <int I> struct KernelTable {
     static void fill(ShortFn *sf, LongFn *lf) {
         sf[I] = bsw_short_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
@@ -409,23 +410,6 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
     if (!filled) { KernelTable<7>::fill(short_fn, long_fn); filled = true; }
     int rc = ensure_aux(h, dev);
     if (rc) return rc;
-    // scratch for the long kernel, sized once per slab before anything is enqueued
-    for (int i = 0; i < nslabs; ++i) {
-        Slab &s = *slabs[i];
-        size_t need = 0;
-        for (const Launch &L : s.launches) {
-            if (L.smem) continue;
-            const size_t nthreads = (size_t)((launch_threads(L.n_wide, L.n - L.n_wide) + kBlockPairs - 1) / kBlockPairs) * kBlockPairs;
-            need = std::max(need, ((size_t)16 * L.row_el + (size_t)4 * L.qs_words) * nthreads + 256);
-        }
-        if (need > s.cap_scratch) {
-            CU(cudaDeviceSynchronize());
-            if (s.d_scratch) cudaFree(s.d_scratch);
-            s.d_scratch = nullptr; s.cap_scratch = 0;
-            CU(cudaMalloc((void **)&s.d_scratch, need));
-            s.cap_scratch = need;
-        }
-    }
     CU(cudaEventRecord(dev.fork_ev, main));
     for (int j = 0; j < kAux; ++j) CU(cudaStreamWaitEvent(dev.aux[j], dev.fork_ev, 0));
     int rr = 0;
@@ -444,9 +428,18 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                                                                 s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.row_el,
                                                                 L.qs_words);
             } else {
-                long_fn[ki]<<<grid, kBlockPairs, 0, dev.aux[0]>>>(
+                // one warp per pair; as many pairs per block as fit (at most 8)
+                const int q_hi = 4 * L.row_el - 4;     // row_el = (qlen + 4) >> 2 was sized from the bin's longest query
+                const int pb = (int)warp_pair_bytes(q_hi + 3);
+                const int wpb = std::max(1, std::min(8, (int)(kMaxSmem / (size_t)pb)));
+                if (!dev.attr_set_long[ki]) {
+                    CU(cudaFuncSetAttribute(long_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                    dev.attr_set_long[ki] = true;
+                }
+                cudaStream_t st = dev.aux[rr++ % kAux];
+                long_fn[ki]<<<(L.n + wpb - 1) / wpb, 32 * wpb, (size_t)wpb * pb, st>>>(
                     s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, h->K,
-                    L.row_el, L.qs_words, s.d_scratch);
+                    L.row_el, pb);
             }
             CU(cudaGetLastError());
             h->stats.kernel_launches++;
@@ -625,7 +618,8 @@ int bsw_gpu_init_devices(const bsw_params *params, int n_devices, const int *dev
     const bsw_params &p = *params;
     if (p.e_del <= 0 || p.e_ins <= 0 || p.o_del < 0 || p.o_ins < 0 || p.match <= 0 || p.match > 127 ||
         p.mismatch < 0 || p.mismatch > 128 || p.ambig < -128 || p.ambig > 127 || p.zdrop < 0 ||
-        p.zdrop > 32767 || p.o_del + p.e_del > 16383 || p.o_ins + p.e_ins > 16383)
+        p.zdrop > 32767 || p.o_del + p.e_del > 16383 || p.o_ins + p.e_ins > 16383 || p.e_del > 8191 ||
+        p.e_ins > 8191)
         return BSW_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return BSW_ERR_NO_DEVICE;

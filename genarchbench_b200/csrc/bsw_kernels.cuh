@@ -614,40 +614,299 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// Long pairs (rows do not fit the shared-memory bins): same per-pair code over a global scratch,
-// interleaved by thread across the whole grid so neighbouring threads touch neighbouring words.
-//   scratch layout: he4[row_el][nthreads] (uint4) | qs[qs_words][nthreads] (u32)
+// Long pairs: ONE WARP per pair. The rows of the pair (same he4 / qs layout, stride 1) live in the
+// warp's slice of shared memory; a row is swept left to right in tiles of 32 elements (128 columns),
+// lane L owning element kb + L = columns 4(kb+L) .. +3 = two groups.
+//
+// The reference's decisions stay row by row (band clamp, row max / last argmax, m == 0, z-drop,
+// leading / trailing trim): every lane holds the same beg / end / best / ... and the row is finished
+// before the next one starts. Inside a row only F runs along the columns, and F is max-plus linear:
+//     F(i, j + d) = max( F_local(j + d), F(i, j) - e_ins * d )
+// so each lane first computes its four columns from F = 0 (pass 1: scores, M, T, E' and the local F
+// chain), a 5-step warp scan (SHFL.UP + VIADDMNMX) then delivers every lane's true incoming F,
+// and pass 2 corrects the lane's F with one VIADDMNMX per group before H = max(M, E, F), the shifted
+// store of H (the diagonal of the next row; the left neighbour's last H arrives by SHFL.UP) and the row
+// statistics. Row max and its LAST column, first / last non-zero entry are warp reductions
+// (REDUX / ballots) instead of per-thread scans.
 // ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t warp_pair_bytes(int qlen) {
+    return (uint32_t)(16 * row_elems(qlen) + 4 * sel_words(qlen) + 15) & ~15u;
+}
+
+template <bool FASTM, bool SYM, bool COUNT, bool WIDE>
+__device__ inline PairResult warp_extend_pair(Rows &R, const uint32_t *__restrict__ blob, int qlen, int tlen,
+                                              int h0, const KParams &P) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
+    const uint32_t NEG_E_DEL = pack2(-P.e_del), NEG_E_INS = pack2(-P.e_ins);
+    // pass-2 offsets of a lane's four columns from its first one: { 0, -e }, { -2e, -3e }
+    const uint32_t OFF01 = ((uint32_t)(-P.e_ins) & 0xFFFFu) << 16;
+    const uint32_t OFF23 = ((uint32_t)(-2 * P.e_ins) & 0xFFFFu) | (((uint32_t)(-3 * P.e_ins) & 0xFFFFu) << 16);
+    const int dec = 4 * P.e_ins;    // F decay across one lane (4 columns)
+    uint32_t LUT_LO, LUT_HI;
+    score_lut<WIDE>(P, LUT_LO, LUT_HI);
+    const uint32_t K16 = P.k16, KM = P.km, K1 = P.k1;
+
+    // ---- query selector seeds and row "-1" (bandedSWA.cpp:159-161), all lanes
+    {
+        const int nsel = sel_words(qlen);
+        if (!WIDE) {
+            for (int k = lane; k < nsel; k += 32) {
+                uint32_t v = (blob[k >> 2] >> (8 * (k & 3))) & 0xFFu;   // 4 bases, 2 bits each
+                v = (v | (v << 12)) & 0x000F000Fu;
+                v = (v | (v << 6)) & 0x03030303u;
+                R.QS2(k) = v * 0x11u;
+            }
+        } else {
+            for (int k = lane; k < nsel; k += 32) {
+                uint32_t v = (blob[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;  // 4 bases, 4 bits each
+                v = (v | (v << 8)) & 0x00FF00FFu;
+                v = (v | (v << 4)) & 0x0F0F0F0Fu;
+                R.QS2(k) = v * 0x11u;
+            }
+        }
+        R.tb = blob + (seq_bytes((uint32_t)qlen, WIDE) >> 2);
+        const int nel = row_elems(qlen);
+        for (int k = lane; k < nel; k += 32) {
+            uint32_t hv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = 4 * k + u;
+                int v = j == 0 ? h0 : max(h0 - oe_ins - (j - 1) * P.e_ins, 0);
+                if (j > qlen) v = 0;
+                hv[u] = (uint32_t)v;
+            }
+            uint4 w; w.x = hv[0] | (hv[1] << 16); w.y = 0u; w.z = hv[2] | (hv[3] << 16); w.w = 0u;
+            R.HE4(k) = w;
+        }
+    }
+    __syncwarp();
+
+    const int band = pair_band(P, qlen);
+    const int budget = min(qlen + band, tlen);
+    int best = h0, best_i = -1, best_j = -1, g_i = -1, gsc = -1, off = 0;
+    int beg = 0, end = qlen;
+    uint32_t tword = 0;
+    int hcol = h0 - P.o_del;
+    uint32_t cells = 0;
+
+    for (int i = 0; i < budget; ++i) {
+        if (beg < i - band) beg = i - band;
+        if (end > i + band + 1) end = i + band + 1;
+        if (beg >= end) break;
+        if (COUNT) cells += (uint32_t)(end - beg);   // beg is the reference's exact beg in this kernel
+
+        if ((i & 7) == 0) tword = R.template TG<WIDE>(i >> 3);
+        const uint32_t tsel = (tword & 7u) * 0x11111111u + 0x80808080u;
+        tword >>= 4;
+        hcol -= P.e_del;
+        const int hleft = beg == 0 ? max(hcol, 0) : 0;
+
+        // entries outside [beg, end) that share an element / a group with live columns must read as
+        // zero (see extend_pair); everything left of beg is zero already
+        if (lane == 0) {
+            if (beg & 3) R.setHE16(beg - 1, 0u, 0u);
+            if (end & 1) R.setHE16(end, 0u, 0u);
+        }
+        __syncwarp();
+
+        const int k0 = beg >> 2, k1 = (end - 1) >> 2, g1 = (end - 1) >> 1;
+        int Ftile = 0;                              // F(i, 4 * kb) entering the tile
+        uint32_t hcarry = (uint32_t)hleft << 16;    // .hi = H(i, 4 * kb - 1)
+        uint32_t rm = 0;                            // per lane: max per 16-bit half over its columns
+        int klo = 0, khi = 0;                       // per lane: element where a half last reached rm
+        uint32_t hw0 = 0, hw1 = 0;                  // this lane's H words of the last tile
+
+        for (int kb = k0; kb <= k1; kb += 32) {
+            const int k = kb + lane;
+            const bool act = k <= k1;
+            uint32_t M0 = 0, M1 = 0, T0 = 0, T1 = 0, E0 = 0, E1 = 0, Ev0 = 0, Ev1 = 0, B0 = 0, B1 = 0;
+            int Fout = 0;
+            if (act) {
+                // ---- pass 1: everything that does not need the incoming F
+                const uint4 a = R.HE4(k);
+                const uint32_t q01 = R.QS2(k);
+                uint32_t s0, s1;
+                if (WIDE || BSW_SEL_LOP3) { s0 = sel_combine(q01, tsel, 0x44444444u); s1 = __umulhi(s0, K16); }
+                else { s0 = q01 * K1 + tsel; s1 = __umulhi(s0, K16); }
+                auto front = [&](const uint32_t Hd, const uint32_t Ev, const uint32_t sel, uint32_t &M, uint32_t &Tins,
+                                 uint32_t &Enew) {
+                    const uint32_t sc = prmt_sx(LUT_LO, LUT_HI, sel);
+                    if (FASTM) {
+                        M = __viaddmin_s16x2(Hd, sc, Hd * KM);
+                    } else {
+                        const uint32_t sm = __vmins2(sc, __vmins2(Hd, 0x00010001u) * (uint32_t)P.match);
+                        M = __vadd2(Hd, sm);
+                    }
+                    const uint32_t Tdel = __viaddmax_s16x2_relu(M, NEG_OE_DEL, NEG_OE_DEL);
+                    Tins = SYM ? Tdel : __viaddmax_s16x2_relu(M, NEG_OE_INS, NEG_OE_INS);
+                    Enew = __viaddmax_s16x2(Ev, NEG_E_DEL, Tdel);
+                };
+                Ev0 = a.y; Ev1 = a.w;
+                front(a.x, a.y, s0, M0, T0, E0);
+                front(a.z, a.w, s1, M1, T1, E1);
+                // local F chain from F = 0 at the lane's first column
+                uint32_t A = 0;
+                uint32_t W1 = __viaddmax_s16x2(A, NEG_E_INS, T0);
+                B0 = W1 * K16 + A;
+                uint32_t W2 = __viaddmax_s16x2(B0, NEG_E_INS, T0);
+                A = __umulhi(W2, K16);
+                W1 = __viaddmax_s16x2(A, NEG_E_INS, T1);
+                B1 = W1 * K16 + A;
+                W2 = __viaddmax_s16x2(B1, NEG_E_INS, T1);
+                Fout = (int)__umulhi(W2, K16);      // F at the next lane's first column, given F = 0 here
+            }
+            // ---- max-plus scan of the lanes' outgoing F (inclusive), then this lane's incoming F
+            int x = Fout;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(FULL, x, d);
+                if (lane >= d) x = max(x, y - dec * d);
+            }
+            int Fin = __shfl_up_sync(FULL, x, 1);
+            Fin = lane == 0 ? Ftile : max(Fin, Ftile - dec * lane);
+            Ftile = max(__shfl_sync(FULL, x, 31), Ftile - dec * 32);
+            // ---- pass 2: H, shifted store, statistics
+            uint32_t h0w = 0, h1w = 0;
+            if (act) {
+                const uint32_t FinBB = (uint32_t)Fin * 0x00010001u;
+                B0 = __viaddmax_s16x2(FinBB, OFF01, B0);
+                B1 = __viaddmax_s16x2(FinBB, OFF23, B1);
+                h0w = __vimax3_s16x2(M0, Ev0, B0);
+                h1w = __vimax3_s16x2(M1, Ev1, B1);
+            }
+            uint32_t hp = __shfl_up_sync(FULL, h1w, 1);   // left neighbour's { H(4k-2), H(4k-1) }
+            if (lane == 0) hp = hcarry;
+            hcarry = __shfl_sync(FULL, h1w, 31);
+            if (act) {
+                const bool g1ok = 2 * k + 1 <= g1;          // the lane's second group holds a live column
+                uint4 o;
+                o.x = __umulhi(hp, K16) + h0w * K16;        // { H(4k-1), H(4k) }
+                o.y = E0;
+                o.z = __umulhi(h0w, K16) + h1w * K16;       // { H(4k+1), H(4k+2) }
+                o.w = E1;
+                if (g1ok) R.HE4(k) = o;
+                else R.HE(2 * k) = make_uint2(o.x, o.y);    // entries right of `end` keep their stale values
+                if (!g1ok) h1w = 0;                          // not part of the row
+                bool phi, plo;
+                rm = __vibmax_s16x2(__vmaxs2(h0w, h1w), rm, &phi, &plo);
+                if (plo) klo = k;
+                if (phi) khi = k;
+            }
+            hw0 = h0w; hw1 = h1w;
+        }
+        __syncwarp();
+
+        // ---- row end, all lanes with the same values
+        // H of the last column, and the reference's eh[end] = { h1, 0 }
+        int hlast;
+        {
+            const int src = (k1 - k0) & 31;                   // lane that owns element k1 in the last tile
+            const uint32_t w = __shfl_sync(FULL, (g1 & 1) ? hw1 : hw0, src);
+            hlast = (end & 1) ? (int)(w & 0xFFFFu) : (int)(w >> 16);
+            if (!(end & 1) && lane == 0) R.setHE16(end, (uint32_t)hlast, 0u);
+        }
+        if (end == qlen) {                                     // bandedSWA.cpp:218-221
+            if (!(gsc > hlast)) g_i = i;
+            gsc = max(gsc, hlast);
+        }
+        const int mlo = (int)(short)(rm & 0xFFFFu), mhi = (int)(short)(rm >> 16);
+        const int m = __reduce_max_sync(FULL, max(mlo, mhi));
+        if (m == 0) break;
+        // LAST column reaching m: H(i, j) sits in Hs[j + 1]; a lane whose half reached m looks its
+        // element up (columns at or right of `end` are never candidates: their H is below m)
+        __syncwarp();
+        int cand = -1;
+        if (mlo == m) {                                        // even columns 4k, 4k+2
+            const int c2 = 4 * klo + 2;
+            cand = (c2 < end && R.getH16(c2 + 1) == (uint32_t)m) ? c2 : 4 * klo;
+        }
+        if (mhi == m) {                                        // odd columns 4k+1, 4k+3
+            const int c3 = 4 * khi + 3;
+            cand = max(cand, (c3 < end && R.getH16(c3 + 1) == (uint32_t)m) ? c3 : 4 * khi + 1);
+        }
+        const int mj = __reduce_max_sync(FULL, cand);
+        if (m > best) {
+            best = m; best_i = i; best_j = mj;
+            off = max(off, abs(mj - i));
+        } else {
+            const int di = i - best_i, dj = mj - best_j;
+            if (best - m - abs(di - dj) > P.zdrop) break;
+        }
+
+        // leading trim, exact (bandedSWA.cpp:234): first j in [beg, end) with Hs[j] | E[j] != 0
+        {
+            int nb = end;
+            for (int kb = k0; kb <= k1; kb += 32) {
+                const int k = kb + lane;
+                uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                if (k <= k1) z = R.HE4(k);
+                const uint32_t w0 = z.x | z.y, w1 = z.z | z.w;
+                int first = 0x7FFFFFFF;
+                if (w0 | w1) first = 4 * k + ((w0 & 0xFFFFu) ? 0 : (w0 ? 1 : ((w1 & 0xFFFFu) ? 2 : 3)));
+                const int f = __reduce_min_sync(FULL, first);
+                if (f != 0x7FFFFFFF) { nb = min(f, end); break; }
+            }
+            beg = max(beg, nb);
+        }
+        // trailing trim (bandedSWA.cpp:236-237): j* = last j in [beg, end] with Hs[j] | E[j] != 0
+        if (hlast) {
+            end = min(end + 2, qlen);
+        } else {
+            int jstar = -1;
+            for (int kb = end >> 2; kb >= 0 && jstar < 0; kb -= 32) {
+                const int k = kb - lane;
+                int last = -1;
+                if (k >= 0) {
+                    const uint4 z = R.HE4(k);
+                    uint32_t w0 = z.x | z.y, w1 = z.z | z.w;
+                    // entries right of `end` are stale
+                    if (4 * k + 3 > end) w1 &= 0xFFFFu;
+                    if (4 * k + 2 > end) w1 = 0u;
+                    if (4 * k + 1 > end) w0 &= 0xFFFFu;
+                    if (w1 >> 16) last = 4 * k + 3;
+                    else if (w1) last = 4 * k + 2;
+                    else if (w0 >> 16) last = 4 * k + 1;
+                    else if (w0) last = 4 * k;
+                }
+                jstar = __reduce_max_sync(FULL, last);
+            }
+            end = min(jstar + 2, qlen);
+        }
+        __syncwarp();
+    }
+
+    PairResult r;
+    r.score = best; r.qle = best_j + 1; r.tle = best_i + 1;
+    r.gtle = g_i + 1; r.gscore = gsc; r.max_off = off;
+    r.cells = cells;
+    return r;
+}
+
+// Launch: block = 32 * warps_per_block threads, dynamic smem = warps_per_block * pair_bytes; pair p =
+// blockIdx.x * warps_per_block + warp of the launch's n_wide + n_narrow pairs (wide ones first).
 template <bool FASTM, bool SYM, bool COUNT>
-__global__ void __launch_bounds__(kBlockPairs)
+__global__ void __launch_bounds__(256)
 bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
                 const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
-                KParams P, int row_el, int qs_words, unsigned char *__restrict__ scratch) {
-    const int nthreads = gridDim.x * blockDim.x;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nwr = (n_wide + 31) & ~31;
-    const bool wide = t < nwr;
-    const int k = wide ? t : t - nwr + n_wide;
-    if (wide ? t >= n_wide : k >= n_wide + n_narrow) return;
-    const PairMeta m = meta[ord[k]];
+                KParams P, int row_el, int pair_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5;
+    const int p = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (p >= n_wide + n_narrow) return;
+    const PairMeta m = meta[ord[p]];
     Rows R;
-    R.stride = nthreads;
-    unsigned char *p = scratch;
-    R.he4 = reinterpret_cast<uint4 *>(p) + t;
-    p += (size_t)16 * row_el * nthreads;
-    R.qs = reinterpret_cast<uint32_t *>(p) + t;
-    (void)qs_words;
+    R.stride = 1;
+    R.he4 = reinterpret_cast<uint4 *>(smem + (size_t)warp * pair_bytes);
+    R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)warp * pair_bytes + (size_t)16 * row_el);
+    R.tb = nullptr;
     const uint32_t *src = blob + m.off;
     PairResult r;
-    if (wide) {
-        src = blob + src[0];
-        unpack_pair<true>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, true>(R, m.len2, m.len1, m.h0, P);
-    } else {
-        unpack_pair<false>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, false>(R, m.len2, m.len1, m.h0, P);
-    }
-    store_result(out, m.id, r);
+    if (p < n_wide) r = warp_extend_pair<FASTM, SYM, COUNT, true>(R, blob + src[0], m.len2, m.len1, m.h0, P);
+    else r = warp_extend_pair<FASTM, SYM, COUNT, false>(R, src, m.len2, m.len1, m.h0, P);
+    if ((threadIdx.x & 31) == 0) store_result(out, m.id, r);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -56,6 +56,48 @@ def test_band_widths(gpu, w):
     assert_same_outputs(b.outputs(), a.outputs(), b, f"w={w}")
 
 
+@pytest.mark.parametrize("w", [2, 7, 40, 100, 500])
+def test_long_pairs_warp_kernel(gpu, w):
+    """Queries of 300..1500 bases run the warp-per-pair kernel (tiles, max-plus scan of F, warp
+    reductions for the row decisions): narrow and wide bands, ambiguous bases, unrelated pairs."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 300, 1500, 0, 200, 0.3, 0.15
+    b = pairio.generate(c, 3000, seed=900 + w)
+    a = b.copy()
+    cells = oracle.oracle_batch(a, w=w)
+    gpu.batch(b.pairs, b.ref, b.qer, w)
+    assert gpu.stats()["pairs_long"] > 1000
+    assert_same_outputs(b.outputs(), a.outputs(), b, f"long pairs, w={w}")
+    gpu.stage(b.pairs, b.ref, b.qer, w)
+    assert gpu.count_staged() == cells                        # the warp kernel's beg is the reference's
+
+
+def test_long_pairs_nondefault_scoring():
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac = 350, 900, 0, 100, 0.2
+    b = pairio.generate(c, 1500, seed=77)
+    for params in (dict(o_del=5, e_del=2, o_ins=7, e_ins=1, zdrop=40, end_bonus=9, match=2, mismatch=3, ambig=-1),
+                   dict(o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=0, end_bonus=5, match=1, mismatch=4, ambig=-1)):
+        a = b.copy(); e = b.copy()
+        oracle.oracle_batch(a, w=60, params=params)
+        with bsw.BswGpu(**params) as g:
+            g.batch(e.pairs, e.ref, e.qer, 60)
+        assert_same_outputs(e.outputs(), a.outputs(), e, f"long pairs, {params}")
+
+
+def test_very_long_pair(gpu):
+    """One pair near the kernel's limits: 20k x 30k bases, a single warp with a 150 KB row."""
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 4, 20000).astype(np.uint8)
+    t = np.concatenate([q[:15000], rng.integers(0, 4, 15000).astype(np.uint8)])
+    t[::97] = (t[::97] + 1) & 3
+    b = pairio.from_sequences([(t, q, 100), (t[:5000], q[:4000], 50)])
+    a = b.copy()
+    oracle.oracle_batch(a)
+    gpu.batch(b.pairs, b.ref, b.qer, 100)
+    assert_same_outputs(b.outputs(), a.outputs(), b, "very long pair")
+
+
 def test_empty_single_and_ragged(gpu):
     e = pairio.from_sequences([([0], [0], 1)])
     gpu.batch(e.pairs[:0], e.ref, e.qer, 100)                  # n = 0 is a no-op
