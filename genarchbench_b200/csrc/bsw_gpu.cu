@@ -40,9 +40,10 @@ constexpr int64_t kSlabBases = 512ll << 20;    // bases per slab (upper bound)
 constexpr size_t kMaxSmem = 227 * 1024 - 64;   // opt-in shared memory per block on sm_100, minus the kernel's static bytes
 constexpr int kBinCols = 16;                   // query-length granularity of a launch bin
 constexpr int kVersion = 2;
-// device sort key of a pair, descending order = launch order:
-//   [30:20] launch bin (len2 - 1) / 16   [19] holds an ambiguous base   [18:15] (len2 - 1) % 16   [14:0] len1
-constexpr int kKeyBits = 31;
+// device sort key of a pair (64 bits), descending order = launch order:
+//   [47:37] launch bin (len2 - 1) / 16   [36] holds an ambiguous base   [35:32] (len2 - 1) % 16
+//   [30:16] len1   [15:0] h0
+constexpr int kKeyBits = 48;
 constexpr int kMaxBins = BSW_MAX_SEQ_LEN / kBinCols + 2;
 
 using Clock = std::chrono::steady_clock;
@@ -73,7 +74,7 @@ struct Slab {
     uint32_t *d_blob = nullptr;
     PairOut *d_out = nullptr;
     unsigned char *d_scratch = nullptr;
-    uint32_t *d_keys = nullptr;      // [2][cap_pairs] sort keys (in / out)
+    uint64_t *d_keys = nullptr;      // [2][cap_pairs] sort keys (in / out)
     uint32_t *d_ord = nullptr;       // [2][cap_pairs] pair indices (in / out): out = the binned order
     void *d_sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
@@ -91,14 +92,17 @@ struct Slab {
     bool pinned = true;      // false for staged slabs (host side borrowed)
 };
 
-constexpr int kAux = 4;   // launch streams per GPU: length bins of a slab run concurrently
+#ifndef BSW_AUX
+#define BSW_AUX 4
+#endif
+constexpr int kAux = BSW_AUX;   // launch streams per GPU: length bins of a slab run concurrently
 
 struct Device {
     int id = 0;
     Slab ring[kRing];
     std::vector<Slab *> staged;  // device-resident slabs of the staged API
-    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t aux_ev[kAux] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t aux[kAux] = {};
+    cudaEvent_t aux_ev[kAux] = {};
     cudaEvent_t fork_ev = nullptr;
     bool attr_set[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_long[8] = {false, false, false, false, false, false, false, false};
@@ -175,8 +179,8 @@ int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
         if (s.d_keys) cudaFree(s.d_keys);
         if (s.d_ord) cudaFree(s.d_ord);
         if (s.d_sort_tmp) cudaFree(s.d_sort_tmp);
-        s.d_keys = s.d_ord = nullptr; s.d_sort_tmp = nullptr;
-        CU(cudaMalloc((void **)&s.d_keys, sizeof(uint32_t) * 2 * cap));
+        s.d_keys = nullptr; s.d_ord = nullptr; s.d_sort_tmp = nullptr;
+        CU(cudaMalloc((void **)&s.d_keys, sizeof(uint64_t) * 2 * cap));
         CU(cudaMalloc((void **)&s.d_ord, sizeof(uint32_t) * 2 * cap));
         s.sort_tmp_bytes = 0;
         CU(cub::DeviceRadixSort::SortPairsDescending(nullptr, s.sort_tmp_bytes, s.d_keys, s.d_keys + cap, s.d_ord,
