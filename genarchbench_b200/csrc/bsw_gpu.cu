@@ -56,6 +56,7 @@ struct Launch {
     int n;           // pairs (the n_wide pairs holding an ambiguous base come first)
     int n_wide;
     int row_el, qs_words;   // per pair: uint4 row elements, u32 selector words
+    int duo_el;             // per duo thread: row elements of two columns
     size_t smem;     // 0 => long kernel
     int64_t work;    // sum len1*len2, for ordering
 };
@@ -106,6 +107,7 @@ struct Device {
     cudaEvent_t fork_ev = nullptr;
     bool attr_set[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_long[8] = {false, false, false, false, false, false, false, false};
+    bool attr_set_duo[8] = {false, false, false, false, false, false, false, false};
 };
 
 }  // namespace
@@ -207,6 +209,14 @@ int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
 
 inline size_t smem_need(int row_el, int qs_words) {
     return ((size_t)16 * row_el + (size_t)4 * qs_words) * kBlockPairs;
+}
+// BSW_DUO=1 routes the short bins to the two-pairs-per-thread kernel (bsw_pair2.cuh) instead of the
+// one-pair-per-thread kernel. It is bit-exact and issues fewer instructions per cell, but each thread
+// then owns two pairs' rows, the shared memory holds half as many warps, and on B200 it measured
+// 41.8 ms against 22.2 ms per 10 M config-3 pairs -- kept for A/B runs, not the default.
+inline bool use_duo() {
+    static const bool v = getenv("BSW_DUO") && getenv("BSW_DUO")[0] == '1';
+    return v;
 }
 
 // Validates and packs slab [lo, lo+n) of the caller's arrays into s (host side), in one parallel pass
@@ -348,7 +358,8 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             L.first = p; L.n = nw + nn; L.n_wide = nw; L.work = (int64_t)(nw + nn) * q_hi * q_hi;
             L.row_el = row_elems(q_hi);
             L.qs_words = sel_words(q_hi);
-            L.smem = smem_need(L.row_el, L.qs_words);
+            L.duo_el = duo_elems(q_hi);
+            L.smem = use_duo() ? (size_t)duo_thread_bytes(q_hi) * kDuoThreads : smem_need(L.row_el, L.qs_words);
             if (L.smem > kMaxSmem) L.smem = 0;  // long kernel
             s.launches.push_back(L);
             p += nw + nn;
@@ -391,15 +402,17 @@ int ensure_aux(bsw_handle *h, Device &dev) {
 
 // The kernel instantiations, indexed [fastm][sym][count].
 typedef void (*ShortFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
+typedef void (*DuoFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int);
 typedef void (*LongFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
 template <int I> struct KernelTable {
-    static void fill(ShortFn *sf, LongFn *lf) {
+    static void fill(ShortFn *sf, LongFn *lf, DuoFn *df) {
         sf[I] = bsw_short_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
         lf[I] = bsw_long_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
-        KernelTable<I - 1>::fill(sf, lf);
+        df[I] = bsw_duo_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
+        KernelTable<I - 1>::fill(sf, lf, df);
     }
 };
-template <> struct KernelTable<-1> { static void fill(ShortFn *, LongFn *) {} };
+template <> struct KernelTable<-1> { static void fill(ShortFn *, LongFn *, DuoFn *) {} };
 inline int kernel_index(bool fastm, bool sym, bool count) {
     return (fastm ? 4 : 0) | (sym ? 2 : 0) | (count ? 1 : 0);
 }
@@ -410,8 +423,9 @@ inline int kernel_index(bool fastm, bool sym, bool count) {
 int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs, bool count = false) {
     static ShortFn short_fn[8];
     static LongFn long_fn[8];
+    static DuoFn duo_fn[8];
     static bool filled = false;
-    if (!filled) { KernelTable<7>::fill(short_fn, long_fn); filled = true; }
+    if (!filled) { KernelTable<7>::fill(short_fn, long_fn, duo_fn); filled = true; }
     int rc = ensure_aux(h, dev);
     if (rc) return rc;
     CU(cudaEventRecord(dev.fork_ev, main));
@@ -422,7 +436,17 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
         for (const Launch &L : s.launches) {
             const int grid = (launch_threads(L.n_wide, L.n - L.n_wide) + kBlockPairs - 1) / kBlockPairs;
             const int ki = kernel_index(s.fastm, h->sym, count);
-            if (L.smem) {
+            if (L.smem && use_duo()) {
+                if (!dev.attr_set_duo[ki]) {
+                    CU(cudaFuncSetAttribute(duo_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                    dev.attr_set_duo[ki] = true;
+                }
+                cudaStream_t st = dev.aux[rr++ % kAux];
+                const int threads = (L.n + 1) / 2;
+                duo_fn[ki]<<<(threads + kDuoThreads - 1) / kDuoThreads, kDuoThreads, L.smem, st>>>(
+                    s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, h->K,
+                    L.duo_el);
+            } else if (L.smem) {
                 if (!dev.attr_set[ki]) {
                     CU(cudaFuncSetAttribute(short_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
                     dev.attr_set[ki] = true;

@@ -179,6 +179,22 @@ struct Rows {
     }
 };
 
+// dst = p ? g * k1 + c : dst   with k1 == 1 read from the parameter bank: a PREDICATED IMAD on the FMA
+// pipe instead of the SEL the compiler emits for `if (p) dst = g + c` (the ALU pipe bounds the kernel).
+#ifndef BSW_SEL_IMAD
+#define BSW_SEL_IMAD 0   // measured: ptxas if-converts it back into IMAD + SEL
+#endif
+template <int C>
+__device__ __forceinline__ void mov_if(int &dst, bool p, int g, uint32_t k1) {
+#if defined(BSW_HOST_EMUL) || !BSW_SEL_IMAD
+    (void)k1;
+    if (p) dst = g + C;
+#else
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\t@q mad.lo.s32 %0, %2, %3, %4;\n\t}"
+        : "+r"(dst) : "r"((unsigned)p), "r"(g), "r"((int)k1), "n"(C));
+#endif
+}
+
 // PTX prmt.b32 (default mode): byte i of the result = byte (nibble_i & 7) of {b:a}; nibble bit 3 set
 // => that byte's SIGN replicated instead. Only the low 16 bits of the selector are used.
 // (__byte_perm() masks the selector with 0x7777 and loses the sign mode, so the instruction is
@@ -449,10 +465,10 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                 R.HE4(k + 1) = ob;
                 Hst = ob.z; En = E3;
                 bool phi, plo;
-                rm = __vibmax_s16x2(h0v, rm, &phi, &plo); if (plo) ilo = g;     if (phi) ihi = g;
-                rm = __vibmax_s16x2(h1v, rm, &phi, &plo); if (plo) ilo = g + 1; if (phi) ihi = g + 1;
-                rm = __vibmax_s16x2(h2v, rm, &phi, &plo); if (plo) ilo = g + 2; if (phi) ihi = g + 2;
-                rm = __vibmax_s16x2(h, rm, &phi, &plo);   if (plo) ilo = g + 3; if (phi) ihi = g + 3;
+                rm = __vibmax_s16x2(h0v, rm, &phi, &plo); mov_if<0>(ilo, plo, g, K1); mov_if<0>(ihi, phi, g, K1);
+                rm = __vibmax_s16x2(h1v, rm, &phi, &plo); mov_if<1>(ilo, plo, g, K1); mov_if<1>(ihi, phi, g, K1);
+                rm = __vibmax_s16x2(h2v, rm, &phi, &plo); mov_if<2>(ilo, plo, g, K1); mov_if<2>(ihi, phi, g, K1);
+                rm = __vibmax_s16x2(h, rm, &phi, &plo);   mov_if<3>(ilo, plo, g, K1); mov_if<3>(ihi, phi, g, K1);
                 if (!BSW_PREFETCH && more) {
                     na = R.HE4(k + 2); nb = R.HE4(k + 3);
                     nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
@@ -566,6 +582,10 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
     return r;
 }
 
+}  // namespace bswk
+#include "bsw_pair2.cuh"
+namespace bswk {
+
 #ifndef BSW_HOST_EMUL
 __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const PairResult &r) {
     union { PairOut o; uint4 v; } u;
@@ -621,6 +641,51 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
         r = extend_pair<FASTM, SYM, COUNT, false>(R, m.len2, m.len1, m.h0, P);
     }
     store_result(out, m.id, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Short pairs, two per thread (extend_duo, bsw_pair2.cuh). Launch: block = kDuoThreads, dynamic smem =
+// 20 * elems * kDuoThreads. Thread t takes the launch's sorted pairs 2t and 2t + 1 (neighbours in
+// (len2, len1, h0) order). A warp whose first thread still falls among the n_wide pairs holding an
+// ambiguous base runs the LOP3-selector instantiation for all of its threads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDuoThreads = 64;
+
+template <bool FASTM, bool SYM, bool COUNT>
+__global__ void __launch_bounds__(kDuoThreads)
+bsw_duo_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
+               const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
+               KParams P, int elems) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NT = kDuoThreads;
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * NT + tid;
+    const int n = n_wide + n_narrow;
+    if (2 * t >= n) return;
+    const bool twide = 2 * (t & ~31) < n_wide;       // warp-uniform
+    const PairMeta mA = meta[ord[2 * t]];
+    const bool hasB = 2 * t + 1 < n;
+    PairMeta mB = mA;
+    if (hasB) mB = meta[ord[2 * t + 1]];
+
+    Rows2 R;
+    R.stride = NT;
+    R.he4 = reinterpret_cast<uint4 *>(smem) + tid;
+    R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)16 * elems * NT) + tid;
+
+    DuoLane L[2];
+    L[0].qlen = mA.len2; L[0].tlen = mA.len1; L[0].h0 = mA.h0; L[0].wide_blob = mA.flags & 1;
+    L[1].qlen = hasB ? mB.len2 : 0; L[1].tlen = hasB ? mB.len1 : 0; L[1].h0 = hasB ? mB.h0 : 0;
+    L[1].wide_blob = hasB && (mB.flags & 1);
+    const uint32_t *bA = blob + mA.off, *bB = blob + mB.off;
+    if (L[0].wide_blob) bA = blob + bA[0];
+    if (L[1].wide_blob) bB = blob + bB[0];
+    duo_unpack(bA, bB, L, R);
+    PairResult r[2];
+    if (twide) extend_duo<FASTM, SYM, COUNT, true>(R, L, P, r);
+    else extend_duo<FASTM, SYM, COUNT, false>(R, L, P, r);
+    store_result(out, mA.id, r[0]);
+    if (hasB) store_result(out, mB.id, r[1]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,10 +24,11 @@ def emul():
                     os.path.join(d, "emul_lib.cpp")], check=True)
     L = C.CDLL(so)
     L.bsw_emul_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+    L.bsw_emul_batch_duo.argtypes = L.bsw_emul_batch.argtypes
 
-    def run(b, w=100, params=None):
-        L.bsw_emul_batch(oracle._params_array(params), b.pairs.ctypes.data, b.ref.ctypes.data,
-                         b.qer.ctypes.data, len(b), w)
+    def run(b, w=100, params=None, duo=False):
+        fn = L.bsw_emul_batch_duo if duo else L.bsw_emul_batch
+        fn(oracle._params_array(params), b.pairs.ctypes.data, b.ref.ctypes.data, b.qer.ctypes.data, len(b), w)
         return b.outputs()
     return run
 
@@ -36,6 +37,24 @@ def emul():
 def test_device_code_matches_golden(emul, name):
     b, w, params, want = load_golden(name)
     assert_same_outputs(emul(b, w, params), want, b, f"emulated kernel vs golden[{name}]")
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_duo_code_matches_golden(emul, name):
+    """Two pairs per thread (extend_duo): neighbours in the fixture's order share the DPX lanes."""
+    b, w, params, want = load_golden(name)
+    assert_same_outputs(emul(b, w, params, duo=True), want, b, f"emulated duo kernel vs golden[{name}]")
+
+
+@pytest.mark.parametrize("w", [1, 2, 5, 17, 100])
+def test_duo_code_matches_oracle_on_small_bands(emul, w):
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 200, 0, 60, 0.3, 0.2
+    b = pairio.generate(c, 6001, seed=300 + w)                # odd count: the last thread has one pair
+    a = b.copy()
+    cells = oracle.oracle_batch(a, w=w)
+    assert_same_outputs(emul(b, w, duo=True), a.outputs(), b, f"emulated duo kernel vs oracle, w={w}")
+    assert int(b.pairs["seqid"].astype(np.int64).sum()) == cells  # COUNT variant: the reference's cells
 
 
 @pytest.mark.parametrize("w", [1, 2, 5, 17, 100])
