@@ -67,6 +67,7 @@ WORKLOAD = ("bsw config 3 (large-shape): synthetic 151-bp read / ref-window exte
             "w=100, match 1 / mismatch 4 / gap 6+1 / zdrop 100 / end bonus 5")
 INSTR_PER_CELL = 2.5          # 5 packed-s16x2 DPX instructions per 2 cells
 BYTES_PER_PAIR_FMT = "ceil(len1/4)+ceil(len2/4)+12+24"
+DRAM_BYTES_PER_PAIR_NCU = 202.1   # measured, see roofline.traffic
 
 
 class ClockSampler:
@@ -267,11 +268,14 @@ def main():
     alg_bytes = algorithmic_bytes(batch.pairs)
     achieved_instr = cells / (dev_ms / args.steps * 1e-3) * INSTR_PER_CELL / 1e9   # this rank's GPU
     roofline = {
-        "bound": "dpx_int", "kernel": "bsw_short_kernel<1,1,0> (thread-per-pair, s16x2 DPX)",
+        "bound": "dpx_int", "kernel": "bsw_short_kernel<1,1,0> (thread-per-pair, s16x2 DPX; > 93 % of the step)",
         "achieved": achieved_instr, "peak": dpx_peak, "unit": "Ginstr/s (packed s16x2 thread-instructions)",
         "frac": achieved_instr / dpx_peak, "instr_per_cell": INSTR_PER_CELL,
         "peak_source": "measured live: VIADDMNMX.S16x2.RELU issue rate, all SMs (bsw_gpu_dpx_peak)",
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the DP kernels, one ncu capture of this workload at
+        # 10 M pairs (profiles/r1_dram_bytes_per_launch_10Mpairs.csv): 202.1 bytes per pair, scaled to this run
+        "traffic": int(DRAM_BYTES_PER_PAIR_NCU * len(batch)), "traffic_unit": "bytes per step (DP kernels)",
+        "traffic_source": "ncu, profiles/r1_dram_bytes_per_launch_10Mpairs.csv, per pair x pairs of this run",
         "hbm": {"algorithmic_bytes_per_step": alg_bytes, "bytes_per_pair": BYTES_PER_PAIR_FMT,
                 "achieved_gbs": alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
                 "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json (of measured)"

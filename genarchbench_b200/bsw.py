@@ -28,7 +28,7 @@ ERRORS = {1: "BSW_ERR_ARG", 2: "BSW_ERR_NO_DEVICE", 3: "BSW_ERR_CUDA", 4: "BSW_E
           5: "BSW_ERR_RANGE", 6: "BSW_ERR_STATE"}
 
 # every symbol include/bsw_gpu.h declares
-EXPORTS = ("bsw_gpu_init", "bsw_gpu_init_devices", "bsw_gpu_free", "bsw_gpu_batch", "bsw_gpu_stage",
+EXPORTS = ("bsw_gpu_init", "bsw_gpu_init_devices", "bsw_gpu_free", "bsw_gpu_batch", "bsw_gpu_batch_retry", "bsw_gpu_stage",
            "bsw_gpu_run_staged", "bsw_gpu_fetch_staged", "bsw_gpu_count_staged", "bsw_gpu_get_stats", "bsw_gpu_dpx_peak",
            "bsw_gpu_strerror", "bsw_gpu_last_error", "bsw_gpu_version")
 
@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         L.bsw_gpu_free.argtypes = [vp]
         L.bsw_gpu_free.restype = None
         L.bsw_gpu_batch.argtypes = [vp, vp, vp, vp, i64, i32]
+        L.bsw_gpu_batch_retry.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
         L.bsw_gpu_stage.argtypes = [vp, vp, vp, vp, i64, i32]
         L.bsw_gpu_run_staged.argtypes = [vp, C.POINTER(C.c_float)]
         L.bsw_gpu_fetch_staged.argtypes = [vp, vp, i64]
@@ -123,6 +124,14 @@ class BswGpu:
         """bsw_gpu_batch: end to end from host buffers; fills the six outputs in place."""
         a, b, c = self._ptrs(pairs, ref, qer)
         self._check(self._L.bsw_gpu_batch(self._h, a, b, c, len(pairs) if n is None else n, w))
+
+    def batch_retry(self, pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int = DEFAULT_W,
+                    max_tries: int = 2) -> np.ndarray:
+        """bsw_gpu_batch_retry: bwa-mem2's band-doubling loop (MAX_BAND_TRY = 2); returns tries per pair."""
+        a, b, c = self._ptrs(pairs, ref, qer)
+        tries = np.zeros(len(pairs), dtype=np.int32)
+        self._check(self._L.bsw_gpu_batch_retry(self._h, a, b, c, len(pairs), w, max_tries, tries.ctypes.data))
+        return tries
 
     def stage(self, pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int = DEFAULT_W) -> None:
         a, b, c = self._ptrs(pairs, ref, qer)

@@ -770,6 +770,60 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
     return rc;
 }
 
+// ---- the production caller's band-doubling retry (bwa-mem2 bwamem.cpp:2448-2508) --------------------
+
+int bsw_gpu_batch_retry(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                        int64_t n, int32_t w, int32_t max_tries, int32_t *tries) {
+    if (!h || n < 0 || (n > 0 && (!pairs || !ref || !qer)) || w < 0 || max_tries < 1 || max_tries > 16 ||
+        ((int64_t)w << (max_tries - 1)) > 0x3FFFFFFF)
+        return BSW_ERR_ARG;
+    // try 0 over everything, in place
+    int rc = bsw_gpu_batch(h, pairs, ref, qer, n, w);
+    if (rc) return rc;
+    bsw_gpu_stats total = h->stats;
+    if (tries) for (int64_t k = 0; k < n; ++k) tries[k] = 1;
+    std::vector<int64_t> act;          // caller indices still being retried
+    std::vector<bsw_seqpair> aux;      // their records, compacted (bwamem.cpp: pair_ar_aux)
+    std::vector<int32_t> prev;
+    for (int t = 0; t + 1 < max_tries; ++t) {
+        const int32_t wt = w << t;
+        const int32_t lim = (wt >> 1) + (wt >> 2);
+        // a pair is final if its score did not change or its alignment stayed within 3/4 of the band
+        // (bwamem.cpp:2479-2480; the score before the first try is -1, as in bwa's mem_chain2aln)
+        if (t == 0) {
+            for (int64_t k = 0; k < n; ++k)
+                if (pairs[k].max_off >= lim) act.push_back(k);
+        } else {
+            std::vector<int64_t> next;
+            std::vector<int32_t> nprev;
+            for (size_t a = 0; a < act.size(); ++a) {
+                const bsw_seqpair &sp = aux[a];
+                if (!(sp.score == prev[a] || sp.max_off < lim)) next.push_back(act[a]);
+            }
+            act.swap(next);
+        }
+        if (act.empty()) break;
+        aux.resize(act.size());
+        prev.resize(act.size());
+        for (size_t a = 0; a < act.size(); ++a) { aux[a] = pairs[act[a]]; prev[a] = aux[a].score; }
+        rc = bsw_gpu_batch(h, aux.data(), ref, qer, (int64_t)aux.size(), w << (t + 1));
+        if (rc) return rc;
+        total.kernel_launches += h->stats.kernel_launches;
+        total.h2d_bytes += h->stats.h2d_bytes; total.d2h_bytes += h->stats.d2h_bytes;
+        total.kernel_ms += h->stats.kernel_ms; total.wall_ms += h->stats.wall_ms;
+        for (size_t a = 0; a < act.size(); ++a) {
+            bsw_seqpair &dst = pairs[act[a]];
+            const bsw_seqpair &sp = aux[a];
+            dst.score = sp.score; dst.tle = sp.tle; dst.gtle = sp.gtle; dst.qle = sp.qle;
+            dst.gscore = sp.gscore; dst.max_off = sp.max_off;
+            if (tries) tries[act[a]] = t + 2;
+        }
+    }
+    total.pairs = n;
+    h->stats = total;
+    return BSW_OK;
+}
+
 // ---- staged API --------------------------------------------------------------------------------
 
 int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,

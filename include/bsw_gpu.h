@@ -51,11 +51,22 @@ void bsw_gpu_free(bsw_handle *h);
  * pairs[k].idr / .idq are byte offsets into ref / qer, .len1 / .len2 the lengths, .h0 the seed score.
  * Writes only score, tle, gtle, qle, gscore, max_off of pairs[0..n).
  * Valid domain (the reference's int16 kernel, SURVEY.md 8a note 4):
- *   0 <= len1, len2 <= BSW_MAX_SEQ_LEN, 0 <= h0, h0 + len2*match <= 32767; otherwise BSW_ERR_RANGE
- *   and nothing is written. One call at a time per handle (same rule as one object per thread in
+ *   0 <= len1, len2 <= BSW_MAX_SEQ_LEN, 0 <= h0, h0 + len2*match <= 32767; otherwise BSW_ERR_RANGE.
+ *   Validation runs slab by slab (~1 M pairs) together with packing: on BSW_ERR_RANGE the slab holding
+ *   the offending pair and every later slab are untouched; earlier slabs may already hold results. One call at a time per handle (same rule as one object per thread in
  *   the reference, bandedSWA.cpp:2771). */
 int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
                   int64_t n, int32_t w);
+
+/* == the band-doubling retry loop the production caller wraps around getScores16
+ * (bwa-mem2, benchmarks/fmi/bwa-mem2/x86_64/src/bwamem.cpp:2448-2508, MAX_BAND_TRY at :51):
+ *   for t in 0 .. max_tries-1:  run the pairs still active with band w << t;
+ *   a pair is final after try t if its score equals its score of the previous try (-1 before the first),
+ *   or max_off < (w<<t)/2 + (w<<t)/4, or t is the last try; the others are compacted and re-run.
+ * On return every pair holds the six outputs of its LAST try; tries[k] (nullable) = tries pair k took.
+ * Same domain / error rules as bsw_gpu_batch. */
+int bsw_gpu_batch_retry(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                        int64_t n, int32_t w, int32_t max_tries, int32_t *tries);
 
 /* ---- staged variant of the same path, for measurement (bench.py `value` vs `e2e`) ----
  * stage:  bin + pack + host->device; inputs stay resident in HBM.

@@ -98,6 +98,34 @@ def test_very_long_pair(gpu):
     assert_same_outputs(b.outputs(), a.outputs(), b, "very long pair")
 
 
+def test_band_doubling_retry_matches_reference_loop(gpu):
+    """bsw_gpu_batch_retry == the production caller's loop around getScores16 (bwamem.cpp:2448-2508),
+    replayed with the oracle: final outputs and the number of tries per pair."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.indel_rate = 40, 400, 10, 80, 0.05
+    b = pairio.generate(c, 20000, seed=4242)
+    w, max_tries = 8, 3
+    want = b.copy()
+    tries_want = np.zeros(len(b), dtype=np.int32)
+    active = np.arange(len(b))
+    prev = np.full(len(b), -1, dtype=np.int64)
+    for t in range(max_tries):
+        wt = w << t
+        sub = pairio.PairBatch(want.pairs[active].copy(), b.ref, b.qer)
+        oracle.oracle_batch(sub, w=wt)
+        for f in pairio.OUTPUT_FIELDS:
+            want.pairs[f][active] = sub.pairs[f]
+        tries_want[active] = t + 1
+        final = (sub.pairs["score"] == prev[active]) | (sub.pairs["max_off"] < (wt >> 1) + (wt >> 2))
+        prev[active] = sub.pairs["score"]
+        active = active[~final]
+        if len(active) == 0:
+            break
+    tries = gpu.batch_retry(b.pairs, b.ref, b.qer, w, max_tries)
+    assert_same_outputs(b.outputs(), want.outputs(), b, "band-doubling retry")
+    assert (tries == tries_want).all() and tries.max() == max_tries and (tries == 1).any()
+
+
 def test_empty_single_and_ragged(gpu):
     e = pairio.from_sequences([([0], [0], 1)])
     gpu.batch(e.pairs[:0], e.ref, e.qer, 100)                  # n = 0 is a no-op
