@@ -35,15 +35,26 @@ using namespace bswk;
 namespace {
 
 constexpr int kRing = 3;                       // slabs in flight per GPU
-constexpr int64_t kSlabPairs = 1 << 20;        // pairs per slab (upper bound)
+// pairs per slab (upper bound); BSW_SLAB_PAIRS overrides (tuning). The streaming path wants small slabs
+// (host packing, GPU and scatter overlap slab by slab: 1 Mi measured best end to end), the resident path
+// larger ones (more blocks per launch, shorter tails: 4 Mi is 4 % faster than 1 Mi on the device).
+constexpr int64_t kSlabPairsBatch = 1 << 20, kSlabPairsStaged = 4 << 20;
+inline int64_t slab_pairs(bool staged) {
+    static const int64_t v = [] {
+        const char *e = getenv("BSW_SLAB_PAIRS");
+        const int64_t x = e ? atoll(e) : 0;
+        return x >= 65536 ? x : 0;
+    }();
+    return v ? v : (staged ? kSlabPairsStaged : kSlabPairsBatch);
+}
 constexpr int64_t kSlabBases = 512ll << 20;    // bases per slab (upper bound)
 constexpr size_t kMaxSmem = 227 * 1024 - 64;   // opt-in shared memory per block on sm_100, minus the kernel's static bytes
 constexpr int kBinCols = 16;                   // query-length granularity of a launch bin
 constexpr int kVersion = 2;
 // device sort key of a pair (64 bits), descending order = launch order:
-//   [47:37] launch bin (len2 - 1) / 16   [36] holds an ambiguous base   [35:32] (len2 - 1) % 16
-//   [30:16] len1   [15:0] h0
-constexpr int kKeyBits = 48;
+//   launch bin (len2 - 1) / 16 | holds an ambiguous base | (len2 - 1) % 16 | len1 (b1 bits) | h0 (b0 bits)
+// with b1, b0 sized per slab; at most 16 + 15 + 15 bits
+constexpr int kKeyBits = 46;
 constexpr int kMaxBins = BSW_MAX_SEQ_LEN / kBinCols + 2;
 
 using Clock = std::chrono::steady_clock;
@@ -89,6 +100,7 @@ struct Slab {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     bool busy = false;
+    int key_b1 = 15, key_b0 = 16, key_bits = 48;   // sort key layout of the current contents (see sort_key)
     bool fastm = false;      // every score of the slab times (match+1) fits int16: one-instruction M
     bool pinned = true;      // false for staged slabs (host side borrowed)
 };
@@ -231,8 +243,42 @@ inline bool use_duo() {
 // Returns BSW_OK, an error, or kRetry with s.blob_bytes = the capacity the slab really needs.
 constexpr int kRetry = -1;
 
+// Results of an older slab that still have to go into the caller's SeqPair array. prepare_slab works
+// them off inside its own parallel loop, interleaved with the packing chunks: the scatter is pure memory
+// traffic (a read-for-ownership of every 72-byte record), the packer is half arithmetic, and together
+// they fill the cores better than one after the other.
+struct ScatterJob {
+    const PairOut *out = nullptr;
+    bsw_seqpair *dst = nullptr;
+    int n = 0;
+};
+constexpr int kScatterChunk = 8192;
+
+struct ScatterJobs {
+    ScatterJob j[4];
+    int first_chunk[5] = {0, 0, 0, 0, 0};   // chunk index ranges of the jobs
+    int count = 0;
+    void add(const ScatterJob &x) {
+        if (count >= 4 || x.n <= 0) return;
+        j[count] = x;
+        first_chunk[count + 1] = first_chunk[count] + (x.n + kScatterChunk - 1) / kScatterChunk;
+        ++count;
+    }
+    int chunks() const { return first_chunk[count]; }
+};
+
+inline void scatter_chunk(const ScatterJob &j, int c) {
+    const int k1 = std::min(j.n, (c + 1) * kScatterChunk);
+    for (int k = c * kScatterChunk; k < k1; ++k) {
+        const PairOut &o = j.out[k];
+        bsw_seqpair &p = j.dst[k];
+        p.score = o.score; p.qle = o.qle; p.tle = o.tle;
+        p.gtle = o.gtle; p.gscore = o.gscore; p.max_off = o.max_off;
+    }
+}
+
 int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t *ref,
-                 const uint8_t *qer, int64_t lo, int n) {
+                 const uint8_t *qer, int64_t lo, int n, const ScatterJobs &jobs) {
     constexpr int kChunk = 2048;
     const bsw_seqpair *pp = pairs + lo;
     bsw_gpu_stats &st = h->stats;
@@ -242,22 +288,33 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     auto t0 = Clock::now();
 
     const int nchunks = (n + kChunk - 1) / kChunk;
+    const int nscat = jobs.chunks();
+    const int nitems = nchunks + nscat;
     const int T = omp_get_max_threads();
     const int match = h->P.match;
     const size_t cap_words = s.cap_blob / 4 > 16 ? s.cap_blob / 4 - 16 : 0;
     uint8_t *blob = reinterpret_cast<uint8_t *>(s.h_blob);
     std::atomic<uint64_t> cursor{0};
-    int bad = 0, maxq = 0, maxsc = 0, overflow = 0;
+    int bad = 0, maxq = 0, maxsc = 0, maxt = 0, maxh = 0, overflow = 0;
     h->hist.assign((size_t)T * 2 * kMaxBins, 0);
     std::vector<std::vector<uint32_t>> triv((size_t)T);
     const int packer = pack_have_avx2() ? 2 : (pack_have_pext() ? 1 : 0);
 
-#pragma omp parallel num_threads(T) reduction(| : bad) reduction(| : overflow) reduction(max : maxq) reduction(max : maxsc)
+#pragma omp parallel num_threads(T) reduction(| : bad) reduction(| : overflow) reduction(max : maxq) reduction(max : maxsc) reduction(max : maxt) reduction(max : maxh)
     {
         const int t = omp_get_thread_num();
         uint32_t *hist = h->hist.data() + (size_t)t * 2 * kMaxBins;
+        // work items: the packing chunks, with the scatter chunks of `job` spread evenly between them
 #pragma omp for schedule(dynamic, 2)
-        for (int c = 0; c < nchunks; ++c) {
+        for (int it = 0; it < nitems; ++it) {
+            const int sc_before = (int)((int64_t)it * nscat / nitems);
+            if ((int)((int64_t)(it + 1) * nscat / nitems) > sc_before) {
+                int jj = 0;
+                while (sc_before >= jobs.first_chunk[jj + 1]) ++jj;
+                scatter_chunk(jobs.j[jj], sc_before - jobs.first_chunk[jj]);
+                continue;
+            }
+            const int c = it - sc_before;
             const int k0 = c * kChunk, k1 = std::min(n, k0 + kChunk);
             // ---- loop A
             uint64_t words = 0;
@@ -324,6 +381,8 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                     hist[wide * kMaxBins + (uint32_t)(sp.len2 - 1) / kBinCols] += 1;
                     maxq = std::max(maxq, sp.len2);
                     maxsc = std::max(maxsc, sp.h0 + sp.len2 * match);
+                    maxt = std::max(maxt, sp.len1);
+                    maxh = std::max(maxh, sp.h0);
                 }
                 off += sw;
             }
@@ -336,6 +395,9 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     if (overflow) return kRetry;
     memset(blob + (size_t)total_words * 4, 0, 16);
     s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
+    s.key_b1 = bits_for((uint32_t)maxt);
+    s.key_b0 = bits_for((uint32_t)maxh);
+    s.key_bits = s.key_b1 + s.key_b0 + bits_for(((((uint32_t)std::max(maxq, 1) - 1) >> 4) << 5) | 31u);
     for (int t = 0; t < T; ++t) s.trivial.insert(s.trivial.end(), triv[(size_t)t].begin(), triv[(size_t)t].end());
     s.n_dev = n - (int)s.trivial.size();
     st.host_pack_ms += ms_since(t0);
@@ -372,14 +434,15 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
 // prepare_slab with the (rare) capacity retry: the first pass over a slab whose blob does not fit the
 // ring slot reports the exact size, the slot grows, the pass runs again.
 int prepare_slab_fit(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
-                     int64_t lo, int n, size_t blob_guess) {
+                     int64_t lo, int n, size_t blob_guess, ScatterJobs jobs = ScatterJobs()) {
     auto t0 = Clock::now();
     int rc = ensure_slab(h, s, n, blob_guess);
     h->stats.host_alloc_ms += ms_since(t0);
     if (rc) return rc;
     for (int attempt = 0; attempt < 3; ++attempt) {
-        rc = prepare_slab(h, s, pairs, ref, qer, lo, n);
+        rc = prepare_slab(h, s, pairs, ref, qer, lo, n, jobs);
         if (rc != kRetry) return rc;
+        jobs = ScatterJobs();   // done (a scatter is idempotent anyway)
         t0 = Clock::now();
         rc = ensure_slab(h, s, n, s.blob_bytes + (s.blob_bytes >> 3) + 4096);
         h->stats.host_alloc_ms += ms_since(t0);
@@ -485,12 +548,12 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
 int bin_slab(bsw_handle *h, Slab &s, cudaStream_t st) {
     if (s.n_dev == 0) return BSW_OK;
     const int n = s.n;
-    bsw_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_meta, n, s.d_keys, s.d_ord);
+    bsw_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_meta, n, s.d_keys, s.d_ord, s.key_b1, s.key_b0);
     CU(cudaGetLastError());
     h->stats.kernel_launches++;
     size_t tmp = s.sort_tmp_bytes;
     CU(cub::DeviceRadixSort::SortPairsDescending(s.d_sort_tmp, tmp, s.d_keys, s.d_keys + s.cap_pairs, s.d_ord,
-                                                 s.d_ord + s.cap_pairs, n, 0, kKeyBits, st));
+                                                 s.d_ord + s.cap_pairs, n, 0, std::min(s.key_bits, kKeyBits), st));
     return BSW_OK;
 }
 
@@ -539,7 +602,8 @@ void scatter_slab(bsw_handle *h, const Slab &s, const PairOut *out, bsw_seqpair 
 // pairs. The lengths are SAMPLED (every 64th record: one cache line in 72 instead of a sweep over the
 // whole array); blob_guess[i] is the pinned-blob capacity to try first for slab i -- prepare_slab
 // reports the exact need if the estimate was short.
-void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts, std::vector<size_t> &blob_guess) {
+void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts, std::vector<size_t> &blob_guess,
+               bool staged) {
     constexpr int64_t G = 1 << 16, S = 64;
     const int64_t ng = (n + G - 1) / G;
     std::vector<int64_t> bases((size_t)ng, 0);
@@ -568,9 +632,36 @@ void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts, 
         const int64_t hi = std::min(n, (c + 1) * G);
         acc += bases[(size_t)c];
         cnt += hi - c * G;
-        if (cnt >= kSlabPairs || acc >= kSlabBases) close(hi);
+        if (cnt >= slab_pairs(staged) || acc >= kSlabBases) close(hi);
     }
     if (cuts.back() != n) close(n);
+}
+
+// Waits for a busy slab, books its kernel time, answers its trivial pairs and hands its result records
+// over as a scatter job (the slab is free afterwards: only h_out is still read, and nothing writes it
+// before the job ran).
+int claim_slab(bsw_handle *h, Slab &s, bsw_seqpair *pairs, double *kernel_ms_acc, ScatterJobs &jobs) {
+    if (!s.busy) return BSW_OK;
+    {
+        auto tw = Clock::now();
+        CU(cudaEventSynchronize(s.ev_done));
+        h->stats.host_wait_ms += ms_since(tw);
+    }
+    if (s.n_dev) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+        *kernel_ms_acc += ms;
+    }
+    bsw_seqpair *pp = pairs + s.lo;
+    ScatterJob j;
+    j.out = s.h_out; j.dst = pp; j.n = s.n_dev ? s.n : 0;
+    jobs.add(j);
+    for (uint32_t k : s.trivial) {   // empty target or query: the DP loop never runs (bandedSWA.cpp:181)
+        bsw_seqpair &p = pp[k];
+        p.score = p.h0; p.qle = 0; p.tle = 0; p.gtle = 0; p.gscore = -1; p.max_off = 0;
+    }
+    s.busy = false;
+    return BSW_OK;
 }
 
 int finish_slab(bsw_handle *h, Slab &s, bsw_seqpair *pairs, double *kernel_ms_acc) {
@@ -726,7 +817,7 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
     std::vector<size_t> guess;
     {
         auto t0 = Clock::now();
-        cut_slabs(pairs, n, cuts, guess);
+        cut_slabs(pairs, n, cuts, guess, false);
         st.host_cut_ms = ms_since(t0);
     }
     const int nslabs = (int)cuts.size() - 1;
@@ -738,10 +829,19 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
         Device &dev = h->devs[(size_t)d];
         Slab &s = dev.ring[r];
         CU(cudaSetDevice(dev.id));
-        rc = finish_slab(h, s, pairs, &kms[(size_t)d]);  // ring slot still owns an older slab
+        // results that are ready go into the caller's array while this slab is packed: the ring slot's
+        // own older slab (wait for it if need be) and any other slab of this GPU that has finished
+        ScatterJobs jobs;
+        rc = claim_slab(h, s, pairs, &kms[(size_t)d], jobs);
+        if (rc) break;
+        for (int r2 = 0; r2 < kRing && rc == BSW_OK; ++r2) {
+            Slab &o = dev.ring[r2];
+            if (&o != &s && o.busy && cudaEventQuery(o.ev_done) == cudaSuccess)
+                rc = claim_slab(h, o, pairs, &kms[(size_t)d], jobs);
+        }
         if (rc) break;
         rc = prepare_slab_fit(h, s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]),
-                              guess[(size_t)sidx]);
+                              guess[(size_t)sidx], jobs);
         if (rc) break;
         if (s.n_dev) {
             if ((rc = upload_slab(h, s))) break;
@@ -837,7 +937,7 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
     const int ng = (int)h->devs.size();
     std::vector<int64_t> cuts;
     std::vector<size_t> guess;
-    cut_slabs(pairs, n, cuts, guess);
+    cut_slabs(pairs, n, cuts, guess, true);
     const int nslabs = (int)cuts.size() - 1;
     for (int sidx = 0; sidx < nslabs; ++sidx) {
         Device &dev = h->devs[(size_t)(sidx % ng)];

@@ -988,24 +988,27 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
 // Length binning on the device: sort key of every pair of a slab (descending order = launch order) and
 // the identity permutation; cub's radix sort then yields ord[]. Pairs with an empty sequence (answered
 // on the host) get key 0 and sort behind everything that is launched.
-//   key = (bin << 5 | wide << 4 | (len2 - 1) % 16) << 32 | len1 << 16 | h0,  bin = (len2 - 1) / 16
+//   key = (bin << 5 | wide << 4 | (len2 - 1) % 16) << (b1 + b0) | len1 << b0 | h0,  bin = (len2 - 1) / 16
 // len1 orders the pairs of a warp by their number of rows, h0 by the width of their first rows (the
 // zero frontier of row i sits about h0 + i columns right of the diagonal): threads of a warp then run
 // the same number of inner-loop trips (measured on config 3: 86 % of the lane slots busy, against 81 %
 // without h0).
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline uint64_t sort_key(uint32_t len2, uint32_t len1, uint32_t h0, uint32_t wide) {
+// The fields are packed as tightly as the slab's largest len1 / h0 allow (b1, b0 bits, chosen by the
+// host from its pass), so the radix sort runs over as few 8-bit digits as possible.
+__host__ __device__ inline uint64_t sort_key(uint32_t len2, uint32_t len1, uint32_t h0, uint32_t wide, int b1, int b0) {
     if (len2 == 0 || len1 == 0) return 0ull;
     const uint32_t v = len2 - 1;
-    return ((uint64_t)(((v >> 4) << 5) | (wide << 4) | (v & 15u)) << 32) | ((uint64_t)len1 << 16) | (h0 & 0xFFFFu);
+    return ((uint64_t)(((v >> 4) << 5) | (wide << 4) | (v & 15u)) << (b1 + b0)) | ((uint64_t)len1 << b0) | h0;
 }
+__host__ __device__ inline int bits_for(uint32_t v) { int b = 1; while ((v >> b) != 0u) ++b; return b; }
 #ifndef BSW_HOST_EMUL
 __global__ void bsw_key_kernel(const PairMeta *__restrict__ meta, int n, uint64_t *__restrict__ keys,
-                               uint32_t *__restrict__ idx) {
+                               uint32_t *__restrict__ idx, int b1, int b0) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const PairMeta m = meta[k];
-    keys[k] = sort_key(m.len2, m.len1, (uint32_t)m.h0, m.flags & 1u);
+    keys[k] = sort_key(m.len2, m.len1, (uint32_t)m.h0, m.flags & 1u, b1, b0);
     idx[k] = (uint32_t)k;
 }
 #endif

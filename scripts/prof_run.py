@@ -27,9 +27,19 @@ b = pairio.generate(cfg, n)
 g.stage(b.pairs, b.ref, b.qer, 100)
 cells = g.count_staged() if not os.environ.get("BSW_NOCOUNT") else 0
 best = 1e9
+rng = os.environ.get("BSW_PROFILE_RANGE")
+if rng:
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    g.run_staged()
+    rt.cudaDeviceSynchronize()
+    rt.cudaProfilerStart()
 for _ in range(reps):
     ms = g.run_staged()
     best = min(best, ms)
+if rng:
+    rt.cudaDeviceSynchronize()
+    rt.cudaProfilerStop()
 print(f"[{tag}] cfg {cfg} n {n}: best kernel {best:.3f} ms, {cells / best / 1e6:.1f} GCUPS, launches {g.stats()['kernel_launches']}", flush=True)
 if os.environ.get("BSW_E2E"):
     w = b.copy()

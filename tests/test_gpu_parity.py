@@ -212,6 +212,27 @@ def test_full_size_properties_config3_sample(gpu):
     assert gpu.stats()["pairs"] == n
 
 
+def test_bsw_main_driver_prints_reference_style_scores(tmp_path):
+    """The C++ driver (reference CLI, pair-file loader, ROI timer, score writer; main_banded.cpp) on top of
+    the C ABI: its "[i] score=" lines are what scripts/regression_small.sh:89-96 diffs against the golden
+    file, its "Overall SW cycles" line is what the script greps as kernel time."""
+    import os
+    import re
+    import subprocess
+    from conftest import ROOT
+    b = pairio.generate(1, 20000, seed=5)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    path = str(tmp_path / "pairs.txt")
+    pairio.write_text(path, b)
+    exe = os.path.join(ROOT, "genarchbench_b200", "bin", "bsw_main")
+    r = subprocess.run([exe, "-pairs", path, "-t", "4", "-b", "512"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    scores = [int(m.group(2)) for m in re.finditer(r"^\[(\d+)\] score=(-?\d+)$", r.stderr, re.M)]
+    assert scores == a.pairs["score"].tolist()
+    assert re.search(r"Overall SW cycles = \d+, [0-9.]+ s", r.stdout) and "Total Pairs processed: 20000" in r.stdout
+
+
 def test_dpx_peak_is_measurable():
     v = bsw.dpx_peak(0)
     assert 5e3 < v < 1e5                                        # giga thread-instructions / s
