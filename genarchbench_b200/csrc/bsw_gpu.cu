@@ -68,6 +68,7 @@ struct Launch {
     int n_wide;
     int row_el, qs_words;   // per pair: uint4 row elements, u32 selector words
     int duo_el;             // per duo thread: row elements of two columns
+    int win_nk;             // > 0: windowed rows of win_nk elements (long query, narrow band)
     size_t smem;     // 0 => long kernel
     int64_t work;    // sum len1*len2, for ordering
 };
@@ -120,6 +121,7 @@ struct Device {
     bool attr_set[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_long[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_duo[8] = {false, false, false, false, false, false, false, false};
+    bool attr_set_win[8] = {false, false, false, false, false, false, false, false};
 };
 
 }  // namespace
@@ -226,6 +228,11 @@ inline size_t smem_need(int row_el, int qs_words) {
 // one-pair-per-thread kernel. It is bit-exact and issues fewer instructions per cell, but each thread
 // then owns two pairs' rows, the shared memory holds half as many warps, and on B200 it measured
 // 41.8 ms against 22.2 ms per 10 M config-3 pairs -- kept for A/B runs, not the default.
+// BSW_WINDOW=0 sends every long pair to the warp-per-pair kernel (A/B against the windowed rows)
+inline bool use_window() {
+    static const bool v = !(getenv("BSW_WINDOW") && getenv("BSW_WINDOW")[0] == '0');
+    return v;
+}
 inline bool use_duo() {
     static const bool v = getenv("BSW_DUO") && getenv("BSW_DUO")[0] == '1';
     return v;
@@ -422,7 +429,14 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             L.qs_words = sel_words(q_hi);
             L.duo_el = duo_elems(q_hi);
             L.smem = use_duo() ? (size_t)duo_thread_bytes(q_hi) * kDuoThreads : smem_need(L.row_el, L.qs_words);
-            if (L.smem > kMaxSmem) L.smem = 0;  // long kernel
+            L.win_nk = 0;
+            if (L.smem > kMaxSmem) {
+                // whole rows do not fit: windowed rows if the band is narrow enough, else one warp per pair
+                const int nk = window_elems(h->K.w);
+                const size_t ws = (size_t)20 * nk * kBlockPairs;
+                if (ws <= kMaxSmem && use_window()) { L.smem = ws; L.win_nk = nk; }
+                else L.smem = 0;
+            }
             s.launches.push_back(L);
             p += nw + nn;
         }
@@ -466,16 +480,18 @@ int ensure_aux(bsw_handle *h, Device &dev) {
 // The kernel instantiations, indexed [fastm][sym][count].
 typedef void (*ShortFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
 typedef void (*DuoFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int);
+typedef void (*WinFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int);
 typedef void (*LongFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
 template <int I> struct KernelTable {
-    static void fill(ShortFn *sf, LongFn *lf, DuoFn *df) {
+    static void fill(ShortFn *sf, LongFn *lf, DuoFn *df, WinFn *wf) {
+        wf[I] = bsw_win_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
         sf[I] = bsw_short_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
         lf[I] = bsw_long_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
         df[I] = bsw_duo_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
-        KernelTable<I - 1>::fill(sf, lf, df);
+        KernelTable<I - 1>::fill(sf, lf, df, wf);
     }
 };
-template <> struct KernelTable<-1> { static void fill(ShortFn *, LongFn *, DuoFn *) {} };
+template <> struct KernelTable<-1> { static void fill(ShortFn *, LongFn *, DuoFn *, WinFn *) {} };
 inline int kernel_index(bool fastm, bool sym, bool count) {
     return (fastm ? 4 : 0) | (sym ? 2 : 0) | (count ? 1 : 0);
 }
@@ -487,8 +503,9 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
     static ShortFn short_fn[8];
     static LongFn long_fn[8];
     static DuoFn duo_fn[8];
+    static WinFn win_fn[8];
     static bool filled = false;
-    if (!filled) { KernelTable<7>::fill(short_fn, long_fn, duo_fn); filled = true; }
+    if (!filled) { KernelTable<7>::fill(short_fn, long_fn, duo_fn, win_fn); filled = true; }
     int rc = ensure_aux(h, dev);
     if (rc) return rc;
     CU(cudaEventRecord(dev.fork_ev, main));
@@ -499,7 +516,15 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
         for (const Launch &L : s.launches) {
             const int grid = (launch_threads(L.n_wide, L.n - L.n_wide) + kBlockPairs - 1) / kBlockPairs;
             const int ki = kernel_index(s.fastm, h->sym, count);
-            if (L.smem && use_duo()) {
+            if (L.win_nk) {
+                if (!dev.attr_set_win[ki]) {
+                    CU(cudaFuncSetAttribute(win_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                    dev.attr_set_win[ki] = true;
+                }
+                cudaStream_t st = dev.aux[rr++ % kAux];
+                win_fn[ki]<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
+                                                              s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.win_nk);
+            } else if (L.smem && use_duo()) {
                 if (!dev.attr_set_duo[ki]) {
                     CU(cudaFuncSetAttribute(duo_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
                     dev.attr_set_duo[ki] = true;
@@ -534,7 +559,7 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
             }
             CU(cudaGetLastError());
             h->stats.kernel_launches++;
-            if (L.smem) h->stats.pairs_short += L.n; else h->stats.pairs_long += L.n;
+            if (L.smem && !L.win_nk) h->stats.pairs_short += L.n; else h->stats.pairs_long += L.n;
         }
     }
     for (int j = 0; j < kAux; ++j) {

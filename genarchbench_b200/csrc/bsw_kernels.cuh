@@ -118,16 +118,22 @@ __device__ __forceinline__ uint32_t pack2(int v) {
 //            element k of this thread lives at he4[k * stride]                      (LDS/STS.128)
 //   qs[k]  : u32 = the PRMT selector seeds of query columns 4k .. 4k+3 (16 bits per group)
 //   tb     : the pair's PACKED target in the slab blob (global memory, read 8 rows at a time)
+//   kmask  : -1 for whole rows. A WINDOWED row (long query, narrow band: extend_pair<.., WIN>) keeps only
+//            kmask + 1 elements -- element k lives in slot k & kmask -- because the live entries of a row
+//            all lie within the band around the diagonal; see extend_pair.
+//   qb     : the pair's packed query (windowed rows expand selector seeds as columns enter the window)
 // ---------------------------------------------------------------------------------------------
 struct Rows {
     uint4 *he4;
     uint32_t *qs;
     const uint32_t *tb;
     int stride;  // threads sharing the arrays (blockDim for shared memory, grid-wide for global)
-    __device__ __forceinline__ uint4 &HE4(int k) const { return he4[(size_t)k * stride]; }
+    int kmask;
+    const uint32_t *qb;
+    __device__ __forceinline__ uint4 &HE4(int k) const { return he4[(size_t)(k & kmask) * stride]; }
     // group g = columns (2g, 2g+1): the .xy or .zw half of element g >> 1
     __device__ __forceinline__ uint2 &HE(int g) const {
-        return reinterpret_cast<uint2 *>(he4 + (size_t)(g >> 1) * stride)[g & 1];
+        return reinterpret_cast<uint2 *>(he4 + (size_t)((g >> 1) & kmask) * stride)[g & 1];
     }
     // 16-bit views of the rows. They go through the SAME 32-bit words the packed loop reads and
     // writes (no differently-typed aliases the compiler could reorder around the packed accesses).
@@ -160,7 +166,7 @@ struct Rows {
 #endif
 #endif
     }
-    __device__ __forceinline__ uint32_t &QS2(int k) const { return qs[(size_t)k * stride]; }
+    __device__ __forceinline__ uint32_t &QS2(int k) const { return qs[(size_t)(k & kmask) * stride]; }
     __device__ __forceinline__ uint32_t QS(int g) const {   // 16-bit seed of one group
         const uint32_t w = QS2(g >> 1);
         return (g & 1) ? (w >> 16) : (w & 0xFFFFu);
@@ -239,12 +245,31 @@ __device__ __forceinline__ void score_lut(const KParams &P, uint32_t &lo, uint32
     }
 }
 
+// selector seeds of query columns 4k .. 4k+3 (element k) from a packed query: a base b becomes the
+// byte b * 0x11 (value nibble and sign nibble of one PRMT lane)
+template <bool WIDE>
+__device__ __forceinline__ uint32_t sel_word(const uint32_t *qb, int k) {
+    uint32_t v;
+    if (!WIDE) {
+        v = (qb[k >> 2] >> (8 * (k & 3))) & 0xFFu;      // 4 bases, 2 bits each
+        v = (v | (v << 12)) & 0x000F000Fu;
+        v = (v | (v << 6)) & 0x03030303u;
+    } else {
+        v = (qb[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;   // 4 bases, 4 bits each
+        v = (v | (v << 8)) & 0x00FF00FFu;
+        v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    }
+    return v * 0x11u;
+}
+
 // Expands the query of this thread's packed blob (4-byte words: query then target, each padded to 4
 // bytes) into qs[] and points R.tb at the target. Narrow blobs hold 2 bits per base, wide blobs 4.
 template <bool WIDE>
 __device__ inline void unpack_pair(const uint32_t *blob, int qlen, Rows &R) {
     R.tb = blob + (seq_bytes((uint32_t)qlen, WIDE) >> 2);
-    const int nsel = (((qlen + 1) >> 1) + 1) >> 1;   // selector words: two groups each (== sel_words)
+    R.qb = blob;
+    int nsel = (((qlen + 1) >> 1) + 1) >> 1;   // selector words: two groups each (== sel_words)
+    if (R.kmask >= 0 && nsel > R.kmask + 1) nsel = R.kmask + 1;   // windowed rows: the first window only
     if (!WIDE) {
         // 16 bases per word -> 8 groups -> 4 selector words; a base b becomes the byte b * 0x11
         for (int w = 0, k = 0; k < nsel; ++w) {
@@ -296,6 +321,12 @@ __device__ __forceinline__ int pair_band(const KParams &P, int qlen) {
 // number of he4 elements (4 columns each) a pair with qlen query bases needs: columns 0 .. qlen
 // (one spare so that the hi lane of the last group is always initialised), rounded up
 __host__ __device__ inline int row_elems(int qlen) { return (qlen + 4) >> 2; }
+// elements of a windowed row (extend_pair<.., WIN>) for band width w: a power of two, 4 * nk >= 2 w + 16
+__host__ __device__ inline int window_elems(int w) {
+    int nk = 8;
+    while (4 * nk < 2 * w + 16) nk <<= 1;
+    return nk;
+}
 // number of qs words (selector seeds of two groups = 4 columns each) for qlen query bases
 __host__ __device__ inline int sel_words(int qlen) { return (((qlen + 1) >> 1) + 1) >> 1; }
 
@@ -309,7 +340,15 @@ __host__ __device__ inline int sel_words(int qlen) { return (((qlen + 1) >> 1) +
 //           visit (bandedSWA.cpp:191-216; the commented SW_cells++ at :215) -- the unit of work of
 //           the GCUPS metric. Used once per input outside any timed region.
 //   WIDE  : the pair may hold ambiguous bases (4-bit blob, LOP3 selector; see score_lut)
-template <bool FASTM, bool SYM, bool COUNT, bool WIDE>
+//   WIN   : windowed rows for long queries under a narrow band. Row i only touches entries
+//           [beg, end] with i - band <= beg and end <= i + band + 1, everything left of beg is dead,
+//           and an entry right of every `end` seen so far still holds its row "-1" value, which has a
+//           closed form. So R keeps kmask + 1 elements (4 * (kmask + 1) >= 2 * band + 16 columns, slot =
+//           element & kmask): before a row, the elements that `end` newly reaches are (re)initialised
+//           -- row "-1" values, zero E, selector seeds from the packed query -- over slots whose old
+//           columns have fallen out of the band. A 1000-base query under w = 100 then needs 1.3 KB of
+//           shared memory instead of 5 KB and stays on the thread-per-pair kernel.
+template <bool FASTM, bool SYM, bool COUNT, bool WIDE, bool WIN = false>
 __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int h0, const KParams &P) {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
@@ -319,28 +358,23 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
     uint32_t LUT_LO, LUT_HI;
     score_lut<WIDE>(P, LUT_LO, LUT_HI);
 
-    // row "-1" (bandedSWA.cpp:159-161) and zeroed E, over every element the row loop may touch
-    {
-        const int nel = row_elems(qlen);
-        int hv = h0;
-        for (int k = 0; k < nel; ++k) {
-            uint32_t w[2];
+    // row "-1" (bandedSWA.cpp:159-161) and zeroed E of element k (columns 4k .. 4k+3):
+    // Hs[0] = h0, Hs[j] = max(h0 - oe_ins - (j-1) e_ins, 0) for 1 <= j <= qlen, 0 beyond (calloc'ed tail)
+    auto init_elem = [&](int k) {
+        uint32_t hv[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int g = 2 * k + u;
-                int a = hv;                                   // Hs[2g]
-                if (g == 0) hv = h0 > oe_ins ? h0 - oe_ins : 0;
-                else hv = max(hv - P.e_ins, 0);
-                int b = hv;                                   // Hs[2g+1]
-                hv = max(hv - P.e_ins, 0);
-                if (2 * g > qlen) a = 0;                      // the reference's calloc'ed tail
-                if (2 * g + 1 > qlen) b = 0;
-                w[u] = (uint32_t)a | ((uint32_t)b << 16);
-            }
-            uint4 v; v.x = w[0]; v.y = 0u; v.z = w[1]; v.w = 0u;
-            R.HE4(k) = v;
+        for (int u = 0; u < 4; ++u) {
+            const int j = 4 * k + u;
+            int v = j == 0 ? h0 : max(h0 - oe_ins - (j - 1) * P.e_ins, 0);
+            if (j > qlen) v = 0;
+            hv[u] = (uint32_t)v;
         }
-    }
+        uint4 w; w.x = hv[0] | (hv[1] << 16); w.y = 0u; w.z = hv[2] | (hv[3] << 16); w.w = 0u;
+        R.HE4(k) = w;
+    };
+    int kinit = row_elems(qlen);            // elements [0, kinit) hold valid entries
+    if (WIN) kinit = min(kinit, R.kmask + 1);
+    for (int k = 0; k < kinit; ++k) init_elem(k);
 
     const int band = pair_band(P, qlen);
     const int budget = min(qlen + band, tlen);
@@ -362,6 +396,15 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             cells += (uint32_t)(end - xbeg);
         }
 
+        if (WIN) {
+            // elements that `end` reaches for the first time enter the window
+            const int kneed = min(end, qlen) >> 2;
+            while (kinit <= kneed) {
+                init_elem(kinit);
+                R.QS2(kinit) = sel_word<WIDE>(R.qb, kinit);
+                ++kinit;
+            }
+        }
         if ((i & 7) == 0) tword = R.template TG<WIDE>(i >> 3);
         // the row's target seed in both halves: nibbles c, c | 8 with c = 4 - code (narrow) / code (wide)
         const uint32_t tsel = (tword & 7u) * 0x11111111u + 0x80808080u;
@@ -564,7 +607,8 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             if (jstar < 0) {
                 int gz = g1 - 1;
                 uint32_t wz = 0;
-                for (; gz >= 0; --gz) {
+                const int glow = WIN ? (beg >> 1) : 0;   // everything left of beg is zero (and, windowed, gone)
+                for (; gz >= glow; --gz) {
                     const uint2 z = R.HE(gz);
                     wz = z.x | z.y;
                     if (wz) break;
@@ -628,6 +672,7 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     R.stride = NT;
     R.he4 = reinterpret_cast<uint4 *>(smem) + tid;
     R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)16 * row_el * NT) + tid;
+    R.kmask = -1; R.qb = nullptr;
     (void)qs_words;
 
     const uint32_t *src = blob + m.off;
@@ -639,6 +684,45 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     } else {
         unpack_pair<false>(src, m.len2, R);
         r = extend_pair<FASTM, SYM, COUNT, false>(R, m.len2, m.len1, m.h0, P);
+    }
+    store_result(out, m.id, r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Long queries under a narrow band: the same thread-per-pair code over WINDOWED rows (extend_pair<.., WIN>).
+// Launch as bsw_short_kernel, dynamic smem = 20 * nk * kBlockPairs with nk = window elements (a power of
+// two, 4 * nk >= 2 * w + 16).
+// ---------------------------------------------------------------------------------------------
+template <bool FASTM, bool SYM, bool COUNT>
+__global__ void __launch_bounds__(kBlockPairs)
+bsw_win_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
+               const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
+               KParams P, int nk) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NT = kBlockPairs;
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * NT + tid;
+    const int nwr = (n_wide + 31) & ~31;
+    const bool wide = t < nwr;                       // warp-uniform
+    const int k = wide ? t : t - nwr + n_wide;
+    if (wide ? t >= n_wide : k >= n_wide + n_narrow) return;
+    const PairMeta m = meta[ord[k]];
+
+    Rows R;
+    R.stride = NT;
+    R.he4 = reinterpret_cast<uint4 *>(smem) + tid;
+    R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)16 * nk * NT) + tid;
+    R.kmask = nk - 1; R.qb = nullptr;
+
+    const uint32_t *src = blob + m.off;
+    PairResult r;
+    if (wide) {
+        src = blob + src[0];
+        unpack_pair<true>(src, m.len2, R);
+        r = extend_pair<FASTM, SYM, COUNT, true, true>(R, m.len2, m.len1, m.h0, P);
+    } else {
+        unpack_pair<false>(src, m.len2, R);
+        r = extend_pair<FASTM, SYM, COUNT, false, true>(R, m.len2, m.len1, m.h0, P);
     }
     store_result(out, m.id, r);
 }
@@ -976,7 +1060,7 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     R.stride = 1;
     R.he4 = reinterpret_cast<uint4 *>(smem + (size_t)warp * pair_bytes);
     R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)warp * pair_bytes + (size_t)16 * row_el);
-    R.tb = nullptr;
+    R.tb = nullptr; R.kmask = -1; R.qb = nullptr;
     const uint32_t *src = blob + m.off;
     PairResult r;
     if (p < n_wide) r = warp_extend_pair<FASTM, SYM, COUNT, true>(R, blob + src[0], m.len2, m.len1, m.h0, P);

@@ -96,13 +96,61 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
                 pack4bit(qer + sp.idq, sp.len2, b);
                 pack4bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, true));
             }
-            Rows R{he.data(), qs.data(), nullptr, 1};
+            Rows R{he.data(), qs.data(), nullptr, 1, -1, nullptr};
             if (wide) unpack_pair<true>(blob.data(), sp.len2, R);
             else unpack_pair<false>(blob.data(), sp.len2, R);
             PairResult r;
             const bool m1 = (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767 && !getenv("BSW_EMUL_SLOWM");
 #define EP(F, S) (wide ? extend_pair<F, S, true, true>(R, sp.len2, sp.len1, sp.h0, K) \
                   : extend_pair<F, S, true, false>(R, sp.len2, sp.len1, sp.h0, K))
+            if (m1) r = sym ? EP(true, true) : EP(true, false);
+            else r = sym ? EP(false, true) : EP(false, false);
+#undef EP
+            sp.score = r.score; sp.qle = r.qle; sp.tle = r.tle; sp.gtle = r.gtle;
+            sp.gscore = r.gscore; sp.max_off = r.max_off;
+            sp.seqid = (int32_t)r.cells;   // test hook: cell count of the COUNT variant
+        }
+    }
+    return 0;
+}
+
+// Windowed rows (extend_pair<.., WIN>): every pair runs with the window a band of w needs.
+extern "C" int bsw_emul_batch_win(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
+                              const uint8_t *qer, int64_t n, int32_t w) {
+    KParams K{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w,
+              max_score_of(p->match, p->mismatch, p->ambig), 65536u, (uint32_t)(p->match + 1), 1u};
+    const bool sym = p->o_del == p->o_ins && p->e_del == p->e_ins;
+#pragma omp parallel
+    {
+        std::vector<uint4> he;
+        std::vector<uint32_t> qs, blob;
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t k = 0; k < n; ++k) {
+            bsw_seqpair &sp = pairs[k];
+            if (sp.len1 == 0 || sp.len2 == 0) {
+                sp.score = sp.h0; sp.qle = sp.tle = sp.gtle = 0; sp.gscore = -1; sp.max_off = 0;
+                continue;
+            }
+            he.assign((size_t)row_elems(sp.len2), uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+            qs.assign((size_t)sel_words(sp.len2), 0xDEADBEEFu);
+            blob.assign((size_t)(seq_bytes(sp.len2, true) + seq_bytes(sp.len1, true)) / 4 + 4, 0);
+            uint8_t *b = reinterpret_cast<uint8_t *>(blob.data());
+            bool wide = pack2bit(qer + sp.idq, sp.len2, b);
+            wide |= pack2bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, false));
+            if (wide) {
+                pack4bit(qer + sp.idq, sp.len2, b);
+                pack4bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, true));
+            }
+            const int nk = window_elems(w);
+            he.assign((size_t)nk, uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
+            qs.assign((size_t)nk, 0xDEADBEEFu);
+            Rows R{he.data(), qs.data(), nullptr, 1, nk - 1, nullptr};
+            if (wide) unpack_pair<true>(blob.data(), sp.len2, R);
+            else unpack_pair<false>(blob.data(), sp.len2, R);
+            PairResult r;
+            const bool m1 = (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767 && !getenv("BSW_EMUL_SLOWM");
+#define EP(F, S) (wide ? extend_pair<F, S, true, true, true>(R, sp.len2, sp.len1, sp.h0, K) \
+                  : extend_pair<F, S, true, false, true>(R, sp.len2, sp.len1, sp.h0, K))
             if (m1) r = sym ? EP(true, true) : EP(true, false);
             else r = sym ? EP(false, true) : EP(false, false);
 #undef EP

@@ -25,9 +25,10 @@ def emul():
     L = C.CDLL(so)
     L.bsw_emul_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
     L.bsw_emul_batch_duo.argtypes = L.bsw_emul_batch.argtypes
+    L.bsw_emul_batch_win.argtypes = L.bsw_emul_batch.argtypes
 
-    def run(b, w=100, params=None, duo=False):
-        fn = L.bsw_emul_batch_duo if duo else L.bsw_emul_batch
+    def run(b, w=100, params=None, duo=False, win=False):
+        fn = L.bsw_emul_batch_duo if duo else (L.bsw_emul_batch_win if win else L.bsw_emul_batch)
         fn(oracle._params_array(params), b.pairs.ctypes.data, b.ref.ctypes.data, b.qer.ctypes.data, len(b), w)
         return b.outputs()
     return run
@@ -37,6 +38,26 @@ def emul():
 def test_device_code_matches_golden(emul, name):
     b, w, params, want = load_golden(name)
     assert_same_outputs(emul(b, w, params), want, b, f"emulated kernel vs golden[{name}]")
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_windowed_rows_match_golden(emul, name):
+    """extend_pair<.., WIN>: rows kept in a sliding window of 2w + 16 columns."""
+    b, w, params, want = load_golden(name)
+    assert_same_outputs(emul(b, w, params, win=True), want, b, f"emulated windowed kernel vs golden[{name}]")
+
+
+@pytest.mark.parametrize("w", [1, 2, 5, 17, 40])
+def test_windowed_rows_match_oracle_on_long_queries(emul, w):
+    """Queries several windows long (up to 600 bases against windows of 32..128 columns), ambiguous bases,
+    unrelated pairs; the COUNT variant's cell count as well."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 600, 0, 120, 0.3, 0.15
+    b = pairio.generate(c, 3000, seed=700 + w)
+    a = b.copy()
+    cells = oracle.oracle_batch(a, w=w)
+    assert_same_outputs(emul(b, w, win=True), a.outputs(), b, f"emulated windowed kernel vs oracle, w={w}")
+    assert int(b.pairs["seqid"].astype(np.int64).sum()) == cells
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
