@@ -348,7 +348,10 @@ __host__ __device__ inline int sel_words(int qlen) { return (((qlen + 1) >> 1) +
 //           -- row "-1" values, zero E, selector seeds from the packed query -- over slots whose old
 //           columns have fallen out of the band. A 1000-base query under w = 100 then needs 1.3 KB of
 //           shared memory instead of 5 KB and stays on the thread-per-pair kernel.
-template <bool FASTM, bool SYM, bool COUNT, bool WIDE, bool WIN = false>
+//   NB    : groups per trip of the inner loop, 4 or 8. Eight help the windowed launches, which run at one
+//           warp per scheduler and have nothing else to hide latency with (config 4: 81 -> 73 ms), and
+//           cost the whole-row launches 8 % (more registers, a longer single-group tail).
+template <bool FASTM, bool SYM, bool COUNT, bool WIDE, bool WIN = false, int NB = 4>
 __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int h0, const KParams &P) {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
@@ -471,54 +474,110 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             return st;
         };
         int g = g0;
-        if (g + 3 <= g1) {
-            uint4 a = R.HE4(g >> 1), b = R.HE4((g >> 1) + 1);
-            uint32_t q01 = R.QS2(g >> 1), q23 = R.QS2((g >> 1) + 1);
-            bool more;
-            do {
-                const int k = g >> 1;
-                more = g + 7 <= g1;
-                uint4 na = a, nb = b;
-                uint32_t nq01 = q01, nq23 = q23;
-                if (BSW_PREFETCH && more) {
-                    na = R.HE4(k + 2); nb = R.HE4(k + 3);
-                    nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
-                }
-                uint32_t s0, s1, s2, s3;
-                if (WIDE || BSW_SEL_LOP3) {
-                    s0 = sel_combine(q01, tsel, 0x44444444u); s1 = __umulhi(s0, K16);
-                    s2 = sel_combine(q23, tsel, 0x44444444u); s3 = __umulhi(s2, K16);
-                } else {
-                    // tsel carries the row's seed in both halves: the upper half of the sum is group 1's selector
-                    s0 = q01 * K1 + tsel; s1 = __umulhi(s0, K16);
-                    s2 = q23 * K1 + tsel; s3 = __umulhi(s2, K16);
-                }
-                uint32_t M0, M1, M2, M3, T0, T1, T2, T3, E0, E1, E2, E3;
-                front(a.x, a.y, s0, M0, T0, E0);
-                front(a.z, a.w, s1, M1, T1, E1);
-                front(b.x, b.y, s2, M2, T2, E2);
-                front(b.z, b.w, s3, M3, T3, E3);
-                uint4 oa, ob;
-                oa.x = back(a.y, M0, T0); const uint32_t h0v = h;
-                oa.z = back(a.w, M1, T1); const uint32_t h1v = h;
-                ob.x = back(b.y, M2, T2); const uint32_t h2v = h;
-                ob.z = back(b.w, M3, T3);
-                oa.y = E0; oa.w = E1; ob.y = E2; ob.w = E3;
-                R.HE4(k) = oa;
-                R.HE4(k + 1) = ob;
-                Hst = ob.z; En = E3;
-                bool phi, plo;
-                rm = __vibmax_s16x2(h0v, rm, &phi, &plo); mov_if<0>(ilo, plo, g, K1); mov_if<0>(ihi, phi, g, K1);
-                rm = __vibmax_s16x2(h1v, rm, &phi, &plo); mov_if<1>(ilo, plo, g, K1); mov_if<1>(ihi, phi, g, K1);
-                rm = __vibmax_s16x2(h2v, rm, &phi, &plo); mov_if<2>(ilo, plo, g, K1); mov_if<2>(ihi, phi, g, K1);
-                rm = __vibmax_s16x2(h, rm, &phi, &plo);   mov_if<3>(ilo, plo, g, K1); mov_if<3>(ihi, phi, g, K1);
-                if (!BSW_PREFETCH && more) {
-                    na = R.HE4(k + 2); nb = R.HE4(k + 3);
-                    nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
-                }
-                a = na; b = nb; q01 = nq01; q23 = nq23;
-                g += 4;
-            } while (more);
+        if (NB == 4) {
+            if (g + 3 <= g1) {
+                uint4 a = R.HE4(g >> 1), b = R.HE4((g >> 1) + 1);
+                uint32_t q01 = R.QS2(g >> 1), q23 = R.QS2((g >> 1) + 1);
+                bool more;
+                do {
+                    const int k = g >> 1;
+                    more = g + 7 <= g1;
+                    uint4 na = a, nb = b;
+                    uint32_t nq01 = q01, nq23 = q23;
+                    if (BSW_PREFETCH && more) {
+                        na = R.HE4(k + 2); nb = R.HE4(k + 3);
+                        nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
+                    }
+                    uint32_t s0, s1, s2, s3;
+                    if (WIDE || BSW_SEL_LOP3) {
+                        s0 = sel_combine(q01, tsel, 0x44444444u); s1 = __umulhi(s0, K16);
+                        s2 = sel_combine(q23, tsel, 0x44444444u); s3 = __umulhi(s2, K16);
+                    } else {
+                        // tsel carries the row's seed in both halves: the upper half of the sum is group 1's selector
+                        s0 = q01 * K1 + tsel; s1 = __umulhi(s0, K16);
+                        s2 = q23 * K1 + tsel; s3 = __umulhi(s2, K16);
+                    }
+                    uint32_t M0, M1, M2, M3, T0, T1, T2, T3, E0, E1, E2, E3;
+                    front(a.x, a.y, s0, M0, T0, E0);
+                    front(a.z, a.w, s1, M1, T1, E1);
+                    front(b.x, b.y, s2, M2, T2, E2);
+                    front(b.z, b.w, s3, M3, T3, E3);
+                    uint4 oa, ob;
+                    oa.x = back(a.y, M0, T0); const uint32_t h0v = h;
+                    oa.z = back(a.w, M1, T1); const uint32_t h1v = h;
+                    ob.x = back(b.y, M2, T2); const uint32_t h2v = h;
+                    ob.z = back(b.w, M3, T3);
+                    oa.y = E0; oa.w = E1; ob.y = E2; ob.w = E3;
+                    R.HE4(k) = oa;
+                    R.HE4(k + 1) = ob;
+                    Hst = ob.z; En = E3;
+                    bool phi, plo;
+                    rm = __vibmax_s16x2(h0v, rm, &phi, &plo); mov_if<0>(ilo, plo, g, K1); mov_if<0>(ihi, phi, g, K1);
+                    rm = __vibmax_s16x2(h1v, rm, &phi, &plo); mov_if<1>(ilo, plo, g, K1); mov_if<1>(ihi, phi, g, K1);
+                    rm = __vibmax_s16x2(h2v, rm, &phi, &plo); mov_if<2>(ilo, plo, g, K1); mov_if<2>(ihi, phi, g, K1);
+                    rm = __vibmax_s16x2(h, rm, &phi, &plo);   mov_if<3>(ilo, plo, g, K1); mov_if<3>(ihi, phi, g, K1);
+                    if (!BSW_PREFETCH && more) {
+                        na = R.HE4(k + 2); nb = R.HE4(k + 3);
+                        nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
+                    }
+                    a = na; b = nb; q01 = nq01; q23 = nq23;
+                    g += 4;
+                } while (more);
+            }
+        } else {
+            // NB groups (NB / 2 elements) per trip
+            constexpr int NE = NB / 2;
+            if (g + NB - 1 <= g1) {
+                uint4 cur[NE];
+                uint32_t cq[NE];
+    #pragma unroll
+                for (int e = 0; e < NE; ++e) { cur[e] = R.HE4((g >> 1) + e); cq[e] = R.QS2((g >> 1) + e); }
+                bool more;
+                do {
+                    const int k = g >> 1;
+                    more = g + 2 * NB - 1 <= g1;
+                    uint4 nxt[NE];
+                    uint32_t nq[NE];
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) { nxt[e] = cur[e]; nq[e] = cq[e]; }
+                    if (BSW_PREFETCH && more) {
+    #pragma unroll
+                        for (int e = 0; e < NE; ++e) { nxt[e] = R.HE4(k + NE + e); nq[e] = R.QS2(k + NE + e); }
+                    }
+                    uint32_t M[NB], T[NB], E[NB], hv[NB];
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        uint32_t s0, s1;
+                        if (WIDE || BSW_SEL_LOP3) { s0 = sel_combine(cq[e], tsel, 0x44444444u); s1 = __umulhi(s0, K16); }
+                        else { s0 = cq[e] * K1 + tsel; s1 = __umulhi(s0, K16); }   // tsel: the row's seed in both halves
+                        front(cur[e].x, cur[e].y, s0, M[2 * e], T[2 * e], E[2 * e]);
+                        front(cur[e].z, cur[e].w, s1, M[2 * e + 1], T[2 * e + 1], E[2 * e + 1]);
+                    }
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) {
+                        uint4 o;
+                        o.x = back(cur[e].y, M[2 * e], T[2 * e]); hv[2 * e] = h;
+                        o.z = back(cur[e].w, M[2 * e + 1], T[2 * e + 1]); hv[2 * e + 1] = h;
+                        o.y = E[2 * e]; o.w = E[2 * e + 1];
+                        R.HE4(k + e) = o;
+                        if (e == NE - 1) { Hst = o.z; En = o.w; }
+                    }
+    #pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        bool phi, plo;
+                        rm = __vibmax_s16x2(hv[u], rm, &phi, &plo);
+                        if (plo) ilo = g + u;
+                        if (phi) ihi = g + u;
+                    }
+                    if (!BSW_PREFETCH && more) {
+    #pragma unroll
+                        for (int e = 0; e < NE; ++e) { nxt[e] = R.HE4(k + NE + e); nq[e] = R.QS2(k + NE + e); }
+                    }
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) { cur[e] = nxt[e]; cq[e] = nq[e]; }
+                    g += NB;
+                } while (more);
+            }
         }
         for (; g <= g1; ++g) {
             const uint2 he0 = R.HE(g);
@@ -719,10 +778,10 @@ bsw_win_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ o
     if (wide) {
         src = blob + src[0];
         unpack_pair<true>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, true, true>(R, m.len2, m.len1, m.h0, P);
+        r = extend_pair<FASTM, SYM, COUNT, true, true, 8>(R, m.len2, m.len1, m.h0, P);
     } else {
         unpack_pair<false>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, false, true>(R, m.len2, m.len1, m.h0, P);
+        r = extend_pair<FASTM, SYM, COUNT, false, true, 8>(R, m.len2, m.len1, m.h0, P);
     }
     store_result(out, m.id, r);
 }

@@ -149,8 +149,8 @@ extern "C" int bsw_emul_batch_win(const bsw_params *p, bsw_seqpair *pairs, const
             else unpack_pair<false>(blob.data(), sp.len2, R);
             PairResult r;
             const bool m1 = (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767 && !getenv("BSW_EMUL_SLOWM");
-#define EP(F, S) (wide ? extend_pair<F, S, true, true, true>(R, sp.len2, sp.len1, sp.h0, K) \
-                  : extend_pair<F, S, true, false, true>(R, sp.len2, sp.len1, sp.h0, K))
+#define EP(F, S) (wide ? extend_pair<F, S, true, true, true, 8>(R, sp.len2, sp.len1, sp.h0, K) \
+                  : extend_pair<F, S, true, false, true, 8>(R, sp.len2, sp.len1, sp.h0, K))
             if (m1) r = sym ? EP(true, true) : EP(true, false);
             else r = sym ? EP(false, true) : EP(false, false);
 #undef EP
