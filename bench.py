@@ -219,6 +219,7 @@ def main():
     g.stage(batch.pairs, batch.ref, batch.qer, 100)
     cells = g.count_staged()                      # unit of work, outside any timed region
     dpx_peak = bsw.dpx_peak(0, device=local_rank)  # Ginstr/s, measured live on this GPU
+    trip_peak = bsw.dpx_peak(9, device=local_rank)  # G cells/s of the inner-loop arithmetic alone (registers only)
 
     # ---- value: device-resident kernel throughput
     for _ in range(args.warmup):
@@ -272,6 +273,10 @@ def main():
         "achieved": achieved_instr, "peak": dpx_peak, "unit": "Ginstr/s (packed s16x2 thread-instructions)",
         "frac": achieved_instr / dpx_peak, "instr_per_cell": INSTR_PER_CELL,
         "peak_source": "measured live: VIADDMNMX.S16x2.RELU issue rate, all SMs (bsw_gpu_dpx_peak)",
+        # second, tighter ceiling: the kernel's own inner-loop arithmetic (8 cells per trip) run on registers
+        # only at full occupancy -- no shared memory, row bookkeeping or divergence (bsw_gpu_dpx_peak(9))
+        "inner_loop_ceiling_gcups": trip_peak,
+        "frac_of_inner_loop_ceiling": (cells / (dev_ms / args.steps * 1e-3) / 1e9) / trip_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of the DP kernels, one ncu capture of this workload at
         # 10 M pairs (profiles/r1_dram_bytes_per_launch_10Mpairs.csv): 202.1 bytes per pair, scaled to this run
         "traffic": int(DRAM_BYTES_PER_PAIR_NCU * len(batch)), "traffic_unit": "bytes per step (DP kernels)",

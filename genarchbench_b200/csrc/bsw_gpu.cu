@@ -1085,6 +1085,22 @@ int bsw_gpu_dpx_peak(int device, int which, double *ginstr_per_s, double *sm_mhz
         case 6: rc = run_peak<6>(iters, blocks, threads, sink, &ms); break;
         case 7: rc = run_peak<7>(iters, blocks, threads, sink, &ms); break;
         case 8: rc = run_peak<8>(iters, blocks, threads, sink, &ms); break;
+        case 9: {   // one inner-loop trip on registers: result in giga CELLS per second
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            bsw_trip_peak_kernel<<<blocks, threads>>>(sink, 16, 3u, 65536u, 2u, 1u);
+            cudaEventRecord(a);
+            bsw_trip_peak_kernel<<<blocks, threads>>>(sink, iters * 4, 3u, 65536u, 2u, 1u);
+            cudaEventRecord(b);
+            rc = cudaEventSynchronize(b) == cudaSuccess ? 0 : 1;
+            cudaEventElapsedTime(&ms, a, b);
+            cudaEventDestroy(a); cudaEventDestroy(b);
+            cudaFree(sink);
+            if (rc) return BSW_ERR_CUDA;
+            *ginstr_per_s = (double)iters * 4.0 * 8.0 * (double)threads * (double)blocks / (ms * 1e-3) / 1e9;
+            if (sm_mhz_est) *sm_mhz_est = (double)prop.clockRate / 1000.0;
+            return BSW_OK;
+        }
         default: cudaFree(sink); return BSW_ERR_ARG;
     }
     cudaFree(sink);

@@ -1191,6 +1191,56 @@ __global__ void dpx_peak_kernel(uint32_t *sink, int iters, uint32_t seed) {
     if (acc == 0x12345678u) sink[threadIdx.x] = acc;  // keep the chains alive
 }
 
+// WHICH == 9 of bsw_gpu_dpx_peak: the arithmetic of one inner-loop trip of extend_pair (four groups =
+// eight cells: selector, PRMT, M, T, E', the F scan, H, shifted store word, row max + argmax) on
+// registers only -- no shared memory, no row bookkeeping, no divergence. Its rate is the ceiling the
+// thread-per-pair kernel could reach if everything but the recurrence were free.
+__global__ void bsw_trip_peak_kernel(uint32_t *sink, int iters, uint32_t seed, uint32_t k16, uint32_t km, uint32_t k1) {
+    uint32_t hd[4], ev[4], q[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hd[k] = (seed * (k + 3) + threadIdx.x) & 0x00FF00FFu; ev[k] = (seed * (k + 7)) & 0x003F003Fu; }
+    q[0] = 0x11002233u & (seed | 0x33333333u); q[1] = 0x22113300u;
+    const uint32_t LUT_LO = 0xFCFCFCFCu, LUT_HI = 0xFCFCFC01u, NEG_OE = pack2(-7), NEG_E = pack2(-1);
+    uint32_t rm = 0, A = 0, hprev = 0, tsel = 0x94949494u;
+    int ilo = 0, ihi = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t M[4], T[4], E[4], hv[4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const uint32_t s0 = q[e] * k1 + tsel, s1 = __umulhi(s0, k16);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int g = 2 * e + u;
+                const uint32_t sc = prmt_sx(LUT_LO, LUT_HI, u ? s1 : s0);
+                M[g] = __viaddmin_s16x2(hd[g], sc, hd[g] * km);
+                T[g] = __viaddmax_s16x2_relu(M[g], NEG_OE, NEG_OE);
+                E[g] = __viaddmax_s16x2(ev[g], NEG_E, T[g]);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint32_t W1 = __viaddmax_s16x2(A, NEG_E, T[g]);
+            const uint32_t B = W1 * k16 + A;
+            const uint32_t h = __vimax3_s16x2(M[g], ev[g], B);
+            const uint32_t W2 = __viaddmax_s16x2(B, NEG_E, T[g]);
+            A = __umulhi(W2, k16);
+            hd[g] = __umulhi(hprev, k16) + h * k16;   // next "row" reads what this one stored
+            hprev = h;
+            hv[g] = h;
+            ev[g] = E[g];
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            bool phi, plo;
+            rm = __vibmax_s16x2(hv[g], rm, &phi, &plo);
+            if (plo) ilo = it + g;
+            if (phi) ihi = it + g;
+        }
+        tsel += 0x01010101u & (uint32_t)it;
+    }
+    if ((rm ^ A ^ (uint32_t)ilo ^ (uint32_t)ihi) == 0x12345678u) sink[threadIdx.x] = rm;
+}
+
 #endif  // !BSW_HOST_EMUL
 
 }  // namespace bswk

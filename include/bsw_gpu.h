@@ -107,7 +107,10 @@ int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out);
 /* Integer-pipe microbenchmark on device `device`: packed s16x2 DPX instruction throughput in
  * giga thread-instructions per second (warp-instructions * 32), all SMs, `which`:
  *   0 VIADDMNMX.S16x2.RELU, 1 VIMNMX3.S16x2, 2 VIADD.16x2, 3 LOP3, 4 PRMT, 5 IMAD,
- *   6 the bsw inner-loop mix. Used by bench.py for the `dpx_peak` roofline denominator. */
+ *   6 SHF, 7 IMAD.HI, 8 VIADDMNMX + IMAD co-issue; 9 = the arithmetic of one inner-loop trip of the
+ *   thread-per-pair kernel on registers only, reported in giga CELLS per second (the ceiling of that
+ *   kernel if shared memory, row bookkeeping and divergence were free).
+ *   Used by bench.py for the `dpx_peak` roofline denominator. */
 int bsw_gpu_dpx_peak(int device, int which, double *ginstr_per_s, double *sm_mhz_est);
 
 const char *bsw_gpu_strerror(int code);

@@ -42,6 +42,12 @@ if rng:
     rt.cudaProfilerStop()
 print(f"[{tag}] cfg {cfg} n {n}: best kernel {best:.3f} ms, {cells / best / 1e6:.1f} GCUPS, launches {g.stats()['kernel_launches']}", flush=True)
 if os.environ.get("BSW_E2E"):
+    try:
+        roll = {l.split(":")[0]: l.split()[1] for l in open("/proc/self/smaps_rollup") if ":" in l and len(l.split()) > 1}
+        print(f"[{tag}] AnonHugePages {roll.get('AnonHugePages')} kB of Rss {roll.get('Rss')} kB; THP:",
+              open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip(), flush=True)
+    except OSError as e:
+        print("smaps:", e)
     w = b.copy()
     g.batch(w.pairs, w.ref, w.qer, 100)
     for _ in range(3):
