@@ -56,7 +56,8 @@ struct Rows2 {
 };
 
 // number of he4 / qs elements (2 columns each) for columns 0 .. qlen
-__host__ __device__ inline int duo_elems(int qlen) { return (qlen + 2) >> 1; }
+// (a whole number of 4-column blocks: the leading trim looks at a block at a time)
+__host__ __device__ inline int duo_elems(int qlen) { return ((qlen + 4) >> 2) << 1; }
 __host__ __device__ inline uint32_t duo_thread_bytes(int qlen) { return 20u * (uint32_t)duo_elems(qlen); }
 
 // One pair of a duo thread.

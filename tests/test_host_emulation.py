@@ -86,3 +86,22 @@ def test_device_code_matches_oracle_on_small_bands(emul, w):
     a = b.copy()
     oracle.oracle_batch(a, w=w)
     assert_same_outputs(emul(b, w), a.outputs(), b, f"emulated kernel vs oracle, w={w}")
+
+
+def test_emulated_device_code_is_clean_under_asan(tmp_path):
+    """Out-of-bounds check of the per-pair device code (the GPU pool has no compute-sanitizer): an
+    AddressSanitizer build of the emulation library, rows allocated at exactly the size the kernels use."""
+    import sys
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    asan = subprocess.run([cxx, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not asan or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    d = os.path.join(ROOT, "tests", "host_emul")
+    so = str(tmp_path / "libbsw_emul_asan.so")
+    subprocess.run([cxx, "-O1", "-g", "-std=c++17", "-fPIC", "-fopenmp", "-shared", "-w", "-fsanitize=address",
+                    "-fno-omit-frame-pointer", f"-I{d}", f"-I{ROOT}/genarchbench_b200/csrc", f"-I{ROOT}/include",
+                    "-o", so, os.path.join(d, "emul_lib.cpp")], check=True)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(d, "asan_check.py"), so], capture_output=True, text=True,
+                       env=env, timeout=600)
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, (r.stdout[-500:], r.stderr[-2000:])
