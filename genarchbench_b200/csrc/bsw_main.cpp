@@ -51,7 +51,10 @@ int main(int argc, char *argv[]) {
 
     using clk = std::chrono::steady_clock;
     auto t0 = clk::now();
-    int64_t numPairs = bsw_count_pairs_text(pairFileName);
+    // a packed binary pair file (include/bsw_pairio.h) is recognised by its magic; anything else is the
+    // reference's 3-line text format
+    const bool packed = bsw_count_pairs_packed(pairFileName) >= 0;
+    int64_t numPairs = packed ? bsw_count_pairs_packed(pairFileName) : bsw_count_pairs_text(pairFileName);
     if (numPairs < 0) {
         fprintf(stderr, "Could not open file: %s\n", pairFileName);
         return EXIT_FAILURE;
@@ -60,7 +63,8 @@ int main(int argc, char *argv[]) {
     std::vector<bsw_seqpair> pairs((size_t)numPairs);
     uint8_t *ref = nullptr, *qer = nullptr;
     int64_t refBytes = 0, qerBytes = 0;
-    int64_t got = bsw_read_pairs_text(pairFileName, numPairs, pairs.data(), &ref, &qer, &refBytes, &qerBytes);
+    int64_t got = packed ? bsw_read_pairs_packed(pairFileName, numPairs, pairs.data(), &ref, &qer, &refBytes, &qerBytes)
+                         : bsw_read_pairs_text(pairFileName, numPairs, pairs.data(), &ref, &qer, &refBytes, &qerBytes);
     if (got < 0) {
         fprintf(stderr, "Malformed pair file: %s\n", pairFileName);
         return EXIT_FAILURE;

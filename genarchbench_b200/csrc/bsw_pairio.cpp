@@ -209,58 +209,229 @@ int64_t bsw_count_pairs_text(const char *path) {
     std::vector<char> buf(1 << 20);
     int64_t lines = 0;
     size_t got;
-    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0)
+    char last = '\n';
+    while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
         lines += std::count(buf.begin(), buf.begin() + (long)got, '\n');
+        last = buf[got - 1];
+    }
     fclose(f);
+    if (last != '\n') ++lines;   // a last line without a newline still counts (the reference would drop it)
     return lines / 3;
 }
 
+// Parallel parse: the file is read in one piece, line starts are indexed by T threads (newline count
+// per block, prefix sum, fill), then pairs are parsed by T threads into dense buffers whose offsets come
+// from a prefix sum over the line lengths. (The reference's loader is a serial fgets loop,
+// main_banded.cpp:164-206.)
 int64_t bsw_read_pairs_text(const char *path, int64_t n, bsw_seqpair *pairs, uint8_t **ref_out,
                             uint8_t **qer_out, int64_t *ref_bytes, int64_t *qer_bytes) {
-    FILE *f = fopen(path, "r");
+    FILE *f = fopen(path, "rb");
     if (!f) return -1;
-    std::vector<uint8_t> ref, qer;
-    char *line = nullptr;
-    size_t cap = 0;
-    int64_t k = 0;
-    auto chomp = [](char *s, ssize_t len) -> int {
-        while (len > 0 && (s[len - 1] == '\n' || s[len - 1] == '\r')) --len;
-        return (int)len;
-    };
-    while (k < n) {
-        ssize_t len = getline(&line, &cap, f);
-        if (len < 0) break;
-        int h0 = atoi(line);
-        len = getline(&line, &cap, f);
-        if (len < 0) break;
-        int l1 = chomp(line, len);
-        size_t t0 = ref.size();
-        for (int i = 0; i < l1; ++i) ref.push_back((uint8_t)(line[i] - '0'));
-        len = getline(&line, &cap, f);
-        if (len < 0) { ref.resize(t0); break; }
-        int l2 = chomp(line, len);
-        size_t q0 = qer.size();
-        for (int j = 0; j < l2; ++j) qer.push_back((uint8_t)(line[j] - '0'));
-        if (l1 <= 0 || l2 <= 0 || l1 > BSW_MAX_SEQ_LEN || l2 > BSW_MAX_SEQ_LEN) {
-            free(line); fclose(f); return -1;  // the reference asserts len > 0 (main_banded.cpp:187-188)
-        }
-        bsw_seqpair &sp = pairs[k];
-        sp.id = k; sp.idr = (int64_t)t0; sp.idq = (int64_t)q0;
-        sp.len1 = l1; sp.len2 = l2; sp.h0 = h0;
-        sp.seqid = sp.regid = sp.score = sp.tle = sp.gtle = sp.qle = -1;
-        sp.gscore = sp.max_off = -1;
-        ++k;
-    }
-    free(line);
+    fseek(f, 0, SEEK_END);
+    const int64_t fsz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)fsz + 1);
+    if (fsz > 0 && fread(buf.data(), 1, (size_t)fsz, f) != (size_t)fsz) { fclose(f); return -1; }
     fclose(f);
-    uint8_t *r = (uint8_t *)malloc(ref.size() + 64), *q = (uint8_t *)malloc(qer.size() + 64);
+    buf[(size_t)fsz] = '\n';
+    const int T = hw_threads(0);
+    const int64_t blk = (fsz + T - 1) / std::max(T, 1) + 1;
+    std::vector<int64_t> cnt((size_t)T + 1, 0);
+    auto in_threads = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    in_threads([&](int t) {
+        const int64_t lo = std::min<int64_t>(fsz, t * blk), hi = std::min<int64_t>(fsz, lo + blk);
+        cnt[(size_t)t + 1] = std::count(buf.begin() + lo, buf.begin() + hi, '\n');
+    });
+    for (int t = 0; t < T; ++t) cnt[(size_t)t + 1] += cnt[(size_t)t];
+    int64_t nlines = cnt[(size_t)T];
+    if (fsz > 0 && buf[(size_t)fsz - 1] != '\n') ++nlines;      // last line without a newline
+    std::vector<int64_t> start((size_t)nlines + 1);              // start[l] = offset of line l
+    if (nlines > 0) start[0] = 0;
+    in_threads([&](int t) {
+        const int64_t lo = std::min<int64_t>(fsz, t * blk), hi = std::min<int64_t>(fsz, lo + blk);
+        int64_t l = cnt[(size_t)t];
+        for (int64_t o = lo; o < hi; ++o)
+            if (buf[(size_t)o] == '\n' && l + 1 <= nlines) start[(size_t)++l] = o + 1;
+    });
+    start[(size_t)nlines] = std::max<int64_t>(start[(size_t)nlines], 0);
+    if (fsz > 0 && buf[(size_t)fsz - 1] != '\n') start[(size_t)nlines] = fsz + 1;
+    const int64_t np = std::min<int64_t>(n, nlines / 3);
+    auto line_len = [&](int64_t l) {   // without the newline / carriage return
+        int64_t e = start[(size_t)l + 1] - 1;
+        if (e > start[(size_t)l] && buf[(size_t)e - 1] == '\r') --e;
+        return e - start[(size_t)l];
+    };
+    // lengths, validation, offsets
+    std::vector<int64_t> roff((size_t)np + 1, 0), qoff((size_t)np + 1, 0);
+    std::vector<int> bad((size_t)T, 0);
+    const int64_t per = (np + T - 1) / std::max(T, 1);
+    in_threads([&](int t) {
+        for (int64_t k = t * per; k < std::min(np, (t + 1) * per); ++k) {
+            const int64_t l1 = line_len(3 * k + 1), l2 = line_len(3 * k + 2);
+            if (l1 <= 0 || l2 <= 0 || l1 > BSW_MAX_SEQ_LEN || l2 > BSW_MAX_SEQ_LEN) bad[(size_t)t] = 1;
+            roff[(size_t)k + 1] = l1; qoff[(size_t)k + 1] = l2;
+        }
+    });
+    for (int t = 0; t < T; ++t) if (bad[(size_t)t]) return -1;   // the reference asserts len > 0 (main_banded.cpp:187-188)
+    for (int64_t k = 0; k < np; ++k) { roff[(size_t)k + 1] += roff[(size_t)k]; qoff[(size_t)k + 1] += qoff[(size_t)k]; }
+    uint8_t *r = (uint8_t *)malloc((size_t)roff[(size_t)np] + 64), *q = (uint8_t *)malloc((size_t)qoff[(size_t)np] + 64);
     if (!r || !q) { free(r); free(q); return -1; }
-    memcpy(r, ref.data(), ref.size()); memset(r + ref.size(), 0, 64);
-    memcpy(q, qer.data(), qer.size()); memset(q + qer.size(), 0, 64);
+    memset(r + roff[(size_t)np], 0, 64);
+    memset(q + qoff[(size_t)np], 0, 64);
+    in_threads([&](int t) {
+        for (int64_t k = t * per; k < std::min(np, (t + 1) * per); ++k) {
+            bsw_seqpair &sp = pairs[k];
+            sp.id = k; sp.idr = roff[(size_t)k]; sp.idq = qoff[(size_t)k];
+            sp.len1 = (int32_t)(roff[(size_t)k + 1] - roff[(size_t)k]);
+            sp.len2 = (int32_t)(qoff[(size_t)k + 1] - qoff[(size_t)k]);
+            sp.h0 = atoi(buf.data() + start[(size_t)(3 * k)]);
+            sp.seqid = sp.regid = sp.score = sp.tle = sp.gtle = sp.qle = -1;
+            sp.gscore = sp.max_off = -1;
+            const char *s1 = buf.data() + start[(size_t)(3 * k + 1)], *s2 = buf.data() + start[(size_t)(3 * k + 2)];
+            for (int i = 0; i < sp.len1; ++i) r[sp.idr + i] = (uint8_t)(s1[i] - '0');
+            for (int j = 0; j < sp.len2; ++j) q[sp.idq + j] = (uint8_t)(s2[j] - '0');
+        }
+    });
     *ref_out = r; *qer_out = q;
-    if (ref_bytes) *ref_bytes = (int64_t)ref.size();
-    if (qer_bytes) *qer_bytes = (int64_t)qer.size();
-    return k;
+    if (ref_bytes) *ref_bytes = roff[(size_t)np];
+    if (qer_bytes) *qer_bytes = qoff[(size_t)np];
+    return np;
+}
+
+// ---- packed binary pair file ---------------------------------------------------
+//   header  : "BSWPAIR1", u64 n, u64 data bytes
+//   records : n x { u16 len1, u16 len2, i32 h0, u32 flags }   (12 bytes; flags bit 0 = 4 bits per base)
+//   data    : per pair, query then target, 2 bits per base (4 if the pair holds a base code >= 4), each
+//             sequence padded to 4 bytes -- the layout of the library's device blob slots
+// About 3.5x smaller than the text format and parsed at memory speed.
+namespace {
+struct PackedRec { uint16_t len1, len2; int32_t h0; uint32_t flags; };
+static_assert(sizeof(PackedRec) == 12, "record layout");
+const char kMagic[8] = {'B', 'S', 'W', 'P', 'A', 'I', 'R', '1'};
+inline uint64_t seq_bytes_io(uint32_t len, bool wide) {
+    uint64_t b = wide ? (len + 1) >> 1 : (len + 3) >> 2;
+    return (b + 3u) & ~(uint64_t)3u;
+}
+void pack_seq(const uint8_t *src, int len, bool wide, uint8_t *dst) {
+    memset(dst, 0, (size_t)seq_bytes_io((uint32_t)len, wide));
+    if (wide) for (int i = 0; i < len; ++i) dst[i >> 1] |= (uint8_t)((src[i] > 4 ? 4 : src[i]) << (4 * (i & 1)));
+    else for (int i = 0; i < len; ++i) dst[i >> 2] |= (uint8_t)((src[i] & 3) << (2 * (i & 3)));
+}
+void unpack_seq(const uint8_t *src, int len, bool wide, uint8_t *dst) {
+    if (wide) for (int i = 0; i < len; ++i) dst[i] = (src[i >> 1] >> (4 * (i & 1))) & 0xF;
+    else for (int i = 0; i < len; ++i) dst[i] = (src[i >> 2] >> (2 * (i & 3))) & 3;
+}
+}  // namespace
+
+int bsw_write_pairs_packed(const char *path, const bsw_seqpair *pairs, const uint8_t *ref,
+                           const uint8_t *qer, int64_t n) {
+    if (!path || n < 0 || (n > 0 && (!pairs || !ref || !qer))) return 1;
+    std::vector<PackedRec> rec((size_t)n);
+    std::vector<uint64_t> off((size_t)n + 1, 0);
+    const int T = hw_threads(0);
+    const int64_t per = (n + T - 1) / std::max(T, 1);
+    auto in_threads = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    std::vector<int> bad((size_t)T, 0);
+    in_threads([&](int t) {
+        for (int64_t k = t * per; k < std::min(n, (t + 1) * per); ++k) {
+            const bsw_seqpair &p = pairs[k];
+            if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN) { bad[(size_t)t] = 1; continue; }
+            bool wide = false;
+            for (int i = 0; i < p.len1 && !wide; ++i) wide = ref[p.idr + i] > 3;
+            for (int j = 0; j < p.len2 && !wide; ++j) wide = qer[p.idq + j] > 3;
+            rec[(size_t)k] = PackedRec{(uint16_t)p.len1, (uint16_t)p.len2, p.h0, wide ? 1u : 0u};
+            off[(size_t)k + 1] = seq_bytes_io((uint32_t)p.len2, wide) + seq_bytes_io((uint32_t)p.len1, wide);
+        }
+    });
+    for (int t = 0; t < T; ++t) if (bad[(size_t)t]) return 1;
+    for (int64_t k = 0; k < n; ++k) off[(size_t)k + 1] += off[(size_t)k];
+    std::vector<uint8_t> data((size_t)off[(size_t)n]);
+    in_threads([&](int t) {
+        for (int64_t k = t * per; k < std::min(n, (t + 1) * per); ++k) {
+            const bsw_seqpair &p = pairs[k];
+            const bool wide = rec[(size_t)k].flags & 1u;
+            uint8_t *d = data.data() + off[(size_t)k];
+            pack_seq(qer + p.idq, p.len2, wide, d);
+            pack_seq(ref + p.idr, p.len1, wide, d + seq_bytes_io((uint32_t)p.len2, wide));
+        }
+    });
+    FILE *f = fopen(path, "wb");
+    if (!f) return 1;
+    const uint64_t hdr[2] = {(uint64_t)n, off[(size_t)n]};
+    bool ok = fwrite(kMagic, 1, 8, f) == 8 && fwrite(hdr, 8, 2, f) == 2 &&
+              (n == 0 || fwrite(rec.data(), sizeof(PackedRec), (size_t)n, f) == (size_t)n) &&
+              (data.empty() || fwrite(data.data(), 1, data.size(), f) == data.size());
+    return (fclose(f) == 0 && ok) ? 0 : 2;
+}
+
+int64_t bsw_count_pairs_packed(const char *path) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    char m[8];
+    uint64_t hdr[2];
+    const bool ok = fread(m, 1, 8, f) == 8 && memcmp(m, kMagic, 8) == 0 && fread(hdr, 8, 2, f) == 2;
+    fclose(f);
+    return ok ? (int64_t)hdr[0] : -1;
+}
+
+int64_t bsw_read_pairs_packed(const char *path, int64_t n, bsw_seqpair *pairs, uint8_t **ref_out,
+                              uint8_t **qer_out, int64_t *ref_bytes, int64_t *qer_bytes) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    char m[8];
+    uint64_t hdr[2];
+    if (fread(m, 1, 8, f) != 8 || memcmp(m, kMagic, 8) != 0 || fread(hdr, 8, 2, f) != 2) { fclose(f); return -1; }
+    const int64_t total = (int64_t)hdr[0], np = std::min<int64_t>(n, total);
+    std::vector<PackedRec> rec((size_t)total);
+    std::vector<uint8_t> data((size_t)hdr[1]);
+    if ((total && fread(rec.data(), sizeof(PackedRec), (size_t)total, f) != (size_t)total) ||
+        (!data.empty() && fread(data.data(), 1, data.size(), f) != data.size())) { fclose(f); return -1; }
+    fclose(f);
+    std::vector<uint64_t> doff((size_t)np + 1, 0), roff((size_t)np + 1, 0), qoff((size_t)np + 1, 0);
+    for (int64_t k = 0; k < np; ++k) {
+        const PackedRec &r = rec[(size_t)k];
+        const bool wide = r.flags & 1u;
+        if (r.len1 > BSW_MAX_SEQ_LEN || r.len2 > BSW_MAX_SEQ_LEN) return -1;
+        doff[(size_t)k + 1] = doff[(size_t)k] + seq_bytes_io(r.len2, wide) + seq_bytes_io(r.len1, wide);
+        roff[(size_t)k + 1] = roff[(size_t)k] + r.len1;
+        qoff[(size_t)k + 1] = qoff[(size_t)k] + r.len2;
+    }
+    if (doff[(size_t)np] > data.size()) return -1;
+    uint8_t *rr = (uint8_t *)malloc((size_t)roff[(size_t)np] + 64), *qq = (uint8_t *)malloc((size_t)qoff[(size_t)np] + 64);
+    if (!rr || !qq) { free(rr); free(qq); return -1; }
+    memset(rr + roff[(size_t)np], 0, 64);
+    memset(qq + qoff[(size_t)np], 0, 64);
+    const int T = hw_threads(0);
+    const int64_t per = (np + T - 1) / std::max(T, 1);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t]() {
+            for (int64_t k = t * per; k < std::min(np, (t + 1) * per); ++k) {
+                const PackedRec &r = rec[(size_t)k];
+                const bool wide = r.flags & 1u;
+                bsw_seqpair &sp = pairs[k];
+                sp.id = k; sp.idr = (int64_t)roff[(size_t)k]; sp.idq = (int64_t)qoff[(size_t)k];
+                sp.len1 = r.len1; sp.len2 = r.len2; sp.h0 = r.h0;
+                sp.seqid = sp.regid = sp.score = sp.tle = sp.gtle = sp.qle = -1;
+                sp.gscore = sp.max_off = -1;
+                const uint8_t *d = data.data() + doff[(size_t)k];
+                unpack_seq(d, r.len2, wide, qq + sp.idq);
+                unpack_seq(d + seq_bytes_io(r.len2, wide), r.len1, wide, rr + sp.idr);
+            }
+        });
+    for (auto &x : th) x.join();
+    *ref_out = rr; *qer_out = qq;
+    if (ref_bytes) *ref_bytes = (int64_t)roff[(size_t)np];
+    if (qer_bytes) *qer_bytes = (int64_t)qoff[(size_t)np];
+    return np;
 }
 
 }  // extern "C"

@@ -67,6 +67,12 @@ def lib() -> C.CDLL:
                                           C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                           C.POINTER(C.c_int64)]
         L.bsw_read_pairs_text.restype = C.c_int64
+        L.bsw_write_pairs_packed.argtypes = L.bsw_write_pairs_text.argtypes
+        L.bsw_write_pairs_packed.restype = C.c_int
+        L.bsw_count_pairs_packed.argtypes = [C.c_char_p]
+        L.bsw_count_pairs_packed.restype = C.c_int64
+        L.bsw_read_pairs_packed.argtypes = L.bsw_read_pairs_text.argtypes
+        L.bsw_read_pairs_packed.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -158,4 +164,26 @@ def read_text(path: str) -> PairBatch:
                                     C.byref(rb), C.byref(qb))
     if got < 0:
         raise OSError(f"malformed pair file {path}")
+    return PairBatch(pairs[:got], _take(rp, rb.value), _take(qp, qb.value))
+
+
+def write_packed(path: str, b: PairBatch) -> None:
+    """Packed binary pair file (include/bsw_pairio.h): 2 bits per base, ~3.5x smaller than the text format."""
+    rc = lib().bsw_write_pairs_packed(path.encode(), b.pairs.ctypes.data, b.ref.ctypes.data,
+                                      b.qer.ctypes.data, len(b))
+    if rc != 0:
+        raise OSError(f"bsw_write_pairs_packed({path}) failed ({rc})")
+
+
+def read_packed(path: str) -> PairBatch:
+    n = lib().bsw_count_pairs_packed(path.encode())
+    if n < 0:
+        raise OSError(f"{path} is not a packed pair file")
+    pairs = np.zeros(n, dtype=SEQPAIR_DTYPE)
+    rp, qp = C.c_void_p(), C.c_void_p()
+    rb, qb = C.c_int64(), C.c_int64()
+    got = lib().bsw_read_pairs_packed(path.encode(), n, pairs.ctypes.data, C.byref(rp), C.byref(qp),
+                                      C.byref(rb), C.byref(qb))
+    if got < 0:
+        raise OSError(f"malformed packed pair file {path}")
     return PairBatch(pairs[:got], _take(rp, rb.value), _take(qp, qb.value))

@@ -54,3 +54,33 @@ def test_seqpair_layout_matches_reference_struct():
     want = dict(idr=0, idq=8, id=16, len1=24, len2=28, h0=32, seqid=36, regid=40, score=44, tle=48,
                 gtle=52, qle=56, gscore=60, max_off=64)     # SURVEY 8a row 1 (offsetof-verified)
     assert {k: d.fields[k][1] for k in want} == want
+
+
+def test_text_and_packed_files_round_trip(tmp_path):
+    """The reference's 3-line text format (parallel reader) and the packed binary format hold the same
+    pairs: lengths, h0 and every base, including ambiguous ones and ragged / very short sequences."""
+    import numpy as np
+    from genarchbench_b200 import pairio
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.n_frac = 1, 700, 0.3
+    b = pairio.generate(c, 5000, seed=99)
+    t, p = str(tmp_path / "pairs.txt"), str(tmp_path / "pairs.bswp")
+    pairio.write_text(t, b)
+    pairio.write_packed(p, b)
+    import os
+    assert os.path.getsize(p) * 2 < os.path.getsize(t)      # 30 % of these pairs are 4-bit (ambiguous base)
+    for got in (pairio.read_text(t), pairio.read_packed(p)):
+        assert len(got) == len(b)
+        for f in ("len1", "len2", "h0"):
+            assert (got.pairs[f] == b.pairs[f]).all()
+        assert (got.pairs["score"] == -1).all()
+        for k in list(range(50)) + [len(b) - 1]:
+            pa, pb = got.pairs[k], b.pairs[k]
+            assert (got.ref[pa["idr"]:pa["idr"] + pa["len1"]] == b.ref[pb["idr"]:pb["idr"] + pb["len1"]]).all()
+            assert (got.qer[pa["idq"]:pa["idq"] + pa["len2"]] == b.qer[pb["idq"]:pb["idq"] + pb["len2"]]).all()
+        assert int(got.ref[:got.pairs["len1"].sum()].astype(np.int64).sum()) == int(b.ref[:b.pairs["len1"].sum()].astype(np.int64).sum())
+    with open(str(tmp_path / "no_newline.txt"), "w") as fh:      # last line without '\n', CRLF line ends
+        fh.write("7\r\n0123\r\n012\r\n5\n3210\n32")
+    g = pairio.read_text(str(tmp_path / "no_newline.txt"))
+    assert g.pairs["len1"].tolist() == [4, 4] and g.pairs["len2"].tolist() == [3, 2] and g.pairs["h0"].tolist() == [7, 5]
+    assert g.qer[g.pairs["idq"][1]:g.pairs["idq"][1] + 2].tolist() == [3, 2]
