@@ -283,6 +283,7 @@ def main():
         "traffic_source": "ncu, profiles/r1_dram_bytes_per_launch_10Mpairs.csv, per pair x pairs of this run",
         "hbm": {"algorithmic_bytes_per_step": alg_bytes, "bytes_per_pair": BYTES_PER_PAIR_FMT,
                 "achieved_gbs": alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
+                "frac": (alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                 "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json (of measured)"
                 if peaks.get("hbm_gbs") else "unavailable"},
     }
