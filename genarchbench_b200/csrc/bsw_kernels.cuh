@@ -171,17 +171,23 @@ struct Rows {
         const uint32_t w = QS2(g >> 1);
         return (g & 1) ? (w >> 16) : (w & 0xFFFFu);
     }
-    // target bases of rows 8w .. 8w+7 as 8 nibbles: 4 - code for narrow pairs (see score_lut), the
-    // code itself for wide pairs
+    // The row's target seed for the PRMT selector, in both 16-bit halves: nibbles c, c | 8 with
+    // c = 4 - code (narrow pairs, see score_lut) or the code itself (wide pairs). `traw` caches the packed
+    // target word (16 rows of 2 bits, or 8 rows of 4 bits) and is refilled when it runs out: one LDG per
+    // 16 / 8 rows and three ALU ops per row.
     template <bool WIDE>
-    __device__ __forceinline__ uint32_t TG(int w) const {
-        if (WIDE) return tb[w];
-        uint32_t x = tb[w >> 1];
-        x = (w & 1) ? (x >> 16) : (x & 0xFFFFu);   // 8 bases, 2 bits each
-        x = (x | (x << 8)) & 0x00FF00FFu;
-        x = (x | (x << 4)) & 0x0F0F0F0Fu;
-        x = (x | (x << 2)) & 0x33333333u;           // -> 8 nibbles
-        return BSW_SEL_LOP3 ? x : 0x44444444u - x;  // never borrows
+    __device__ __forceinline__ uint32_t row_seed(int i, uint32_t &traw) const {
+        uint32_t code;
+        if (WIDE) {
+            if ((i & 7) == 0) traw = tb[i >> 3];
+            code = traw & 7u;
+            traw >>= 4;
+        } else {
+            if ((i & 15) == 0) traw = tb[i >> 4];
+            code = BSW_SEL_LOP3 ? (traw & 3u) : 4u - (traw & 3u);
+            traw >>= 2;
+        }
+        return code * 0x11111111u + 0x80808080u;
     }
 };
 
@@ -408,10 +414,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                 ++kinit;
             }
         }
-        if ((i & 7) == 0) tword = R.template TG<WIDE>(i >> 3);
-        // the row's target seed in both halves: nibbles c, c | 8 with c = 4 - code (narrow) / code (wide)
-        const uint32_t tsel = (tword & 7u) * 0x11111111u + 0x80808080u;
-        tword >>= 4;
+        const uint32_t tsel = R.template row_seed<WIDE>(i, tword);
 
         hcol -= P.e_del;
         const int hleft = beg == 0 ? max(hcol, 0) : 0;
@@ -916,9 +919,7 @@ __device__ inline PairResult warp_extend_pair(Rows &R, const uint32_t *__restric
         if (beg >= end) break;
         if (COUNT) cells += (uint32_t)(end - beg);   // beg is the reference's exact beg in this kernel
 
-        if ((i & 7) == 0) tword = R.template TG<WIDE>(i >> 3);
-        const uint32_t tsel = (tword & 7u) * 0x11111111u + 0x80808080u;
-        tword >>= 4;
+        const uint32_t tsel = R.template row_seed<WIDE>(i, tword);
         hcol -= P.e_del;
         const int hleft = beg == 0 ? max(hcol, 0) : 0;
 
