@@ -233,6 +233,33 @@ def test_bsw_main_driver_prints_reference_style_scores(tmp_path):
     assert re.search(r"Overall SW cycles = \d+, [0-9.]+ s", r.stdout) and "Total Pairs processed: 20000" in r.stdout
 
 
+def test_in_process_multi_gpu_split():
+    """bsw_gpu_init(params, n_gpus): slabs go round-robin over the GPUs of one process (host split and
+    gather, no collective). Needs at least two devices."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("one GPU visible")
+    b = pairio.generate(3, 3_000_000, seed=3)
+    b.pairs[-500:] = b.pairs[:500]
+    with bsw.BswGpu(n_gpus=min(ndev, 4)) as g:
+        g.batch(b.pairs, b.ref, b.qer, 100)
+        st = g.stats()
+        assert st["n_gpus"] == min(ndev, 4) and st["pairs"] == len(b)
+        out = b.outputs().copy()
+        g.stage(b.pairs, b.ref, b.qer, 100)
+        assert g.run_staged() > 0
+        for f in pairio.OUTPUT_FIELDS:
+            b.pairs[f] = -1
+        g.fetch_staged(b.pairs)
+        assert (b.outputs() == out).all()
+    assert (out[-500:] == out[:500]).all()
+    idx = np.random.default_rng(4).choice(len(b), 30000, replace=False)
+    samp = pairio.PairBatch(b.pairs[idx].copy(), b.ref, b.qer)
+    oracle.oracle_batch(samp)
+    assert_same_outputs(out[idx], samp.outputs(), samp, "multi-GPU split, sampled")
+
+
 def test_dpx_peak_is_measurable():
     v = bsw.dpx_peak(0)
     assert 5e3 < v < 1e5                                        # giga thread-instructions / s
