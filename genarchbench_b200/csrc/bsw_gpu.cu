@@ -53,8 +53,9 @@ constexpr int kBinCols = 16;                   // query-length granularity of a 
 constexpr int kVersion = 2;
 // device sort key of a pair (64 bits), descending order = launch order:
 //   launch bin (len2 - 1) / 16 | holds an ambiguous base | (len2 - 1) % 16 | len1 (b1 bits) | h0 (b0 bits)
-// with b1, b0 sized per slab; at most 16 + 15 + 15 bits
-constexpr int kKeyBits = 46;
+// with b1, b0 sized per slab (bins merged into the windowed launch: 1 | wide | len2 - 1 on top instead);
+// at most 17 + 15 + 15 bits
+constexpr int kKeyBits = 47;
 constexpr int kMaxBins = BSW_MAX_SEQ_LEN / kBinCols + 2;
 
 using Clock = std::chrono::steady_clock;
@@ -102,6 +103,7 @@ struct Slab {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     bool busy = false;
     int key_b1 = 15, key_b0 = 16, key_bits = 48;   // sort key layout of the current contents (see sort_key)
+    int long_bin0 = 0x7FFFFFFF;                    // launch bins >= this one are merged (windowed rows)
     bool fastm = false;      // every score of the slab times (match+1) fits int16: one-instruction M
     bool pinned = true;      // false for staged slabs (host side borrowed)
 };
@@ -404,22 +406,47 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
     s.key_b1 = bits_for((uint32_t)maxt);
     s.key_b0 = bits_for((uint32_t)maxh);
-    s.key_bits = s.key_b1 + s.key_b0 + bits_for(((((uint32_t)std::max(maxq, 1) - 1) >> 4) << 5) | 31u);
     for (int t = 0; t < T; ++t) s.trivial.insert(s.trivial.end(), triv[(size_t)t].begin(), triv[(size_t)t].end());
     s.n_dev = n - (int)s.trivial.size();
     st.host_pack_ms += ms_since(t0);
     t0 = Clock::now();
 
     // ---- plan: one launch per query-length bin, longest first, the wide pairs of a bin in front
-    // (== the device sort order: key descending)
+    // (== the device sort order: key descending). The bins that run on windowed rows need the same
+    // shared memory whatever their query length, so they are merged into ONE launch at the front (the sort
+    // key puts all of their wide pairs first): a slab of mixed lengths then issues a few hundred blocks
+    // at once instead of dozens of 30-block launches that each last as long as their slowest pair.
+    s.long_bin0 = 0x7FFFFFFF;
     if (s.n_dev > 0) {
         const int nbins = maxq / kBinCols + 1;
+        const int nk = window_elems(h->K.w);
+        const size_t ws = (size_t)20 * nk * kBlockPairs;
+        const bool can_window = ws <= kMaxSmem && use_window();
+        auto bin_smem = [&](int b) {
+            const int q_hi = std::min(maxq, (b + 1) * kBinCols);
+            return use_duo() ? (size_t)duo_thread_bytes(q_hi) * kDuoThreads : smem_need(row_elems(q_hi), sel_words(q_hi));
+        };
+        if (can_window)
+            for (int b = 0; b < nbins; ++b) if (bin_smem(b) > kMaxSmem) { s.long_bin0 = b; break; }
         int p = 0;
+        int nw_long = 0, nn_long = 0;
         for (int b = nbins - 1; b >= 0; --b) {
             int nw = 0, nn = 0;
             for (int t = 0; t < T; ++t) {
                 nn += (int)h->hist[(size_t)t * 2 * kMaxBins + (size_t)b];
                 nw += (int)h->hist[(size_t)t * 2 * kMaxBins + kMaxBins + (size_t)b];
+            }
+            if (b >= s.long_bin0) {
+                nw_long += nw; nn_long += nn;
+                if (b == s.long_bin0 && nw_long + nn_long > 0) {
+                    Launch L;
+                    L.first = 0; L.n = nw_long + nn_long; L.n_wide = nw_long; L.work = (int64_t)L.n * maxq * 2 * h->K.w;
+                    L.row_el = L.qs_words = L.duo_el = 0;
+                    L.smem = ws; L.win_nk = nk;
+                    s.launches.push_back(L);
+                    p = L.n;
+                }
+                continue;
             }
             if (nw + nn == 0) continue;
             const int q_hi = std::min(maxq, (b + 1) * kBinCols);
@@ -428,19 +455,15 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             L.row_el = row_elems(q_hi);
             L.qs_words = sel_words(q_hi);
             L.duo_el = duo_elems(q_hi);
-            L.smem = use_duo() ? (size_t)duo_thread_bytes(q_hi) * kDuoThreads : smem_need(L.row_el, L.qs_words);
+            L.smem = bin_smem(b);
             L.win_nk = 0;
-            if (L.smem > kMaxSmem) {
-                // whole rows do not fit: windowed rows if the band is narrow enough, else one warp per pair
-                const int nk = window_elems(h->K.w);
-                const size_t ws = (size_t)20 * nk * kBlockPairs;
-                if (ws <= kMaxSmem && use_window()) { L.smem = ws; L.win_nk = nk; }
-                else L.smem = 0;
-            }
+            if (L.smem > kMaxSmem) L.smem = 0;   // whole rows do not fit and the band is too wide for a window: one warp per pair
             s.launches.push_back(L);
             p += nw + nn;
         }
     }
+    // sort key layout (see sort_key)
+    s.key_bits = s.key_b1 + s.key_b0 + (s.long_bin0 != 0x7FFFFFFF ? 17 : bits_for(((((uint32_t)std::max(maxq, 1) - 1) >> 4) << 5) | 31u));
     st.host_plan_ms += ms_since(t0);
     return BSW_OK;
 }
@@ -573,7 +596,7 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
 int bin_slab(bsw_handle *h, Slab &s, cudaStream_t st) {
     if (s.n_dev == 0) return BSW_OK;
     const int n = s.n;
-    bsw_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_meta, n, s.d_keys, s.d_ord, s.key_b1, s.key_b0);
+    bsw_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_meta, n, s.d_keys, s.d_ord, s.key_b1, s.key_b0, s.long_bin0);
     CU(cudaGetLastError());
     h->stats.kernel_launches++;
     size_t tmp = s.sort_tmp_bytes;

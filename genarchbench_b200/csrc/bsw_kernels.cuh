@@ -1140,19 +1140,23 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 // The fields are packed as tightly as the slab's largest len1 / h0 allow (b1, b0 bits, chosen by the
 // host from its pass), so the radix sort runs over as few 8-bit digits as possible.
-__host__ __device__ inline uint64_t sort_key(uint32_t len2, uint32_t len1, uint32_t h0, uint32_t wide, int b1, int b0) {
+// Launch bins >= long_bin0 run as ONE windowed-rows launch: their top field is 1 | wide | len2 - 1 (17
+// bits), which sorts them in front of everything else, their wide pairs first.
+__host__ __device__ inline uint64_t sort_key(uint32_t len2, uint32_t len1, uint32_t h0, uint32_t wide, int b1, int b0,
+                                             int long_bin0) {
     if (len2 == 0 || len1 == 0) return 0ull;
     const uint32_t v = len2 - 1;
-    return ((uint64_t)(((v >> 4) << 5) | (wide << 4) | (v & 15u)) << (b1 + b0)) | ((uint64_t)len1 << b0) | h0;
+    const uint32_t top = (int)(v >> 4) >= long_bin0 ? (0x10000u | (wide << 15) | v) : (((v >> 4) << 5) | (wide << 4) | (v & 15u));
+    return ((uint64_t)top << (b1 + b0)) | ((uint64_t)len1 << b0) | h0;
 }
 __host__ __device__ inline int bits_for(uint32_t v) { int b = 1; while ((v >> b) != 0u) ++b; return b; }
 #ifndef BSW_HOST_EMUL
 __global__ void bsw_key_kernel(const PairMeta *__restrict__ meta, int n, uint64_t *__restrict__ keys,
-                               uint32_t *__restrict__ idx, int b1, int b0) {
+                               uint32_t *__restrict__ idx, int b1, int b0, int long_bin0) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const PairMeta m = meta[k];
-    keys[k] = sort_key(m.len2, m.len1, (uint32_t)m.h0, m.flags & 1u, b1, b0);
+    keys[k] = sort_key(m.len2, m.len1, (uint32_t)m.h0, m.flags & 1u, b1, b0, long_bin0);
     idx[k] = (uint32_t)k;
 }
 #endif
