@@ -329,6 +329,7 @@ __device__ __forceinline__ int pair_band(const KParams &P, int qlen) {
 __host__ __device__ inline int row_elems(int qlen) { return (qlen + 4) >> 2; }
 // elements of a windowed row (extend_pair<.., WIN>) for band width w: a power of two, 4 * nk >= 2 w + 16
 __host__ __device__ inline int window_elems(int w) {
+    if (w > 65536) w = 65536;   // a pair's band never exceeds its query length; keeps the arithmetic in range
     int nk = 8;
     while (4 * nk < 2 * w + 16) nk <<= 1;
     return nk;

@@ -85,6 +85,17 @@ def test_long_pairs_nondefault_scoring():
         assert_same_outputs(e.outputs(), a.outputs(), e, f"long pairs, {params}")
 
 
+def test_huge_band_argument(gpu):
+    """w far beyond any sequence length (the per-pair band clamps it, bandedSWA.cpp:2898-2919)."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max = 100, 700
+    b = pairio.generate(c, 3000, seed=21)
+    a = b.copy()
+    oracle.oracle_batch(a, w=1 << 29)
+    gpu.batch(b.pairs, b.ref, b.qer, 1 << 29)
+    assert_same_outputs(b.outputs(), a.outputs(), b, "w = 2^29")
+
+
 def test_very_long_pair(gpu):
     """One pair near the kernel's limits: 20k x 30k bases, a single warp with a 150 KB row."""
     rng = np.random.default_rng(5)
