@@ -45,7 +45,7 @@ def test_reference_interface_mirror():
     assert_same_outputs(b.outputs(), a.outputs(), b, "mirror class, 512-pair batches")
 
 
-@pytest.mark.parametrize("w", [1, 3, 10, 30, 200])
+@pytest.mark.parametrize("w", [0, 1, 3, 10, 30, 200])
 def test_band_widths(gpu, w):
     c = pairio.preset(4)
     c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 300, 0, 80, 0.3, 0.2
@@ -83,6 +83,19 @@ def test_long_pairs_nondefault_scoring():
         with bsw.BswGpu(**params) as g:
             g.batch(e.pairs, e.ref, e.qer, 60)
         assert_same_outputs(e.outputs(), a.outputs(), e, f"long pairs, {params}")
+
+
+def test_large_seed_scores_take_the_general_m_path(gpu):
+    """h0 close to the int16 limit: score * (match + 1) no longer fits, so the launches use the general
+    M = Hd ? Hd + s : 0 instructions (FASTM off) -- thread-per-pair, windowed and warp kernels."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac = 20, 900, 20000, 31000, 0.2
+    b = pairio.generate(c, 4000, seed=31)
+    for w in (100, 300):
+        a = b.copy(); e = b.copy()
+        oracle.oracle_batch(a, w=w)
+        gpu.batch(e.pairs, e.ref, e.qer, w)
+        assert_same_outputs(e.outputs(), a.outputs(), e, f"large h0, w={w}")
 
 
 def test_huge_band_argument(gpu):
