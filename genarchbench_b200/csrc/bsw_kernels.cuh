@@ -37,6 +37,9 @@
 #ifndef BSW_PREFETCH      // issue the next block's loads before computing the current block
 #define BSW_PREFETCH 1
 #endif
+#ifndef BSW_WIN_GROUPS    // groups per inner-loop trip of the windowed kernel
+#define BSW_WIN_GROUPS 8
+#endif
 #ifndef BSW_ST_SHARED     // 16-bit row stores through st.shared (short kernel only)
 #define BSW_ST_SHARED 0
 #endif
@@ -782,10 +785,10 @@ bsw_win_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ o
     if (wide) {
         src = blob + src[0];
         unpack_pair<true>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, true, true, 8>(R, m.len2, m.len1, m.h0, P);
+        r = extend_pair<FASTM, SYM, COUNT, true, true, BSW_WIN_GROUPS>(R, m.len2, m.len1, m.h0, P);
     } else {
         unpack_pair<false>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, false, true, 8>(R, m.len2, m.len1, m.h0, P);
+        r = extend_pair<FASTM, SYM, COUNT, false, true, BSW_WIN_GROUPS>(R, m.len2, m.len1, m.h0, P);
     }
     store_result(out, m.id, r);
 }
