@@ -457,7 +457,20 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             L.duo_el = duo_elems(q_hi);
             L.smem = bin_smem(b);
             L.win_nk = 0;
-            if (L.smem > kMaxSmem) L.smem = 0;   // whole rows do not fit and the band is too wide for a window: one warp per pair
+            if (L.smem > kMaxSmem) {
+                // whole rows do not fit and the band is too wide for a window: one warp per pair. Its shared
+                // memory per pair is small against the SM's, so neighbouring bins share a launch as long as
+                // the longest query of the launch is at most twice theirs (one launch per length octave).
+                L.smem = 0;
+                if (!s.launches.empty()) {
+                    Launch &prev = s.launches.back();
+                    if (prev.smem == 0 && prev.win_nk == 0 && prev.first + prev.n == p && prev.row_el <= 2 * L.row_el) {
+                        prev.n += L.n; prev.n_wide += L.n_wide;
+                        p += nw + nn;
+                        continue;
+                    }
+                }
+            }
             s.launches.push_back(L);
             p += nw + nn;
         }

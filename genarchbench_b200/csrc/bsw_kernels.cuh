@@ -1127,7 +1127,9 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     R.tb = nullptr; R.kmask = -1; R.qb = nullptr;
     const uint32_t *src = blob + m.off;
     PairResult r;
-    if (p < n_wide) r = warp_extend_pair<FASTM, SYM, COUNT, true>(R, blob + src[0], m.len2, m.len1, m.h0, P);
+    // one pair per warp: the pair's own flag picks the instantiation (launches of this kernel merge several
+    // length bins, so the pairs holding an ambiguous base are not all in front)
+    if (m.flags & 1) r = warp_extend_pair<FASTM, SYM, COUNT, true>(R, blob + src[0], m.len2, m.len1, m.h0, P);
     else r = warp_extend_pair<FASTM, SYM, COUNT, false>(R, src, m.len2, m.len1, m.h0, P);
     if ((threadIdx.x & 31) == 0) store_result(out, m.id, r);
 }
