@@ -251,6 +251,7 @@ inline bool use_duo() {
 // The histogram is the launch plan: the device sorts pair indices by (bin, wide, len2, len1) itself.
 // Returns BSW_OK, an error, or kRetry with s.blob_bytes = the capacity the slab really needs.
 constexpr int kRetry = -1;
+constexpr uint64_t kArenaWords = 32 << 10;   // 128 KiB of blob per reservation
 
 // Results of an older slab that still have to go into the caller's SeqPair array. prepare_slab works
 // them off inside its own parallel loop, interleaved with the packing chunks: the scatter is pure memory
@@ -313,6 +314,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     {
         const int t = omp_get_thread_num();
         uint32_t *hist = h->hist.data() + (size_t)t * 2 * kMaxBins;
+        uint64_t aoff = 0, aend = 0;   // this thread's current arena of the blob, in 4-byte words
         // work items: the packing chunks, with the scatter chunks of `job` spread evenly between them
 #pragma omp for schedule(dynamic, 2)
         for (int it = 0; it < nitems; ++it) {
@@ -325,32 +327,33 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             }
             const int c = it - sc_before;
             const int k0 = c * kChunk, k1 = std::min(n, k0 + kChunk);
-            // ---- loop A
-            uint64_t words = 0;
-            int cbad = 0;
-            for (int k = k0; k < k1; ++k) {
-                const bsw_seqpair &p = pp[k];
-                if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN ||
-                    p.h0 < 0 || (int64_t)p.h0 + (int64_t)p.len2 * match > 32767) {
-                    cbad = 1;
-                    break;
-                }
-                words += slot_words((uint32_t)p.len2, (uint32_t)p.len1);
-            }
-            if (cbad) { bad |= 1; continue; }
-            uint64_t off = cursor.fetch_add(words, std::memory_order_relaxed);
-            if (off + words > cap_words) { overflow |= 1; continue; }
-            // ---- loop B
+            // The thread packs into its own arena of the pinned blob and reserves the next one with a single
+            // atomic add when a slot does not fit (the unused tail of an arena, less than one slot, is simply
+            // uploaded with the rest): no sizing pass over the records.
             for (int k = k0; k < k1; ++k) {
                 const bsw_seqpair &sp = pp[k];
+                if (sp.len1 < 0 || sp.len2 < 0 || sp.len1 > BSW_MAX_SEQ_LEN || sp.len2 > BSW_MAX_SEQ_LEN ||
+                    sp.h0 < 0 || (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767) {
+                    bad |= 1;
+                    continue;
+                }
                 if (k + 4 < k1) {   // the records are read in order; pull the next sequences in early
                     __builtin_prefetch(qer + pp[k + 4].idq);
                     __builtin_prefetch(ref + pp[k + 4].idr);
                     __builtin_prefetch(ref + pp[k + 4].idr + 64);
                 }
-                uint8_t *dst = blob + (size_t)off * 4;
                 const uint32_t qb = seq_bytes((uint32_t)sp.len2, false);
                 const uint32_t sw = slot_words((uint32_t)sp.len2, (uint32_t)sp.len1);
+                if (aoff + sw > aend) {
+                    const uint64_t want = std::max<uint64_t>(kArenaWords, sw);
+                    aoff = cursor.fetch_add(want, std::memory_order_relaxed);
+                    aend = aoff + want;
+                    if (aend > cap_words) { overflow |= 1; aend = aoff; }   // stays empty: every later slot retries and fails
+                }
+                if (aoff + sw > aend) continue;
+                const uint64_t off = aoff;
+                aoff += sw;
+                uint8_t *dst = blob + (size_t)off * 4;
                 bool w1, w2;
                 if (packer == 2) {
                     w1 = pack2bit_avx2(qer + sp.idq, sp.len2, dst);
@@ -393,7 +396,6 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                     maxt = std::max(maxt, sp.len1);
                     maxh = std::max(maxh, sp.h0);
                 }
-                off += sw;
             }
         }
     }
@@ -486,6 +488,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
 int prepare_slab_fit(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
                      int64_t lo, int n, size_t blob_guess, ScatterJobs jobs = ScatterJobs()) {
     auto t0 = Clock::now();
+    blob_guess += (size_t)omp_get_max_threads() * kArenaWords * 4;   // every thread may leave an arena partly unused
     int rc = ensure_slab(h, s, n, blob_guess);
     h->stats.host_alloc_ms += ms_since(t0);
     if (rc) return rc;
