@@ -40,6 +40,9 @@
 #ifndef BSW_WIN_GROUPS    // groups per inner-loop trip of the windowed kernel
 #define BSW_WIN_GROUPS 8
 #endif
+#ifndef BSW_TAIL_NOUNROLL  // keep the single-group tail loop rolled (smaller code)
+#define BSW_TAIL_NOUNROLL 1
+#endif
 #ifndef BSW_ST_SHARED     // 16-bit row stores through st.shared (short kernel only)
 #define BSW_ST_SHARED 0
 #endif
@@ -586,6 +589,9 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                 } while (more);
             }
         }
+#if BSW_TAIL_NOUNROLL
+#pragma unroll 1
+#endif
         for (; g <= g1; ++g) {
             const uint2 he0 = R.HE(g);
             const uint32_t q = R.QS(g);
