@@ -131,7 +131,7 @@ struct Device {
 struct bsw_handle {
     bsw_params P;
     KParams K;
-    bool match1 = false, sym = false;
+    bool sym = false;
     std::vector<Device> devs;
     bsw_gpu_stats stats;
     std::string err;
@@ -822,7 +822,6 @@ int bsw_gpu_init_devices(const bsw_params *params, int n_devices, const int *dev
     h->P = p;
     h->K = KParams{p.o_del, p.e_del, p.o_ins, p.e_ins, p.zdrop, p.end_bonus, p.match, p.mismatch, p.ambig, 0,
                    max_score_of(p.match, p.mismatch, p.ambig), 65536u, (uint32_t)(p.match + 1), 1u};
-    h->match1 = (p.match == 1);
     h->sym = (p.o_del == p.o_ins && p.e_del == p.e_ins);
     memset(&h->stats, 0, sizeof h->stats);
     h->stats.n_gpus = (int)ids.size();

@@ -5,21 +5,28 @@
 // row budget :3035-3036,3130-3144).
 //
 // Design:
-//  * one THREAD per pair. The H/E band rows of the pair live in shared memory, interleaved by
-//    thread (word w of thread t at [w*NT + t]) so every access is bank-conflict free whatever column
-//    each thread is at. Long pairs use the same code over a global-memory scratch.
+//  * bsw_short_kernel: one THREAD per pair. The H/E rows of the pair live in shared memory,
+//    interleaved by thread (element k of thread t at [k*NT + t]) so every access is bank-conflict free
+//    whatever column each thread is at. bsw_win_kernel is the same code over a sliding window of the
+//    rows (long queries under a narrow band); bsw_long_kernel gives everything longer one WARP per
+//    pair (tiles of 128 columns, max-plus warp scan of F, REDUX row decisions).
 //  * the two 16-bit lanes of every DPX instruction are two ADJACENT COLUMNS (2g, 2g+1) of the same
 //    row of the same pair, so all row-sequential decisions of the reference (band clamp, row max /
 //    last argmax, m==0 exit, z-drop, trailing-zero trimming) stay exact and per pair.
-//      M  = Hd + min(s, Hd)            (== Hd ? Hd+s : 0 up to values <= 0, which behave like 0)
-//      T  = max(M - oe, 0)             VIADDMNMX.S16x2.RELU
-//      E' = max(E - e_del, T)          VIADDMNMX.S16x2
-//      F  : two-step in-register scan  2 x VIADDMNMX.S16x2 (+1 IMAD, +1 shift)
-//      H  = max(M, E, F)               VIMNMX3.S16x2
-//    substitution scores for both lanes come from ONE PRMT that indexes an 8-byte LUT with the
-//    per-lane (query ^ target) code (ambiguous base folded in through an OR on bit 2).
+//      M  = min(Hd + s, Hd * (match+1))  VIADDMNMX.S16x2 (== Hd ? Hd+s : 0 up to values <= 0, which
+//                                        behave like 0); general form when the product may overflow
+//      T  = max(M - oe, 0)               VIADDMNMX.S16x2.RELU
+//      E' = max(E - e_del, T)            VIADDMNMX.S16x2
+//      F  : two-step in-register scan    2 x VIADDMNMX.S16x2 (+ IMAD, IMAD.HI lane moves)
+//      H  = max(M, E, F)                 VIMNMX3.S16x2
+//    substitution scores for both lanes come from ONE PRMT that indexes an 8-byte LUT; the selector is
+//    query seed + target seed (an IMAD) for plain pairs, a LOP3 for pairs holding an ambiguous base.
 //  * packed sequences (2-bit, or 4-bit when a pair holds an ambiguous base) sit in 16-byte aligned
-//    slots in the caller's order; each thread expands its own slot into shared memory once per pair.
+//    slots of the slab blob; each thread expands its query into selector seeds once per pair and
+//    reads its target 16 rows at a time.
+//  * bsw_key_kernel + cub radix sort bin the pairs by length on the device; extend_duo
+//    (bsw_pair2.cuh) is an evaluated alternative with two pairs per thread.
+// The BSW_* macros below are the A/B switches of the experiments recorded in DESIGN.md 5.6.
 #pragma once
 #include <stdint.h>
 #ifndef BSW_HIER_ARGMAX
@@ -343,7 +350,7 @@ __host__ __device__ inline int window_elems(int w) {
 // number of qs words (selector seeds of two groups = 4 columns each) for qlen query bases
 __host__ __device__ inline int sel_words(int qlen) { return (((qlen + 1) >> 1) + 1) >> 1; }
 
-// The DP of one pair over row storage R (already holding qs[] and tg[]).
+// The DP of one pair over row storage R (already holding the selector seeds qs[]; R.tb = packed target).
 //   FASTM : every score of the launch satisfies score * (match + 1) <= 32767, so the reference's
 //           M = Hd ? Hd + s : 0 is ONE instruction, min(Hd + s, Hd * (match + 1)) (the product on the
 //           FMA pipe): for Hd >= 1 the second term is >= Hd + match >= Hd + s, for Hd == 0 it caps M
