@@ -28,7 +28,7 @@ ERRORS = {1: "BSW_ERR_ARG", 2: "BSW_ERR_NO_DEVICE", 3: "BSW_ERR_CUDA", 4: "BSW_E
           5: "BSW_ERR_RANGE", 6: "BSW_ERR_STATE"}
 
 # every symbol include/bsw_gpu.h declares
-EXPORTS = ("bsw_gpu_init", "bsw_gpu_init_devices", "bsw_gpu_free", "bsw_gpu_batch", "bsw_gpu_batch_retry", "bsw_gpu_stage",
+EXPORTS = ("bsw_gpu_init", "bsw_gpu_init_devices", "bsw_gpu_free", "bsw_gpu_reserve", "bsw_gpu_batch", "bsw_gpu_batch_retry", "bsw_gpu_stage",
            "bsw_gpu_run_staged", "bsw_gpu_fetch_staged", "bsw_gpu_count_staged", "bsw_gpu_get_stats", "bsw_gpu_dpx_peak",
            "bsw_gpu_strerror", "bsw_gpu_last_error", "bsw_gpu_version")
 
@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         L.bsw_gpu_init_devices.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
         L.bsw_gpu_free.argtypes = [vp]
         L.bsw_gpu_free.restype = None
+        L.bsw_gpu_reserve.argtypes = [vp, i64, i64]
         L.bsw_gpu_batch.argtypes = [vp, vp, vp, vp, i64, i32]
         L.bsw_gpu_batch_retry.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
         L.bsw_gpu_stage.argtypes = [vp, vp, vp, vp, i64, i32]
@@ -118,6 +119,10 @@ class BswGpu:
         assert pairs.dtype == SEQPAIR_DTYPE and pairs.flags["C_CONTIGUOUS"]
         assert ref.dtype == np.uint8 and qer.dtype == np.uint8
         return pairs.ctypes.data, ref.ctypes.data, qer.ctypes.data
+
+    def reserve(self, n_pairs: int, total_bases: int) -> None:
+        """bsw_gpu_reserve: pre-sizes pinned rings / device arenas so the first batch() does not allocate."""
+        self._check(self._L.bsw_gpu_reserve(self._h, n_pairs, total_bases))
 
     def batch(self, pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int = DEFAULT_W,
               n: Optional[int] = None) -> None:

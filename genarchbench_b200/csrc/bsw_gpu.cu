@@ -863,6 +863,27 @@ int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out) {
     return BSW_OK;
 }
 
+int bsw_gpu_reserve(bsw_handle *h, int64_t n_pairs, int64_t total_bases) {
+    if (!h || n_pairs < 0 || total_bases < 0) return BSW_ERR_ARG;
+    if (n_pairs == 0) return BSW_OK;
+    // one ring slot holds a slab: at most slab_pairs(false) pairs and their share of the bases
+    const int64_t slab = std::min<int64_t>(n_pairs, slab_pairs(false));
+    const double share = (double)slab / (double)n_pairs;
+    const size_t blob = (size_t)(((double)total_bases * share / 4 + 20.0 * (double)slab) * 1.15) + 65536 +
+                        (size_t)omp_get_max_threads() * kArenaWords * 4;
+    const int64_t nslabs = (n_pairs + slab - 1) / slab;
+    for (size_t d = 0; d < h->devs.size(); ++d) {
+        Device &dev = h->devs[d];
+        CU(cudaSetDevice(dev.id));
+        int rc = ensure_aux(h, dev);
+        if (rc) return rc;
+        const int64_t mine = (nslabs + (int64_t)h->devs.size() - 1 - (int64_t)d) / (int64_t)h->devs.size();
+        for (int r = 0; r < kRing && r < mine; ++r)
+            if ((rc = ensure_slab(h, dev.ring[r], slab, blob))) return rc;
+    }
+    return BSW_OK;
+}
+
 int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
                   int64_t n, int32_t w) {
     if (!h || n < 0 || (n > 0 && (!pairs || !ref || !qer)) || w < 0) return BSW_ERR_ARG;

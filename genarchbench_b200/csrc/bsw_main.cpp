@@ -78,6 +78,11 @@ int main(int argc, char *argv[]) {
         fprintf(stderr, "bsw_gpu_init: %s\n", bsw_gpu_strerror(rc));
         return EXIT_FAILURE;
     }
+    {
+        int64_t bases = 0;
+        for (int64_t i = 0; i < numPairs; ++i) bases += (int64_t)pairs[(size_t)i].len1 + pairs[(size_t)i].len2;
+        bsw_gpu_reserve(h, numPairs, bases);
+    }
     // warm the context, streams and pinned rings outside the ROI (the reference constructs its
     // BandedPairWiseSW objects, 6 MiB of scratch each, before its ROI as well: main_banded.cpp:271-276)
     {

@@ -47,6 +47,13 @@ int bsw_gpu_init_devices(const bsw_params *params, int n_devices, const int *dev
 /* == BandedPairWiseSW::~BandedPairWiseSW (bandedSWA.cpp:100-103). */
 void bsw_gpu_free(bsw_handle *h);
 
+/* Optional: sizes the pinned staging rings and device arenas for calls of about n_pairs pairs holding
+ * total_bases bases (len1 + len2 summed), so that the first bsw_gpu_batch does not pay for the
+ * allocations (about 0.7 s for full-size slabs: page-locking host memory is slow). The reference
+ * allocates its scratch in the constructor as well (bandedSWA.cpp:70-97); here the sizes depend on the
+ * input, so it is a separate call. Buffers still grow on demand if a call needs more. */
+int bsw_gpu_reserve(bsw_handle *h, int64_t n_pairs, int64_t total_bases);
+
 /* == getScores16 (bandedSWA.cpp:2679-2703) over n pairs with band width w.
  * pairs[k].idr / .idq are byte offsets into ref / qer, .len1 / .len2 the lengths, .h0 the seed score.
  * Writes only score, tle, gtle, qle, gscore, max_off of pairs[0..n).

@@ -183,6 +183,17 @@ def test_out_of_domain_is_rejected(gpu):
     assert e.value.code == 5 and (b.pairs["score"] == -1).all()
 
 
+def test_reserve_presizes_the_rings():
+    b = pairio.generate(1, 300000, seed=2)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    with bsw.BswGpu() as g:
+        g.reserve(len(b), int(b.pairs["len1"].sum() + b.pairs["len2"].sum()))
+        g.batch(b.pairs, b.ref, b.qer, 100)
+        assert g.stats()["host_alloc_ms"] < 5.0               # nothing left to allocate in the call
+    assert_same_outputs(b.outputs(), a.outputs(), b, "after reserve")
+
+
 def test_staged_api_matches_batch(gpu):
     b = pairio.generate(1, 200000, seed=17)
     s = b.copy()
