@@ -30,7 +30,7 @@
 #pragma once
 #include <stdint.h>
 #ifndef BSW_HIER_ARGMAX
-#define BSW_HIER_ARGMAX 0
+#define BSW_HIER_ARGMAX 0      // experiment (8-group trips): one argmax event per trip + a post-row scan
 #endif
 #ifndef BSW_SEL_LOP3      // experiment: LOP3 selector for narrow pairs too
 #define BSW_SEL_LOP3 0
@@ -447,6 +447,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         int F = 0;                               // F(i, 2g), a plain int: the only serial chain of the row
         uint32_t rm = 0;                         // running max per lane (even / odd columns)
         int ilo = g0, ihi = g0;                  // last group where a lane reached rm
+        constexpr bool HIER = BSW_HIER_ARGMAX && NB >= 8;   // measured slower: DESIGN.md 5.6
         uint32_t h = 0, En = 0, Hst = 0;
 
         // One group = columns (2g, 2g+1). The scores, M, T and E' of different groups are independent;
@@ -579,12 +580,24 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                         R.HE4(k + e) = o;
                         if (e == NE - 1) { Hst = o.z; En = o.w; }
                     }
+                    if (HIER) {
+                        // one >= event per trip: the post-row scan finds the group inside it
+                        uint32_t tm = hv[0];
     #pragma unroll
-                    for (int u = 0; u < NB; ++u) {
+                        for (int u = 1; u + 1 < NB; u += 2) tm = __vimax3_s16x2(tm, hv[u], hv[u + 1]);
+                        if (!(NB & 1)) tm = __vmaxs2(tm, hv[NB - 1]);
                         bool phi, plo;
-                        rm = __vibmax_s16x2(hv[u], rm, &phi, &plo);
-                        if (plo) ilo = g + u;
-                        if (phi) ihi = g + u;
+                        rm = __vibmax_s16x2(tm, rm, &phi, &plo);
+                        if (plo) ilo = g + NB - 1;
+                        if (phi) ihi = g + NB - 1;
+                    } else {
+    #pragma unroll
+                        for (int u = 0; u < NB; ++u) {
+                            bool phi, plo;
+                            rm = __vibmax_s16x2(hv[u], rm, &phi, &plo);
+                            if (plo) ilo = g + u;
+                            if (phi) ihi = g + u;
+                        }
                     }
                     if (!BSW_PREFETCH && more) {
     #pragma unroll
@@ -631,29 +644,27 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         if (m == 0) break;
         // LAST column reaching m
         int mj;
-#if BSW_HIER_ARGMAX
-        // H(i, j) now sits in Hs[j + 1]; the lane's last >= event happened in the (at most four)
-        // groups ending at ilo / ihi, so the scan below stops within them.
-        // (the hi lane of the last group is column `end` when end is odd: never a candidate)
-        mj = -1;
-        if (mlo >= mhi) {
-            int gg = ilo;
+        if (HIER) {
+            // H(i, j) now sits in Hs[j + 1]; the lane's last >= event happened in the (at most NB)
+            // groups ending at ilo / ihi, so the scan below stops within them.
+            // (the hi lane of the last group is column `end` when end is odd: never a candidate)
+            mj = -1;
+            if (mlo >= mhi) {
+                int gg = ilo;
 #pragma unroll 1
-            for (int t = 0; t < 3 && R.getH16(2 * gg + 1) != (uint32_t)mlo; ++t) --gg;
-            mj = 2 * gg;
-        }
-        if (mhi >= mlo) {
-            int gg = min(ihi, (end - 2) >> 1);
+                for (int t = 0; t < NB - 1 && R.getH16(2 * gg + 1) != (uint32_t)mlo; ++t) --gg;
+                mj = 2 * gg;
+            }
+            if (mhi >= mlo) {
+                int gg = min(ihi, (end - 2) >> 1);
 #pragma unroll 1
-            for (int t = 0; t < 3 && R.getH16(2 * gg + 2) != (uint32_t)mhi; ++t) --gg;
-            mj = max(mj, 2 * gg + 1);
-        }
-#else
-        {
+                for (int t = 0; t < NB - 1 && R.getH16(2 * gg + 2) != (uint32_t)mhi; ++t) --gg;
+                mj = max(mj, 2 * gg + 1);
+            }
+        } else {
             const int jlo = 2 * ilo, jhi = 2 * ihi + 1;
             mj = mlo > mhi ? jlo : (mhi > mlo ? jhi : max(jlo, jhi));
         }
-#endif
         if (m > best) {
             best = m; best_i = i; best_j = mj;
             off = max(off, abs(mj - i));
