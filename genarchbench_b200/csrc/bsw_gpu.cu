@@ -50,7 +50,7 @@ inline int64_t slab_pairs(bool staged) {
 constexpr int64_t kSlabBases = 512ll << 20;    // bases per slab (upper bound)
 constexpr size_t kMaxSmem = 227 * 1024 - 64;   // opt-in shared memory per block on sm_100, minus the kernel's static bytes
 constexpr int kBinCols = 16;                   // query-length granularity of a launch bin
-constexpr int kVersion = 2;
+constexpr int kVersion = 3;
 // device sort key of a pair (64 bits), descending order = launch order:
 //   launch bin (len2 - 1) / 16 | holds an ambiguous base | (len2 - 1) % 16 | len1 (b1 bits) | h0 (b0 bits)
 // with b1, b0 sized per slab (bins merged into the windowed launch: 1 | wide | len2 - 1 on top instead);
@@ -105,6 +105,7 @@ struct Slab {
     int key_b1 = 15, key_b0 = 16, key_bits = 48;   // sort key layout of the current contents (see sort_key)
     int long_bin0 = 0x7FFFFFFF;                    // launch bins >= this one are merged (windowed rows)
     bool fastm = false;      // every score of the slab times (match+1) fits int16: one-instruction M
+    int max_sc = 0;          // largest h0 + len2 * match of the slab (bounds every H of its pairs)
     bool pinned = true;      // false for staged slabs (host side borrowed)
 };
 
@@ -121,6 +122,7 @@ struct Device {
     cudaEvent_t aux_ev[kAux] = {};
     cudaEvent_t fork_ev = nullptr;
     bool attr_set[8] = {false, false, false, false, false, false, false, false};
+    bool attr_set_key[2] = {false, false};
     bool attr_set_long[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_duo[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_win[8] = {false, false, false, false, false, false, false, false};
@@ -233,6 +235,11 @@ inline size_t smem_need(int row_el, int qs_words) {
 // BSW_WINDOW=0 sends every long pair to the warp-per-pair kernel (A/B against the windowed rows)
 inline bool use_window() {
     static const bool v = !(getenv("BSW_WINDOW") && getenv("BSW_WINDOW")[0] == '0');
+    return v;
+}
+// BSW_KEY=0: the short kernel's general argmax bookkeeping everywhere (A/B switch of extend_pair<.., KEY>)
+inline bool use_key() {
+    static const bool v = !(getenv("BSW_KEY") && getenv("BSW_KEY")[0] == '0');
     return v;
 }
 inline bool use_duo() {
@@ -406,6 +413,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     if (overflow) return kRetry;
     memset(blob + (size_t)total_words * 4, 0, 16);
     s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
+    s.max_sc = (int)std::min<int64_t>(maxsc, INT32_MAX);
     s.key_b1 = bits_for((uint32_t)maxt);
     s.key_b0 = bits_for((uint32_t)maxh);
     for (int t = 0; t < T; ++t) s.trivial.insert(s.trivial.end(), triv[(size_t)t].begin(), triv[(size_t)t].end());
@@ -543,6 +551,8 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
     static LongFn long_fn[8];
     static DuoFn duo_fn[8];
     static WinFn win_fn[8];
+    static const ShortFn short_key_fn[2] = {bsw_short_kernel<true, false, false, true>,
+                                            bsw_short_kernel<true, true, false, true>};
     static bool filled = false;
     if (!filled) { KernelTable<7>::fill(short_fn, long_fn, duo_fn, win_fn); filled = true; }
     int rc = ensure_aux(h, dev);
@@ -574,14 +584,22 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                     s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, h->K,
                     L.duo_el);
             } else if (L.smem) {
-                if (!dev.attr_set[ki]) {
-                    CU(cudaFuncSetAttribute(short_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-                    dev.attr_set[ki] = true;
+                // keyed row argmax when the launch's scores and group indices share 16 bits
+                // (a query of this launch has at most 4 * row_el - 1 bases: groups 0 .. 2 * row_el - 1)
+                const int kbits = bits_for((uint32_t)(2 * L.row_el - 1));
+                const bool keyed = s.fastm && !count && use_key() && kbits < 16 && s.max_sc < (1 << (16 - kbits));
+                ShortFn fn = keyed ? short_key_fn[h->sym ? 1 : 0] : short_fn[ki];
+                bool &attr = keyed ? dev.attr_set_key[h->sym ? 1 : 0] : dev.attr_set[ki];
+                if (!attr) {
+                    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                    attr = true;
                 }
+                KParams K = h->K;
+                if (keyed) { K.kbits = (uint32_t)kbits; K.kkey = 1u << kbits; }
                 cudaStream_t st = dev.aux[rr++ % kAux];
-                short_fn[ki]<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
-                                                                s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.row_el,
-                                                                L.qs_words);
+                fn<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
+                                                      s.d_out, L.n_wide, L.n - L.n_wide, K, L.row_el, L.qs_words);
+                if (keyed) h->stats.pairs_keyed += L.n;
             } else {
                 // one warp per pair; as many pairs per block as fit (at most 8)
                 const int q_hi = 4 * L.row_el - 4;     // row_el = (qlen + 4) >> 2 was sized from the bin's longest query
@@ -891,7 +909,7 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
     const int ng = (int)h->devs.size();
     bsw_gpu_stats &st = h->stats;
     st.pairs = n; st.kernel_launches = 0; st.h2d_bytes = 0; st.d2h_bytes = 0;
-    st.pairs_short = 0; st.pairs_long = 0;
+    st.pairs_short = 0; st.pairs_long = 0; st.pairs_keyed = 0;
     st.host_bin_ms = st.host_pack_ms = st.host_scatter_ms = st.kernel_ms = 0;
     st.host_sort_ms = st.host_plan_ms = st.host_alloc_ms = st.host_cut_ms = st.host_wait_ms = 0;
     h->K.w = w;
@@ -1016,7 +1034,7 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
     drop_staged(h);
     bsw_gpu_stats &st = h->stats;
     st.pairs = n; st.h2d_bytes = 0; st.d2h_bytes = 0; st.kernel_launches = 0;
-    st.pairs_short = st.pairs_long = 0;
+    st.pairs_short = st.pairs_long = st.pairs_keyed = 0;
     h->K.w = w;
     const int ng = (int)h->devs.size();
     std::vector<int64_t> cuts;
@@ -1044,7 +1062,7 @@ int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms) {
     if (h->staged_n < 0) return BSW_ERR_STATE;
     h->K.w = h->staged_w;
     h->stats.kernel_launches = 0;
-    h->stats.pairs_short = h->stats.pairs_long = 0;
+    h->stats.pairs_short = h->stats.pairs_long = h->stats.pairs_keyed = 0;
     // all slabs of one GPU run back to back on that GPU's first stream; GPUs run concurrently
     for (Device &dev : h->devs) {
         if (dev.staged.empty()) continue;

@@ -50,6 +50,9 @@
 #ifndef BSW_TAIL_NOUNROLL  // keep the single-group tail loop rolled (smaller code)
 #define BSW_TAIL_NOUNROLL 1
 #endif
+#ifndef BSW_HALF_TRIP      // a two-group step between the four-group trips and the single-group tail
+#define BSW_HALF_TRIP 1
+#endif
 #ifndef BSW_ST_SHARED     // 16-bit row stores through st.shared (short kernel only)
 #define BSW_ST_SHARED 0
 #endif
@@ -81,6 +84,8 @@ struct KParams {
     // below as IMAD / IMAD.HI on the FMA pipe instead of folding them into ALU-pipe shifts (the
     // ALU pipe is what bounds this kernel): k16 = 65536, km = match + 1, k1 = 1.
     uint32_t k16, km, k1;
+    // extend_pair<.., KEY>: row argmax by key = score << kbits | group (set per launch, 0 otherwise)
+    uint32_t kkey, kbits;
 };
 __host__ __device__ inline int max_score_of(int match, int mismatch, int ambig) {
     int mx = 0;
@@ -188,15 +193,17 @@ struct Rows {
     // c = 4 - code (narrow pairs, see score_lut) or the code itself (wide pairs). `traw` caches the packed
     // target word (16 rows of 2 bits, or 8 rows of 4 bits) and is refilled when it runs out: one LDG per
     // 16 / 8 rows and three ALU ops per row.
+    // tnext (initially tb[0]) holds the word after the current one (loaded a refill period ahead, so the global-load
+    // latency is off the row's critical path; it may be the word past the target: slots are padded).
     template <bool WIDE>
-    __device__ __forceinline__ uint32_t row_seed(int i, uint32_t &traw) const {
+    __device__ __forceinline__ uint32_t row_seed(int i, uint32_t &traw, uint32_t &tnext) const {
         uint32_t code;
         if (WIDE) {
-            if ((i & 7) == 0) traw = tb[i >> 3];
+            if ((i & 7) == 0) { traw = tnext; tnext = tb[(i >> 3) + 1]; }
             code = traw & 7u;
             traw >>= 4;
         } else {
-            if ((i & 15) == 0) traw = tb[i >> 4];
+            if ((i & 15) == 0) { traw = tnext; tnext = tb[(i >> 4) + 1]; }
             code = BSW_SEL_LOP3 ? (traw & 3u) : 4u - (traw & 3u);
             traw >>= 2;
         }
@@ -337,6 +344,8 @@ __device__ __forceinline__ int pair_band(const KParams &P, int qlen) {
     return band;
 }
 
+// bits needed to hold v (at least 1)
+__host__ __device__ inline int bits_for(uint32_t v) { int b = 1; while ((v >> b) != 0u) ++b; return b; }
 // number of he4 elements (4 columns each) a pair with qlen query bases needs: columns 0 .. qlen
 // (one spare so that the hi lane of the last group is always initialised), rounded up
 __host__ __device__ inline int row_elems(int qlen) { return (qlen + 4) >> 2; }
@@ -371,7 +380,11 @@ __host__ __device__ inline int sel_words(int qlen) { return (((qlen + 1) >> 1) +
 //   NB    : groups per trip of the inner loop, 4 or 8. Eight help the windowed launches, which run at one
 //           warp per scheduler and have nothing else to hide latency with (config 4: 81 -> 73 ms), and
 //           cost the whole-row launches 8 % (more registers, a longer single-group tail).
-template <bool FASTM, bool SYM, bool COUNT, bool WIDE, bool WIN = false, int NB = 4>
+//   KEY   : every score of the launch is < 2^(16 - kbits) and every group index < 2^kbits (P.kkey =
+//           1 << P.kbits): the row's "last column reaching the maximum" (bandedSWA.cpp:204-205) is then
+//           the unsigned lane maximum of score << kbits | group -- per trip four IMADs on the FMA pipe
+//           and three ALU-pipe maxima instead of 4 x (VIMNMX with predicates + 2 SEL + index add).
+template <bool FASTM, bool SYM, bool COUNT, bool WIDE, bool WIN = false, int NB = 4, bool KEY = false>
 __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int h0, const KParams &P) {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
     const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
@@ -402,10 +415,12 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
     const int band = pair_band(P, qlen);
     const int budget = min(qlen + band, tlen);
     const uint32_t K16 = P.k16, KM = P.km, K1 = P.k1;
+    static_assert(!KEY || (NB == 4 && !WIN && !COUNT), "keyed argmax: whole rows, 4-group trips");
+    const uint32_t KK = P.kkey;
 
     int best = h0, best_i = -1, best_j = -1, g_i = -1, gsc = -1, off = 0;
     int beg = 0, end = qlen;
-    uint32_t tword = 0;
+    uint32_t tword = 0, tnext = R.tb[0];
     int hcol = h0 - P.o_del;  // first column: H(i,-1) = max(h0 - o_del - e_del*(i+1), 0)
     int xbeg = 0;             // COUNT: the reference's exact beg (ours lags it by up to 3 columns)
     uint32_t cells = 0;
@@ -428,7 +443,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                 ++kinit;
             }
         }
-        const uint32_t tsel = R.template row_seed<WIDE>(i, tword);
+        const uint32_t tsel = R.template row_seed<WIDE>(i, tword, tnext);
 
         hcol -= P.e_del;
         const int hleft = beg == 0 ? max(hcol, 0) : 0;
@@ -529,11 +544,18 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                     R.HE4(k) = oa;
                     R.HE4(k + 1) = ob;
                     Hst = ob.z; En = E3;
-                    bool phi, plo;
-                    rm = __vibmax_s16x2(h0v, rm, &phi, &plo); mov_if<0>(ilo, plo, g, K1); mov_if<0>(ihi, phi, g, K1);
-                    rm = __vibmax_s16x2(h1v, rm, &phi, &plo); mov_if<1>(ilo, plo, g, K1); mov_if<1>(ihi, phi, g, K1);
-                    rm = __vibmax_s16x2(h2v, rm, &phi, &plo); mov_if<2>(ilo, plo, g, K1); mov_if<2>(ihi, phi, g, K1);
-                    rm = __vibmax_s16x2(h, rm, &phi, &plo);   mov_if<3>(ilo, plo, g, K1); mov_if<3>(ihi, phi, g, K1);
+                    if (KEY) {
+                        // the later group wins ties, as `h >= m` does in the reference
+                        const uint32_t t3 = __vimax3_u16x2(h0v * KK, h1v * KK + 0x00010001u, h2v * KK + 0x00020002u);
+                        const uint32_t t4 = __vmaxu2(t3, h * KK + 0x00030003u);
+                        rm = __viaddmax_u16x2(t4, (uint32_t)g * 0x00010001u, rm);
+                    } else {
+                        bool phi, plo;
+                        rm = __vibmax_s16x2(h0v, rm, &phi, &plo); mov_if<0>(ilo, plo, g, K1); mov_if<0>(ihi, phi, g, K1);
+                        rm = __vibmax_s16x2(h1v, rm, &phi, &plo); mov_if<1>(ilo, plo, g, K1); mov_if<1>(ihi, phi, g, K1);
+                        rm = __vibmax_s16x2(h2v, rm, &phi, &plo); mov_if<2>(ilo, plo, g, K1); mov_if<2>(ihi, phi, g, K1);
+                        rm = __vibmax_s16x2(h, rm, &phi, &plo);   mov_if<3>(ilo, plo, g, K1); mov_if<3>(ihi, phi, g, K1);
+                    }
                     if (!BSW_PREFETCH && more) {
                         na = R.HE4(k + 2); nb = R.HE4(k + 3);
                         nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
@@ -609,6 +631,35 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                 } while (more);
             }
         }
+#if BSW_HALF_TRIP
+        // whole elements (two groups) of what the trips left, so that at most one group goes through
+        // the (per group much dearer) single-group loop below
+#pragma unroll 1
+        for (; g + 1 <= g1; g += 2) {
+            const int k = g >> 1;
+            const uint4 a = R.HE4(k);
+            const uint32_t q01 = R.QS2(k);
+            const uint32_t s0 = (WIDE || BSW_SEL_LOP3) ? sel_combine(q01, tsel, 0x44444444u) : q01 * K1 + tsel;
+            const uint32_t s1 = __umulhi(s0, K16);
+            uint32_t M0, M1, T0, T1, E0, E1;
+            front(a.x, a.y, s0, M0, T0, E0);
+            front(a.z, a.w, s1, M1, T1, E1);
+            uint4 oa;
+            oa.x = back(a.y, M0, T0); const uint32_t h0v = h;
+            oa.z = back(a.w, M1, T1);
+            oa.y = E0; oa.w = E1;
+            R.HE4(k) = oa;
+            Hst = oa.z; En = E1;
+            if (KEY) {
+                const uint32_t t2 = __vmaxu2(h0v * KK, h * KK + 0x00010001u);
+                rm = __viaddmax_u16x2(t2, (uint32_t)g * 0x00010001u, rm);
+            } else {
+                bool phi, plo;
+                rm = __vibmax_s16x2(h0v, rm, &phi, &plo); if (plo) ilo = g; if (phi) ihi = g;
+                rm = __vibmax_s16x2(h, rm, &phi, &plo); if (plo) ilo = g + 1; if (phi) ihi = g + 1;
+            }
+        }
+#endif
 #if BSW_TAIL_NOUNROLL
 #pragma unroll 1
 #endif
@@ -621,10 +672,14 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             Hst = back(he0.y, M0, T0);
             En = E0;
             R.HE(g) = make_uint2(Hst, En);
-            bool phi, plo;
-            rm = __vibmax_s16x2(h, rm, &phi, &plo);
-            if (plo) ilo = g;
-            if (phi) ihi = g;
+            if (KEY) {
+                rm = __vmaxu2(rm, h * KK + (uint32_t)g * 0x00010001u);
+            } else {
+                bool phi, plo;
+                rm = __vibmax_s16x2(h, rm, &phi, &plo);
+                if (plo) ilo = g;
+                if (phi) ihi = g;
+            }
         }
 
         // last computed column's H, and the reference's eh[end] = { h1, 0 }
@@ -639,7 +694,14 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             if (!(gsc > hlast)) g_i = i;
             gsc = max(gsc, hlast);
         }
-        const int mlo = (int)(short)(rm & 0xFFFFu), mhi = (int)(short)(rm >> 16);
+        int mlo, mhi;
+        if (KEY) {
+            const uint32_t klo = rm & 0xFFFFu, khi = rm >> 16;
+            mlo = (int)(klo >> P.kbits); ilo = (int)(klo & (KK - 1u));
+            mhi = (int)(khi >> P.kbits); ihi = (int)(khi & (KK - 1u));
+        } else {
+            mlo = (int)(short)(rm & 0xFFFFu); mhi = (int)(short)(rm >> 16);
+        }
         const int m = max(mlo, mhi);
         if (m == 0) break;
         // LAST column reaching m
@@ -743,7 +805,7 @@ __device__ __forceinline__ void store_result(PairOut *out, uint32_t id, const Pa
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline int launch_threads(int n_wide, int n_narrow) { return ((n_wide + 31) & ~31) + n_narrow; }
 
-template <bool FASTM, bool SYM, bool COUNT>
+template <bool FASTM, bool SYM, bool COUNT, bool KEY = false>
 __global__ void __launch_bounds__(kBlockPairs)
 bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
                  const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
@@ -770,10 +832,10 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     if (wide) {
         src = blob + src[0];
         unpack_pair<true>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, true>(R, m.len2, m.len1, m.h0, P);
+        r = extend_pair<FASTM, SYM, COUNT, true, false, 4, KEY>(R, m.len2, m.len1, m.h0, P);
     } else {
         unpack_pair<false>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, false>(R, m.len2, m.len1, m.h0, P);
+        r = extend_pair<FASTM, SYM, COUNT, false, false, 4, KEY>(R, m.len2, m.len1, m.h0, P);
     }
     store_result(out, m.id, r);
 }
@@ -937,7 +999,7 @@ __device__ inline PairResult warp_extend_pair(Rows &R, const uint32_t *__restric
     const int budget = min(qlen + band, tlen);
     int best = h0, best_i = -1, best_j = -1, g_i = -1, gsc = -1, off = 0;
     int beg = 0, end = qlen;
-    uint32_t tword = 0;
+    uint32_t tword = 0, tnext = R.tb[0];
     int hcol = h0 - P.o_del;
     uint32_t cells = 0;
 
@@ -947,7 +1009,7 @@ __device__ inline PairResult warp_extend_pair(Rows &R, const uint32_t *__restric
         if (beg >= end) break;
         if (COUNT) cells += (uint32_t)(end - beg);   // beg is the reference's exact beg in this kernel
 
-        const uint32_t tsel = R.template row_seed<WIDE>(i, tword);
+        const uint32_t tsel = R.template row_seed<WIDE>(i, tword, tnext);
         hcol -= P.e_del;
         const int hleft = beg == 0 ? max(hcol, 0) : 0;
 
@@ -1179,7 +1241,6 @@ __host__ __device__ inline uint64_t sort_key(uint32_t len2, uint32_t len1, uint3
     const uint32_t top = (int)(v >> 4) >= long_bin0 ? (0x10000u | (wide << 15) | v) : (((v >> 4) << 5) | (wide << 4) | (v & 15u));
     return ((uint64_t)top << (b1 + b0)) | ((uint64_t)len1 << b0) | h0;
 }
-__host__ __device__ inline int bits_for(uint32_t v) { int b = 1; while ((v >> b) != 0u) ++b; return b; }
 #ifndef BSW_HOST_EMUL
 __global__ void bsw_key_kernel(const PairMeta *__restrict__ meta, int n, uint64_t *__restrict__ keys,
                                uint32_t *__restrict__ idx, int b1, int b0, int long_bin0) {

@@ -40,7 +40,7 @@ for _ in range(reps):
 if rng:
     rt.cudaDeviceSynchronize()
     rt.cudaProfilerStop()
-print(f"[{tag}] cfg {cfg} n {n}: best kernel {best:.3f} ms, {cells / best / 1e6:.1f} GCUPS, launches {g.stats()['kernel_launches']}", flush=True)
+print(f"[{tag}] cfg {cfg} n {n}: best kernel {best:.3f} ms, {cells / best / 1e6:.1f} GCUPS, launches {g.stats()['kernel_launches']}, keyed pairs {g.stats().get('pairs_keyed')}", flush=True)
 if os.environ.get("BSW_E2E"):
     try:
         roll = {l.split(":")[0]: l.split()[1] for l in open("/proc/self/smaps_rollup") if ":" in l and len(l.split()) > 1}

@@ -49,6 +49,14 @@ static inline uint32_t __viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c) {
     int h = std::min(emul::wrap16(emul::hi(a) + emul::hi(b)), (int)emul::hi(c));
     return emul::pk(l, h);
 }
+static inline uint32_t __vmaxu2(uint32_t a, uint32_t b) {
+    return std::max(a & 0xFFFFu, b & 0xFFFFu) | (std::max(a >> 16, b >> 16) << 16);
+}
+static inline uint32_t __vimax3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vmaxu2(__vmaxu2(a, b), c); }
+static inline uint32_t __viaddmax_u16x2(uint32_t a, uint32_t b, uint32_t c) {   // max(a + b, c), wrapping add
+    const uint32_t s = (((a & 0xFFFFu) + (b & 0xFFFFu)) & 0xFFFFu) | ((((a >> 16) + (b >> 16)) & 0xFFFFu) << 16);
+    return __vmaxu2(s, c);
+}
 static inline int __viaddmax_s32(int a, int b, int c) { return std::max((int)((uint32_t)a + (uint32_t)b), c); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline uint32_t __vimax3_s16x2(uint32_t a, uint32_t b, uint32_t c) {

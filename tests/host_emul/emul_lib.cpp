@@ -70,10 +70,12 @@ extern "C" int bsw_emul_batch_duo(const bsw_params *p, bsw_seqpair *pairs, const
     return 0;
 }
 
-extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
-                              const uint8_t *qer, int64_t n, int32_t w) {
-    KParams K{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w,
-              max_score_of(p->match, p->mismatch, p->ambig), 65536u, (uint32_t)(p->match + 1), 1u};
+// key = true: pairs whose scores and group indices fit the 16-bit key run extend_pair<.., KEY> (with the
+// tightest index width their own query allows, so the packing is exercised at its limits).
+static int emul_batch_impl(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
+                           const uint8_t *qer, int64_t n, int32_t w, bool key) {
+    const KParams K0{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w,
+                     max_score_of(p->match, p->mismatch, p->ambig), 65536u, (uint32_t)(p->match + 1), 1u, 0u, 0u};
     const bool sym = p->o_del == p->o_ins && p->e_del == p->e_ins;
 #pragma omp parallel
     {
@@ -101,17 +103,38 @@ extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uin
             else unpack_pair<false>(blob.data(), sp.len2, R);
             PairResult r;
             const bool m1 = (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767 && !getenv("BSW_EMUL_SLOWM");
+            KParams K = K0;
+            const int kbits = bits_for((uint32_t)(sp.len2 - 1) >> 1);
+            if (key && m1 && sp.h0 + sp.len2 * p->match < (1 << (16 - kbits))) {
+                K.kbits = (uint32_t)kbits; K.kkey = 1u << kbits;
+#define EK(S) (wide ? extend_pair<true, S, false, true, false, 4, true>(R, sp.len2, sp.len1, sp.h0, K) \
+               : extend_pair<true, S, false, false, false, 4, true>(R, sp.len2, sp.len1, sp.h0, K))
+                r = sym ? EK(true) : EK(false);
+#undef EK
+                r.cells = 0xFFFFFFFFu;
+            } else {
 #define EP(F, S) (wide ? extend_pair<F, S, true, true>(R, sp.len2, sp.len1, sp.h0, K) \
                   : extend_pair<F, S, true, false>(R, sp.len2, sp.len1, sp.h0, K))
-            if (m1) r = sym ? EP(true, true) : EP(true, false);
-            else r = sym ? EP(false, true) : EP(false, false);
+                if (m1) r = sym ? EP(true, true) : EP(true, false);
+                else r = sym ? EP(false, true) : EP(false, false);
 #undef EP
+            }
             sp.score = r.score; sp.qle = r.qle; sp.tle = r.tle; sp.gtle = r.gtle;
             sp.gscore = r.gscore; sp.max_off = r.max_off;
             sp.seqid = (int32_t)r.cells;   // test hook: cell count of the COUNT variant
         }
     }
     return 0;
+}
+
+extern "C" int bsw_emul_batch(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
+                              const uint8_t *qer, int64_t n, int32_t w) {
+    return emul_batch_impl(p, pairs, ref, qer, n, w, false);
+}
+// returns in seqid 0xFFFFFFFF (-1) for the pairs that took the keyed path
+extern "C" int bsw_emul_batch_key(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
+                                  const uint8_t *qer, int64_t n, int32_t w) {
+    return emul_batch_impl(p, pairs, ref, qer, n, w, true);
 }
 
 // Windowed rows (extend_pair<.., WIN>): every pair runs with the window a band of w needs.

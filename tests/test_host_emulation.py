@@ -26,9 +26,12 @@ def emul():
     L.bsw_emul_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
     L.bsw_emul_batch_duo.argtypes = L.bsw_emul_batch.argtypes
     L.bsw_emul_batch_win.argtypes = L.bsw_emul_batch.argtypes
+    L.bsw_emul_batch_key.argtypes = L.bsw_emul_batch.argtypes
 
-    def run(b, w=100, params=None, duo=False, win=False):
+    def run(b, w=100, params=None, duo=False, win=False, key=False):
         fn = L.bsw_emul_batch_duo if duo else (L.bsw_emul_batch_win if win else L.bsw_emul_batch)
+        if key:
+            fn = L.bsw_emul_batch_key
         fn(oracle._params_array(params), b.pairs.ctypes.data, b.ref.ctypes.data, b.qer.ctypes.data, len(b), w)
         return b.outputs()
     return run
@@ -58,6 +61,27 @@ def test_windowed_rows_match_oracle_on_long_queries(emul, w):
     cells = oracle.oracle_batch(a, w=w)
     assert_same_outputs(emul(b, w, win=True), a.outputs(), b, f"emulated windowed kernel vs oracle, w={w}")
     assert int(b.pairs["seqid"].astype(np.int64).sum()) == cells
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_keyed_argmax_matches_golden(emul, name):
+    """extend_pair<.., KEY>: the row's last argmax as the lane maximum of score << kbits | group."""
+    b, w, params, want = load_golden(name)
+    assert_same_outputs(emul(b, w, params, key=True), want, b, f"emulated keyed kernel vs golden[{name}]")
+
+
+@pytest.mark.parametrize("w", [1, 5, 17, 100])
+def test_keyed_argmax_matches_oracle(emul, w):
+    """Scores and group indices right up to the limits of the 16-bit key (each pair runs with the
+    narrowest index field its query allows), ties between lanes and groups, unrelated pairs."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 260, 0, 400, 0.3, 0.2
+    b = pairio.generate(c, 8000, seed=900 + w)
+    a = b.copy()
+    oracle.oracle_batch(a, w=w)
+    assert_same_outputs(emul(b, w, key=True), a.outputs(), b, f"emulated keyed kernel vs oracle, w={w}")
+    keyed = int((b.pairs["seqid"] == -1).sum())
+    assert 0.3 * len(b) < keyed < len(b), keyed      # both the keyed and the general path were exercised
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
