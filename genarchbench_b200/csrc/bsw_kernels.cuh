@@ -50,11 +50,20 @@
 #ifndef BSW_TAIL_NOUNROLL  // keep the single-group tail loop rolled (smaller code)
 #define BSW_TAIL_NOUNROLL 1
 #endif
+#ifndef BSW_SHORT_GROUPS  // groups per inner-loop trip of the whole-row thread-per-pair kernel
+#define BSW_SHORT_GROUPS 4
+#endif
+#ifndef BSW_PIN_CONSTS    // keep the lane-move multipliers in registers across the row loop
+#define BSW_PIN_CONSTS 1
+#endif
+#ifndef BSW_PINGPONG      // two copies of the four-group trip alternate between two register sets
+#define BSW_PINGPONG 1
+#endif
 #ifndef BSW_HALF_TRIP      // a two-group step between the four-group trips and the single-group tail
 #define BSW_HALF_TRIP 1
 #endif
-#ifndef BSW_ST_SHARED     // 16-bit row stores through st.shared (short kernel only)
-#define BSW_ST_SHARED 0
+#ifndef BSW_ST_SHARED     // 16-bit row stores through st.shared (32-bit addresses) instead of generic stores
+#define BSW_ST_SHARED 1
 #endif
 #ifdef BSW_HOST_EMUL
 // tests/host_emul compiles the per-pair code below with g++ against an emulation of the few CUDA
@@ -69,8 +78,8 @@ namespace bswk {
 #ifndef BSW_NT            // threads per block == pairs per block of the thread-per-pair kernel
 #define BSW_NT 128
 #endif
-#ifndef BSW_HST_PRMT      // experiment: shifted H store through one PRMT instead of IMAD.HI + IMAD
-#define BSW_HST_PRMT 0
+#ifndef BSW_HST_PRMT      // shifted H store through one PRMT (ALU pipe) instead of IMAD.HI + IMAD (FMA pipe)
+#define BSW_HST_PRMT 1
 #endif
 constexpr int kBlockPairs = BSW_NT;
 
@@ -384,6 +393,9 @@ __host__ __device__ inline int sel_words(int qlen) { return (((qlen + 1) >> 1) +
 //           1 << P.kbits): the row's "last column reaching the maximum" (bandedSWA.cpp:204-205) is then
 //           the unsigned lane maximum of score << kbits | group -- per trip four IMADs on the FMA pipe
 //           and three ALU-pipe maxima instead of 4 x (VIMNMX with predicates + 2 SEL + index add).
+#ifndef BSW_HOST_EMUL
+__device__ uint32_t g_zero = 0;   // see BSW_PIN_CONSTS
+#endif
 template <bool FASTM, bool SYM, bool COUNT, bool WIDE, bool WIN = false, int NB = 4, bool KEY = false>
 __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int h0, const KParams &P) {
     const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
@@ -414,9 +426,16 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
 
     const int band = pair_band(P, qlen);
     const int budget = min(qlen + band, tlen);
-    const uint32_t K16 = P.k16, KM = P.km, K1 = P.k1;
-    static_assert(!KEY || (NB == 4 && !WIN && !COUNT), "keyed argmax: whole rows, 4-group trips");
-    const uint32_t KK = P.kkey;
+    static_assert(!KEY || (!WIN && !COUNT), "keyed argmax: whole rows only");
+    uint32_t K16 = P.k16, KM = P.km, K1 = P.k1, KK = P.kkey;
+#if !defined(BSW_HOST_EMUL) && BSW_PIN_CONSTS
+    // made opaque by a run-time zero from global memory: ptxas otherwise re-loads all four from the
+    // parameter bank inside every trip (three LDC per trip)
+    {
+        const uint32_t z = *reinterpret_cast<const volatile uint32_t *>(&g_zero);
+        K16 ^= z; KM ^= z; K1 ^= z; KK ^= z;
+    }
+#endif
 
     int best = h0, best_i = -1, best_j = -1, g_i = -1, gsc = -1, off = 0;
     int beg = 0, end = qlen;
@@ -509,14 +528,13 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         int g = g0;
         if (NB == 4) {
             if (g + 3 <= g1) {
-                uint4 a = R.HE4(g >> 1), b = R.HE4((g >> 1) + 1);
-                uint32_t q01 = R.QS2(g >> 1), q23 = R.QS2((g >> 1) + 1);
-                bool more;
-                do {
+                // one trip over the elements (a, b); the next trip's elements are loaded into (na, nb)
+                // before the arithmetic. Two copies alternate between two register sets (BSW_PINGPONG), so
+                // no moves rotate the prefetched values.
+                auto trip = [&](const uint4 &a, const uint4 &b, const uint32_t q01, const uint32_t q23, uint4 &na,
+                                uint4 &nb, uint32_t &nq01, uint32_t &nq23) -> bool {
                     const int k = g >> 1;
-                    more = g + 7 <= g1;
-                    uint4 na = a, nb = b;
-                    uint32_t nq01 = q01, nq23 = q23;
+                    const bool more = g + 7 <= g1;
                     if (BSW_PREFETCH && more) {
                         na = R.HE4(k + 2); nb = R.HE4(k + 3);
                         nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
@@ -560,9 +578,27 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                         na = R.HE4(k + 2); nb = R.HE4(k + 3);
                         nq01 = R.QS2(k + 2); nq23 = R.QS2(k + 3);
                     }
-                    a = na; b = nb; q01 = nq01; q23 = nq23;
                     g += 4;
+                    return more;
+                };
+                uint4 a0 = R.HE4(g >> 1), b0 = R.HE4((g >> 1) + 1);
+                uint32_t q0 = R.QS2(g >> 1), r0 = R.QS2((g >> 1) + 1);
+#if BSW_PINGPONG
+                uint4 a1, b1;           // written by the first trip before the second reads them
+                uint32_t q1, r1;
+                for (;;) {
+                    if (!trip(a0, b0, q0, r0, a1, b1, q1, r1)) break;
+                    if (!trip(a1, b1, q1, r1, a0, b0, q0, r0)) break;
+                }
+#else
+                bool more;
+                do {
+                    uint4 na = a0, nb = b0;
+                    uint32_t nq = q0, nr = r0;
+                    more = trip(a0, b0, q0, r0, na, nb, nq, nr);
+                    a0 = na; b0 = nb; q0 = nq; r0 = nr;
                 } while (more);
+#endif
             }
         } else {
             // NB groups (NB / 2 elements) per trip
@@ -602,7 +638,15 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                         R.HE4(k + e) = o;
                         if (e == NE - 1) { Hst = o.z; En = o.w; }
                     }
-                    if (HIER) {
+                    if (KEY) {
+                        uint32_t t = hv[0] * KK;
+    #pragma unroll
+                        for (int u = 1; u + 1 < NB; u += 2)
+                            t = __vimax3_u16x2(t, hv[u] * KK + (uint32_t)u * 0x00010001u,
+                                               hv[u + 1] * KK + (uint32_t)(u + 1) * 0x00010001u);
+                        if (!(NB & 1)) t = __vmaxu2(t, hv[NB - 1] * KK + (uint32_t)(NB - 1) * 0x00010001u);
+                        rm = __viaddmax_u16x2(t, (uint32_t)g * 0x00010001u, rm);
+                    } else if (HIER) {
                         // one >= event per trip: the post-row scan finds the group inside it
                         uint32_t tm = hv[0];
     #pragma unroll
@@ -682,6 +726,10 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             }
         }
 
+        // first element of the row for the leading trim below, loaded here so that its latency hides behind
+        // the row decisions (the store of entry `end` that follows is why the trim then skips an element
+        // holding that entry)
+        const uint4 ztrim = R.HE4(g0 >> 1);
         // last computed column's H, and the reference's eh[end] = { h1, 0 }
         int hlast;
         if (end & 1) {
@@ -743,8 +791,8 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         }
         // leading trim (not semantic: skipped cells are all-zero; done lazily, four columns at a time)
         if ((i & (BSW_TRIM_EVERY - 1)) == BSW_TRIM_EVERY - 1) {
-            const uint4 z = R.HE4(g0 >> 1);
-            if ((z.x | z.y | z.z | z.w) == 0u && 2 * g0 + 4 > beg) beg = 2 * g0 + 4;
+            const uint4 z = ztrim;
+            if ((z.x | z.y | z.z | z.w) == 0u && 2 * g0 + 4 > beg && 2 * g0 + 4 <= end) beg = 2 * g0 + 4;
         }
         // trailing trim (semantic): j* = last j in [beg,end] with Hs[j] | E[j] != 0 (m > 0
         // guarantees one exists); the new end is min(j* + 2, qlen). Hs[end] = H(i,end-1) is almost
@@ -832,10 +880,10 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     if (wide) {
         src = blob + src[0];
         unpack_pair<true>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, true, false, 4, KEY>(R, m.len2, m.len1, m.h0, P);
+        r = extend_pair<FASTM, SYM, COUNT, true, false, BSW_SHORT_GROUPS, KEY>(R, m.len2, m.len1, m.h0, P);
     } else {
         unpack_pair<false>(src, m.len2, R);
-        r = extend_pair<FASTM, SYM, COUNT, false, false, 4, KEY>(R, m.len2, m.len1, m.h0, P);
+        r = extend_pair<FASTM, SYM, COUNT, false, false, BSW_SHORT_GROUPS, KEY>(R, m.len2, m.len1, m.h0, P);
     }
     store_result(out, m.id, r);
 }
