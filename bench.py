@@ -295,7 +295,7 @@ def main():
     peaks = measured_peaks()
     achieved_instr = cells / (dev_ms / args.steps * 1e-3) * INSTR_PER_CELL / 1e9   # this rank's GPU
     roofline = {
-        "bound": "dpx_int", "kernel": "bsw_short_kernel<1,1,0> (thread-per-pair, s16x2 DPX; > 93 % of the step)",
+        "bound": "dpx_int", "kernel": "bsw_short_kernel<1,1,0,1> (thread-per-pair, s16x2 DPX, keyed row argmax; > 93 % of the step)",
         "achieved": achieved_instr, "peak": dpx_peak, "unit": "Ginstr/s (packed s16x2 thread-instructions)",
         "frac": achieved_instr / dpx_peak, "instr_per_cell": INSTR_PER_CELL,
         "peak_source": "measured live: VIADDMNMX.S16x2.RELU issue rate, all SMs (bsw_gpu_dpx_peak)",

@@ -1165,9 +1165,9 @@ int bsw_gpu_dpx_peak(int device, int which, double *ginstr_per_s, double *sm_mhz
         case 9: {   // one inner-loop trip on registers: result in giga CELLS per second
             cudaEvent_t a, b;
             cudaEventCreate(&a); cudaEventCreate(&b);
-            bsw_trip_peak_kernel<<<blocks, threads>>>(sink, 16, 3u, 65536u, 2u, 1u);
+            bsw_trip_peak_kernel<<<blocks, threads>>>(sink, 16, 3u, 65536u, 2u, 1u, 128u);
             cudaEventRecord(a);
-            bsw_trip_peak_kernel<<<blocks, threads>>>(sink, iters * 4, 3u, 65536u, 2u, 1u);
+            bsw_trip_peak_kernel<<<blocks, threads>>>(sink, iters * 4, 3u, 65536u, 2u, 1u, 128u);
             cudaEventRecord(b);
             rc = cudaEventSynchronize(b) == cudaSuccess ? 0 : 1;
             cudaEventElapsedTime(&ms, a, b);

@@ -1006,7 +1006,13 @@ __device__ inline PairResult warp_extend_pair(Rows &R, const uint32_t *__restric
     const int dec = 4 * P.e_ins;    // F decay across one lane (4 columns)
     uint32_t LUT_LO, LUT_HI;
     score_lut<WIDE>(P, LUT_LO, LUT_HI);
-    const uint32_t K16 = P.k16, KM = P.km, K1 = P.k1;
+    uint32_t K16 = P.k16, KM = P.km, K1 = P.k1;
+#if !defined(BSW_HOST_EMUL) && BSW_PIN_CONSTS
+    {   // as in extend_pair: keeps ptxas from re-loading them from the parameter bank inside the loops
+        const uint32_t z = *reinterpret_cast<const volatile uint32_t *>(&g_zero);
+        K16 ^= z; KM ^= z; K1 ^= z;
+    }
+#endif
 
     // ---- query selector seeds and row "-1" (bandedSWA.cpp:159-161), all lanes
     {
@@ -1335,18 +1341,22 @@ __global__ void dpx_peak_kernel(uint32_t *sink, int iters, uint32_t seed) {
     if (acc == 0x12345678u) sink[threadIdx.x] = acc;  // keep the chains alive
 }
 
-// WHICH == 9 of bsw_gpu_dpx_peak: the arithmetic of one inner-loop trip of extend_pair (four groups =
-// eight cells: selector, PRMT, M, T, E', the F scan, H, shifted store word, row max + argmax) on
+// WHICH == 9 of bsw_gpu_dpx_peak: the arithmetic of one inner-loop trip of extend_pair<.., KEY> (four
+// groups = eight cells: selector, PRMT, M, T, E', the F scan, H, shifted store word, keyed row max) on
 // registers only -- no shared memory, no row bookkeeping, no divergence. Its rate is the ceiling the
 // thread-per-pair kernel could reach if everything but the recurrence were free.
-__global__ void bsw_trip_peak_kernel(uint32_t *sink, int iters, uint32_t seed, uint32_t k16, uint32_t km, uint32_t k1) {
+__global__ void bsw_trip_peak_kernel(uint32_t *sink, int iters, uint32_t seed, uint32_t k16, uint32_t km, uint32_t k1,
+                                     uint32_t kk) {
     uint32_t hd[4], ev[4], q[2];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { hd[k] = (seed * (k + 3) + threadIdx.x) & 0x00FF00FFu; ev[k] = (seed * (k + 7)) & 0x003F003Fu; }
     q[0] = 0x11002233u & (seed | 0x33333333u); q[1] = 0x22113300u;
     const uint32_t LUT_LO = 0xFCFCFCFCu, LUT_HI = 0xFCFCFC01u, NEG_OE = pack2(-7), NEG_E = pack2(-1);
     uint32_t rm = 0, A = 0, hprev = 0, tsel = 0x94949494u;
-    int ilo = 0, ihi = 0;
+    {   // as in extend_pair (BSW_PIN_CONSTS)
+        const uint32_t z = *reinterpret_cast<const volatile uint32_t *>(&g_zero);
+        k16 ^= z; km ^= z; k1 ^= z; kk ^= z;
+    }
     for (int it = 0; it < iters; ++it) {
         uint32_t M[4], T[4], E[4], hv[4];
 #pragma unroll
@@ -1368,21 +1378,17 @@ __global__ void bsw_trip_peak_kernel(uint32_t *sink, int iters, uint32_t seed, u
             const uint32_t h = __vimax3_s16x2(M[g], ev[g], B);
             const uint32_t W2 = __viaddmax_s16x2(B, NEG_E, T[g]);
             A = __umulhi(W2, k16);
-            hd[g] = __umulhi(hprev, k16) + h * k16;   // next "row" reads what this one stored
+            hd[g] = __byte_perm(hprev, h, 0x5432);   // next "row" reads what this one stored
             hprev = h;
             hv[g] = h;
             ev[g] = E[g];
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            bool phi, plo;
-            rm = __vibmax_s16x2(hv[g], rm, &phi, &plo);
-            if (plo) ilo = it + g;
-            if (phi) ihi = it + g;
-        }
+        const uint32_t t3 = __vimax3_u16x2(hv[0] * kk, hv[1] * kk + 0x00010001u, hv[2] * kk + 0x00020002u);
+        const uint32_t t4 = __vmaxu2(t3, hv[3] * kk + 0x00030003u);
+        rm = __viaddmax_u16x2(t4, (uint32_t)it * 0x00010001u, rm);
         tsel += 0x01010101u & (uint32_t)it;
     }
-    if ((rm ^ A ^ (uint32_t)ilo ^ (uint32_t)ihi) == 0x12345678u) sink[threadIdx.x] = rm;
+    if ((rm ^ A) == 0x12345678u) sink[threadIdx.x] = rm;
 }
 
 #endif  // !BSW_HOST_EMUL
