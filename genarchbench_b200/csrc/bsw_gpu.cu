@@ -430,14 +430,20 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     if (s.n_dev > 0) {
         const int nbins = maxq / kBinCols + 1;
         const int nk = window_elems(h->K.w);
-        const size_t ws = (size_t)20 * nk * kBlockPairs;
-        const bool can_window = ws <= kMaxSmem && use_window();
+        const size_t ws = (size_t)20 * nk * kWinBlockPairs;
+        // (bands whose window would leave fewer than four warps on an SM go to the warp-per-pair kernel)
+        const bool can_window = (size_t)20 * nk * 128 <= kMaxSmem && use_window();
         auto bin_smem = [&](int b) {
             const int q_hi = std::min(maxq, (b + 1) * kBinCols);
             return use_duo() ? (size_t)duo_thread_bytes(q_hi) * kDuoThreads : smem_need(row_elems(q_hi), sel_words(q_hi));
         };
+        // windowed rows from the first bin whose whole rows do not fit (BSW_WINDOW_EARLY=1, experiment: from
+        // the first bin whose whole rows need more shared memory per pair than the window -- config 2
+        // 37.4 ms against 34.6 ms, config 4 38.0 against 38.7)
+        static const bool early = getenv("BSW_WINDOW_EARLY") && getenv("BSW_WINDOW_EARLY")[0] == '1';
         if (can_window)
-            for (int b = 0; b < nbins; ++b) if (bin_smem(b) > kMaxSmem) { s.long_bin0 = b; break; }
+            for (int b = 0; b < nbins; ++b)
+                if (bin_smem(b) > (early ? (size_t)20 * nk * kBlockPairs : kMaxSmem)) { s.long_bin0 = b; break; }
         int p = 0;
         int nw_long = 0, nn_long = 0;
         for (int b = nbins - 1; b >= 0; --b) {
@@ -566,12 +572,13 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
             const int grid = (launch_threads(L.n_wide, L.n - L.n_wide) + kBlockPairs - 1) / kBlockPairs;
             const int ki = kernel_index(s.fastm, h->sym, count);
             if (L.win_nk) {
+                const int wgrid = (launch_threads(L.n_wide, L.n - L.n_wide) + kWinBlockPairs - 1) / kWinBlockPairs;
                 if (!dev.attr_set_win[ki]) {
                     CU(cudaFuncSetAttribute(win_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
                     dev.attr_set_win[ki] = true;
                 }
                 cudaStream_t st = dev.aux[rr++ % kAux];
-                win_fn[ki]<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
+                win_fn[ki]<<<wgrid, kWinBlockPairs, L.smem, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
                                                               s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.win_nk);
             } else if (L.smem && use_duo()) {
                 if (!dev.attr_set_duo[ki]) {

@@ -53,6 +53,9 @@
 #ifndef BSW_SHORT_GROUPS  // groups per inner-loop trip of the whole-row thread-per-pair kernel
 #define BSW_SHORT_GROUPS 4
 #endif
+#ifndef BSW_PINGPONG_WIDE_TRIPS  // the same for trips of more than four groups: config 4 44.9 ms vs 41.5 ms (110 registers)
+#define BSW_PINGPONG_WIDE_TRIPS 0
+#endif
 #ifndef BSW_PIN_CONSTS    // keep the lane-move multipliers in registers across the row loop
 #define BSW_PIN_CONSTS 1
 #endif
@@ -82,6 +85,10 @@ namespace bswk {
 #define BSW_HST_PRMT 1
 #endif
 constexpr int kBlockPairs = BSW_NT;
+#ifndef BSW_WIN_NT        // threads per block of the windowed-rows kernel: its blocks are shared-memory bound, and
+#define BSW_WIN_NT 32     // 41 KB blocks of one warp pack five warps on an SM where a 164 KB block packs four
+#endif
+constexpr int kWinBlockPairs = BSW_WIN_NT;
 
 struct KParams {
     int o_del, e_del, o_ins, e_ins, zdrop, end_bonus, match, mismatch, ambig, w;
@@ -604,18 +611,10 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             // NB groups (NB / 2 elements) per trip
             constexpr int NE = NB / 2;
             if (g + NB - 1 <= g1) {
-                uint4 cur[NE];
-                uint32_t cq[NE];
-    #pragma unroll
-                for (int e = 0; e < NE; ++e) { cur[e] = R.HE4((g >> 1) + e); cq[e] = R.QS2((g >> 1) + e); }
-                bool more;
-                do {
+                auto trip = [&](const uint4 (&cur)[NE], const uint32_t (&cq)[NE], uint4 (&nxt)[NE],
+                                uint32_t (&nq)[NE]) -> bool {
                     const int k = g >> 1;
-                    more = g + 2 * NB - 1 <= g1;
-                    uint4 nxt[NE];
-                    uint32_t nq[NE];
-    #pragma unroll
-                    for (int e = 0; e < NE; ++e) { nxt[e] = cur[e]; nq[e] = cq[e]; }
+                    const bool more = g + 2 * NB - 1 <= g1;
                     if (BSW_PREFETCH && more) {
     #pragma unroll
                         for (int e = 0; e < NE; ++e) { nxt[e] = R.HE4(k + NE + e); nq[e] = R.QS2(k + NE + e); }
@@ -669,10 +668,32 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
     #pragma unroll
                         for (int e = 0; e < NE; ++e) { nxt[e] = R.HE4(k + NE + e); nq[e] = R.QS2(k + NE + e); }
                     }
-    #pragma unroll
-                    for (int e = 0; e < NE; ++e) { cur[e] = nxt[e]; cq[e] = nq[e]; }
                     g += NB;
+                    return more;
+                };
+                uint4 c0[NE];
+                uint32_t d0[NE];
+    #pragma unroll
+                for (int e = 0; e < NE; ++e) { c0[e] = R.HE4((g >> 1) + e); d0[e] = R.QS2((g >> 1) + e); }
+#if BSW_PINGPONG_WIDE_TRIPS
+                uint4 c1[NE];
+                uint32_t d1[NE];
+                for (;;) {
+                    if (!trip(c0, d0, c1, d1)) break;
+                    if (!trip(c1, d1, c0, d0)) break;
+                }
+#else
+                bool more;
+                do {
+                    uint4 nxt[NE];
+                    uint32_t nq[NE];
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) { nxt[e] = c0[e]; nq[e] = d0[e]; }
+                    more = trip(c0, d0, nxt, nq);
+    #pragma unroll
+                    for (int e = 0; e < NE; ++e) { c0[e] = nxt[e]; d0[e] = nq[e]; }
                 } while (more);
+#endif
             }
         }
 #if BSW_HALF_TRIP
@@ -890,16 +911,16 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
 
 // ---------------------------------------------------------------------------------------------
 // Long queries under a narrow band: the same thread-per-pair code over WINDOWED rows (extend_pair<.., WIN>).
-// Launch as bsw_short_kernel, dynamic smem = 20 * nk * kBlockPairs with nk = window elements (a power of
+// Launch as bsw_short_kernel but with kWinBlockPairs threads, dynamic smem = 20 * nk * kWinBlockPairs with nk = window elements (a power of
 // two, 4 * nk >= 2 * w + 16).
 // ---------------------------------------------------------------------------------------------
 template <bool FASTM, bool SYM, bool COUNT>
-__global__ void __launch_bounds__(kBlockPairs)
+__global__ void __launch_bounds__(kWinBlockPairs)
 bsw_win_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
                const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
                KParams P, int nk) {
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int NT = kBlockPairs;
+    constexpr int NT = kWinBlockPairs;
     const int tid = threadIdx.x;
     const int t = blockIdx.x * NT + tid;
     const int nwr = (n_wide + 31) & ~31;

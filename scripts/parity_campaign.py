@@ -21,6 +21,10 @@ scorings = [dict(o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=100, end_bonus=5, mat
 for i, sc in enumerate(scorings[1:]):
     for w in (7, 100, 300):
         cases.append((f"scoring {i + 1} w={w}", 4, 100_000, w, sc, dict(len2_min=1, len2_max=900, h0_min=0, h0_max=200, n_frac=0.2, random_frac=0.1)))
+# keyed row argmax at the limits of its 16-bit key: queries <= 60 bases (5 index bits, scores < 2048)
+cases.append(("keyed limit below", 4, 200_000, 100, None, dict(len2_min=1, len2_max=60, h0_min=0, h0_max=1985, n_frac=0.2, random_frac=0.1)))
+cases.append(("keyed limit above", 4, 200_000, 100, None, dict(len2_min=1, len2_max=60, h0_min=0, h0_max=1995, n_frac=0.2, random_frac=0.1)))
+cases.append(("keyed 7-bit index", 4, 200_000, 30, None, dict(len2_min=100, len2_max=250, h0_min=0, h0_max=260, n_frac=0.2, random_frac=0.1)))
 cases.append(("large h0", 4, 100_000, 100, None, dict(len2_min=10, len2_max=800, h0_min=15000, h0_max=31000, n_frac=0.1)))
 
 total = bad_total = 0
@@ -37,6 +41,6 @@ for name, cfg, n, w, sc, over in cases:
         st = g.stats()
     bad = int((a.outputs() != b.outputs()).any(axis=1).sum())
     total += n; bad_total += bad
-    print(f"{name:28s} n={n:8d} short={st['pairs_short']:8d} long={st['pairs_long']:7d} mismatches={bad}", flush=True)
+    print(f"{name:28s} n={n:8d} short={st['pairs_short']:8d} long={st['pairs_long']:7d} keyed={st['pairs_keyed']:8d} mismatches={bad}", flush=True)
 print(f"TOTAL {total} pairs, {bad_total} mismatches, {time.time() - t00:.0f} s")
 sys.exit(1 if bad_total else 0)
