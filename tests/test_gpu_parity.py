@@ -98,6 +98,28 @@ def test_large_seed_scores_take_the_general_m_path(gpu):
         assert_same_outputs(e.outputs(), a.outputs(), e, f"large h0, w={w}")
 
 
+@pytest.mark.parametrize("h0_max,all_keyed", [(1985, True), (1995, False), (40000, False)])
+def test_keyed_argmax_at_the_limits_of_its_key(gpu, h0_max, all_keyed):
+    """extend_pair<.., KEY>: launches whose scores and group indices share 16 bits take the row argmax as
+    one unsigned lane maximum of score << kbits | group. Queries <= 60 bases need 5 index bits, so scores up
+    to 2047 are keyed: h0 <= 1985 keeps every launch below, h0 <= 1995 pushes the longest bin above (general
+    argmax for that launch only), a huge h0 turns the keyed path off altogether."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 60, 0, min(h0_max, 30000), 0.2, 0.1
+    b = pairio.generate(c, 40000, seed=77)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    gpu.batch(b.pairs, b.ref, b.qer, 100)
+    assert_same_outputs(b.outputs(), a.outputs(), b, f"keyed argmax, h0 <= {h0_max}")
+    st = gpu.stats()
+    if all_keyed:
+        assert st["pairs_keyed"] == st["pairs_short"] > 0
+    elif h0_max < 30000:
+        assert 0 < st["pairs_keyed"] < st["pairs_short"]
+    else:
+        assert st["pairs_keyed"] == 0
+
+
 def test_huge_band_argument(gpu):
     """w far beyond any sequence length (the per-pair band clamps it, bandedSWA.cpp:2898-2919)."""
     c = pairio.preset(4)
