@@ -593,7 +593,9 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
             } else if (L.smem) {
                 // keyed row argmax when the launch's scores and group indices share 16 bits
                 // (a query of this launch has at most 4 * row_el - 1 bases: groups 0 .. 2 * row_el - 1)
-                const int kbits = bits_for((uint32_t)(2 * L.row_el - 1));
+                // and a row never spans more than band + 2 <= w + 2 groups (beg >= i - band, end <= i + band + 1,
+                // the first group rounded down to a 4-column boundary)
+                const int kbits = bits_for((uint32_t)std::min<int64_t>(2 * L.row_el - 1, BSW_KEY_REL ? (int64_t)h->K.w + 2 : INT32_MAX));
                 const bool keyed = s.fastm && !count && use_key() && kbits < 16 && s.max_sc < (1 << (16 - kbits));
                 ShortFn fn = keyed ? short_key_fn[h->sym ? 1 : 0] : short_fn[ki];
                 bool &attr = keyed ? dev.attr_set_key[h->sym ? 1 : 0] : dev.attr_set[ki];

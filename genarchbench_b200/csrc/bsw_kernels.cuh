@@ -53,6 +53,9 @@
 #ifndef BSW_SHORT_GROUPS  // groups per inner-loop trip of the whole-row thread-per-pair kernel
 #define BSW_SHORT_GROUPS 4
 #endif
+#ifndef BSW_KEY_REL        // keyed argmax: index field relative to the row's first group (would also key config 2's
+#define BSW_KEY_REL 0      // 250-300-base queries: 34.44 vs 34.49 ms there, 7.22 vs 7.16 ms on config 3 -- off)
+#endif
 #ifndef BSW_PINGPONG_WIDE_TRIPS  // the same for trips of more than four groups: config 4 44.9 ms vs 41.5 ms (110 registers)
 #define BSW_PINGPONG_WIDE_TRIPS 0
 #endif
@@ -488,6 +491,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         int F = 0;                               // F(i, 2g), a plain int: the only serial chain of the row
         uint32_t rm = 0;                         // running max per lane (even / odd columns)
         int ilo = g0, ihi = g0;                  // last group where a lane reached rm
+        const int KEY_G0 = BSW_KEY_REL ? g0 : 0;   // base of the key's index field
         constexpr bool HIER = BSW_HIER_ARGMAX && NB >= 8;   // measured slower: DESIGN.md 5.6
         uint32_t h = 0, En = 0, Hst = 0;
 
@@ -573,7 +577,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                         // the later group wins ties, as `h >= m` does in the reference
                         const uint32_t t3 = __vimax3_u16x2(h0v * KK, h1v * KK + 0x00010001u, h2v * KK + 0x00020002u);
                         const uint32_t t4 = __vmaxu2(t3, h * KK + 0x00030003u);
-                        rm = __viaddmax_u16x2(t4, (uint32_t)g * 0x00010001u, rm);
+                        rm = __viaddmax_u16x2(t4, (uint32_t)(g - KEY_G0) * 0x00010001u, rm);
                     } else {
                         bool phi, plo;
                         rm = __vibmax_s16x2(h0v, rm, &phi, &plo); mov_if<0>(ilo, plo, g, K1); mov_if<0>(ihi, phi, g, K1);
@@ -644,7 +648,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                             t = __vimax3_u16x2(t, hv[u] * KK + (uint32_t)u * 0x00010001u,
                                                hv[u + 1] * KK + (uint32_t)(u + 1) * 0x00010001u);
                         if (!(NB & 1)) t = __vmaxu2(t, hv[NB - 1] * KK + (uint32_t)(NB - 1) * 0x00010001u);
-                        rm = __viaddmax_u16x2(t, (uint32_t)g * 0x00010001u, rm);
+                        rm = __viaddmax_u16x2(t, (uint32_t)(g - KEY_G0) * 0x00010001u, rm);
                     } else if (HIER) {
                         // one >= event per trip: the post-row scan finds the group inside it
                         uint32_t tm = hv[0];
@@ -717,7 +721,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             Hst = oa.z; En = E1;
             if (KEY) {
                 const uint32_t t2 = __vmaxu2(h0v * KK, h * KK + 0x00010001u);
-                rm = __viaddmax_u16x2(t2, (uint32_t)g * 0x00010001u, rm);
+                rm = __viaddmax_u16x2(t2, (uint32_t)(g - KEY_G0) * 0x00010001u, rm);
             } else {
                 bool phi, plo;
                 rm = __vibmax_s16x2(h0v, rm, &phi, &plo); if (plo) ilo = g; if (phi) ihi = g;
@@ -738,7 +742,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             En = E0;
             R.HE(g) = make_uint2(Hst, En);
             if (KEY) {
-                rm = __vmaxu2(rm, h * KK + (uint32_t)g * 0x00010001u);
+                rm = __vmaxu2(rm, h * KK + (uint32_t)(g - KEY_G0) * 0x00010001u);
             } else {
                 bool phi, plo;
                 rm = __vibmax_s16x2(h, rm, &phi, &plo);
@@ -766,8 +770,8 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
         int mlo, mhi;
         if (KEY) {
             const uint32_t klo = rm & 0xFFFFu, khi = rm >> 16;
-            mlo = (int)(klo >> P.kbits); ilo = (int)(klo & (KK - 1u));
-            mhi = (int)(khi >> P.kbits); ihi = (int)(khi & (KK - 1u));
+            mlo = (int)(klo >> P.kbits); ilo = KEY_G0 + (int)(klo & (KK - 1u));
+            mhi = (int)(khi >> P.kbits); ihi = KEY_G0 + (int)(khi & (KK - 1u));
         } else {
             mlo = (int)(short)(rm & 0xFFFFu); mhi = (int)(short)(rm >> 16);
         }

@@ -104,7 +104,7 @@ static int emul_batch_impl(const bsw_params *p, bsw_seqpair *pairs, const uint8_
             PairResult r;
             const bool m1 = (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767 && !getenv("BSW_EMUL_SLOWM");
             KParams K = K0;
-            const int kbits = bits_for((uint32_t)(sp.len2 - 1) >> 1);
+            const int kbits = bits_for((uint32_t)std::min<int64_t>((sp.len2 - 1) >> 1, BSW_KEY_REL ? (int64_t)w + 2 : INT32_MAX));
             if (key && m1 && sp.h0 + sp.len2 * p->match < (1 << (16 - kbits))) {
                 K.kbits = (uint32_t)kbits; K.kkey = 1u << kbits;
 #define EK(S) (wide ? extend_pair<true, S, false, true, false, 4, true>(R, sp.len2, sp.len1, sp.h0, K) \
