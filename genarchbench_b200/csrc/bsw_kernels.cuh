@@ -412,6 +412,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
     const uint32_t NEG_OE_DEL = pack2(-oe_del), NEG_OE_INS = pack2(-oe_ins);
     const uint32_t NEG_E_DEL = pack2(-P.e_del);
     const int NEG_E_INS_S = -P.e_ins;
+    (void)NEG_E_INS_S;   // BSW_SCALAR_F only
     const uint32_t NEG_E_INS = pack2(-P.e_ins);
     uint32_t LUT_LO, LUT_HI;
     score_lut<WIDE>(P, LUT_LO, LUT_HI);
