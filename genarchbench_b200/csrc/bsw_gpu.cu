@@ -110,7 +110,7 @@ struct Slab {
 };
 
 #ifndef BSW_AUX
-#define BSW_AUX 4
+#define BSW_AUX 8
 #endif
 constexpr int kAux = BSW_AUX;   // launch streams per GPU: length bins of a slab run concurrently
 
