@@ -351,20 +351,20 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                 }
                 const uint32_t qb = seq_bytes((uint32_t)sp.len2, false);
                 const uint32_t sw = slot_words((uint32_t)sp.len2, (uint32_t)sp.len1);
-                if (aoff + sw > aend) {
-                    const uint64_t want = std::max<uint64_t>(kArenaWords, sw);
+                // (one spare word behind the slot: pack_pair_avx2 may write four zero bytes past it)
+                if (aoff + sw + 1 > aend) {
+                    const uint64_t want = std::max<uint64_t>(kArenaWords, sw + 1);
                     aoff = cursor.fetch_add(want, std::memory_order_relaxed);
                     aend = aoff + want;
                     if (aend > cap_words) { overflow |= 1; aend = aoff; }   // stays empty: every later slot retries and fails
                 }
-                if (aoff + sw > aend) continue;
+                if (aoff + sw + 1 > aend) continue;
                 const uint64_t off = aoff;
                 aoff += sw;
                 uint8_t *dst = blob + (size_t)off * 4;
-                bool w1, w2;
+                bool w1, w2 = false;
                 if (packer == 2) {
-                    w1 = pack2bit_avx2(qer + sp.idq, sp.len2, dst);
-                    w2 = pack2bit_avx2(ref + sp.idr, sp.len1, dst + qb);
+                    w1 = pack_pair_avx2(qer + sp.idq, sp.len2, ref + sp.idr, sp.len1, dst, qb);
                 } else if (packer == 1) {
                     w1 = pack2bit_pext(qer + sp.idq, sp.len2, dst);
                     w2 = pack2bit_pext(ref + sp.idr, sp.len1, dst + qb);

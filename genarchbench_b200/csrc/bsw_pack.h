@@ -135,8 +135,50 @@ inline bool pack2bit_avx2(const uint8_t *src, int len, uint8_t *dst) {
     for (; o < nbytes; ++o) dst[o] = 0;
     return !_mm256_testz_si256(bad, _mm256_set1_epi8((char)0xFC));
 }
+// One pair in one call: query at dst, target at dst + qb (qb = the query's padded bytes). Every step stores
+// eight bytes, so up to FOUR bytes past a sequence's padded length are written (zeros: the masked lanes
+// pack to zero): the query's spill lands where the target is packed next, the target's in the slot's own
+// padding or -- at most one word -- in what follows the slot, which the caller therefore must own (the
+// thread's next slot, or the spare word it keeps at the end of its arena). No zero-fill loop, one
+// ambiguity test per pair. Returns true when either sequence holds a base > 3.
+__attribute__((target("avx2")))
+inline void pack2bit_avx2_steps(const uint8_t *src, int len, uint8_t *dst, __m256i &bad) {
+    int i = 0, o = 0;
+    for (; i + 32 <= len; i += 32, o += 8) {
+        const uint64_t r = pack_fold32(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)), bad);
+        memcpy(dst + o, &r, 8);
+    }
+    if (i < len) {
+        const int rem = len - i;
+        __m256i v;
+        if (((uintptr_t)(src + i) & 4095u) <= 4096u - 32u) {
+            const __m256i iota = _mm256_setr_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19,
+                                                  20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31);
+            const __m256i keep = _mm256_cmpgt_epi8(_mm256_set1_epi8((char)rem), iota);
+            v = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)), keep);
+        } else {
+            alignas(32) uint8_t tmp[32] = {0};
+            memcpy(tmp, src + i, (size_t)rem);
+            v = _mm256_load_si256(reinterpret_cast<const __m256i *>(tmp));
+        }
+        const uint64_t r = pack_fold32(v, bad);
+        memcpy(dst + o, &r, 8);
+    }
+}
+__attribute__((target("avx2")))
+inline bool pack_pair_avx2(const uint8_t *q, int qlen, const uint8_t *t, int tlen, uint8_t *dst, uint32_t qb) {
+    __m256i bad = _mm256_setzero_si256();
+    pack2bit_avx2_steps(q, qlen, dst, bad);
+    pack2bit_avx2_steps(t, tlen, dst + qb, bad);
+    return !_mm256_testz_si256(bad, _mm256_set1_epi8((char)0xFC));
+}
 #else
 inline bool pack2bit_avx2(const uint8_t *src, int len, uint8_t *dst) { return pack2bit(src, len, dst); }
+inline bool pack_pair_avx2(const uint8_t *q, int qlen, const uint8_t *t, int tlen, uint8_t *dst, uint32_t qb) {
+    const bool a = pack2bit(q, qlen, dst);
+    const bool b = pack2bit(t, tlen, dst + qb);
+    return a || b;
+}
 #endif
 
 inline void pack4bit(const uint8_t *src, int len, uint8_t *dst) {

@@ -13,7 +13,7 @@ from genarchbench_b200 import pairio  # noqa: E402
 
 L = C.CDLL(sys.argv[1])
 total = 0
-for name in ("bsw_emul_batch", "bsw_emul_batch_win", "bsw_emul_batch_duo"):
+for name in ("bsw_emul_batch", "bsw_emul_batch_key", "bsw_emul_batch_win", "bsw_emul_batch_duo"):
     fn = getattr(L, name)
     fn.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32]
     for w in (1, 3, 17, 100):
@@ -24,5 +24,9 @@ for name in ("bsw_emul_batch", "bsw_emul_batch_win", "bsw_emul_batch_duo"):
         oracle.oracle_batch(a, w=w)
         fn(oracle._params_array(None), b.pairs.ctypes.data, b.ref.ctypes.data, b.qer.ctypes.data, len(b), w)
         total += int((a.outputs() != b.outputs()).any(axis=1).sum())
+# the host packers: destinations of exactly slot + one spare word, so any further overrun is caught
+L.bsw_emul_pack_check.argtypes = [C.c_int64, C.c_uint32]
+L.bsw_emul_pack_check.restype = C.c_int64
+total += int(L.bsw_emul_pack_check(20000, 7))
 print("asan_check mismatches", total)
 sys.exit(1 if total else 0)

@@ -184,3 +184,51 @@ extern "C" int bsw_emul_batch_win(const bsw_params *p, bsw_seqpair *pairs, const
     }
     return 0;
 }
+
+// The host packers against the scalar one: random lengths and contents (ambiguous bases included), sources
+// placed so that tails end right at a page boundary, destination buffers of exactly slot + one spare word
+// (what the product's arenas guarantee), so the AddressSanitizer build sees any further overrun.
+// Returns the number of mismatching pairs.
+#include <random>
+#include <sys/mman.h>
+extern "C" int64_t bsw_emul_pack_check(int64_t n, uint32_t seed) {
+    if (!pack_have_avx2() || !pack_have_pext()) return 0;   // nothing to compare on such a host
+    std::mt19937 rng(seed);
+    const size_t page = 4096;
+    uint8_t *area = static_cast<uint8_t *>(mmap(nullptr, 3 * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+    if (area == MAP_FAILED) return -1;
+    mprotect(area + 2 * page, page, PROT_NONE);   // reads past the end of the second page fault
+    int64_t bad = 0;
+    for (int64_t it = 0; it < n; ++it) {
+        const int qlen = (int)(rng() % 300), tlen = (int)(rng() % 700);
+        const bool amb = rng() % 4 == 0;
+        // (the packers read a tail in one 32-byte piece when that cannot cross a page: sources may be over-READ
+        // within their page by design, so the heap-allocated query gets that much slack; the target sits
+        // against a protected page instead)
+        std::vector<uint8_t> q((size_t)qlen + 32);
+        for (auto &b : q) b = (uint8_t)(rng() & 3);
+        if (amb && qlen) q[rng() % (size_t)qlen] = 4;
+        // the target ends exactly at the protected page (or a few bytes before it)
+        uint8_t *t = area + 2 * page - (size_t)tlen - (rng() % 3 ? 0 : rng() % 40);
+        for (int i = 0; i < tlen; ++i) t[i] = (uint8_t)(rng() & 3);
+        if (amb && tlen && (rng() & 1)) t[rng() % (size_t)tlen] = (uint8_t)(4 + rng() % 3);
+        const uint32_t qb = seq_bytes((uint32_t)qlen, false), tb = seq_bytes((uint32_t)tlen, false);
+        const size_t slot = (size_t)slot_words((uint32_t)qlen, (uint32_t)tlen) * 4;
+        std::vector<uint8_t> want(slot + 4, 0xAB), got(slot + 4, 0xCD), got2(slot + 4, 0xEF);
+        const bool w0a = pack2bit(q.data(), qlen, want.data());
+        const bool w0b = pack2bit(t, tlen, want.data() + qb);
+        const bool w0 = w0a || w0b;
+        const bool w1 = pack_pair_avx2(q.data(), qlen, t, tlen, got.data(), qb);
+        const bool w2a = pack2bit_avx2(q.data(), qlen, got2.data());
+        const bool w2b = pack2bit_avx2(t, tlen, got2.data() + qb);
+        const bool w3a = pack2bit_pext(q.data(), qlen, got2.data());   // overwrites with the same bytes
+        const bool w3b = pack2bit_pext(t, tlen, got2.data() + qb);
+        bool ok = w0 == w1 && w0 == (w2a || w2b) && w0 == (w3a || w3b);
+        if (!w0) {   // packed bytes only matter for pairs without ambiguous bases (the others are re-packed in 4 bits)
+            ok = ok && memcmp(want.data(), got.data(), qb + tb) == 0 && memcmp(want.data(), got2.data(), qb + tb) == 0;
+        }
+        if (!ok) ++bad;
+    }
+    munmap(area, 3 * page);
+    return bad;
+}

@@ -27,6 +27,8 @@ def emul():
     L.bsw_emul_batch_duo.argtypes = L.bsw_emul_batch.argtypes
     L.bsw_emul_batch_win.argtypes = L.bsw_emul_batch.argtypes
     L.bsw_emul_batch_key.argtypes = L.bsw_emul_batch.argtypes
+    L.bsw_emul_pack_check.argtypes = [C.c_int64, C.c_uint32]
+    L.bsw_emul_pack_check.restype = C.c_int64
 
     def run(b, w=100, params=None, duo=False, win=False, key=False):
         fn = L.bsw_emul_batch_duo if duo else (L.bsw_emul_batch_win if win else L.bsw_emul_batch)
@@ -34,6 +36,7 @@ def emul():
             fn = L.bsw_emul_batch_key
         fn(oracle._params_array(params), b.pairs.ctypes.data, b.ref.ctypes.data, b.qer.ctypes.data, len(b), w)
         return b.outputs()
+    run.lib = L
     return run
 
 
@@ -110,6 +113,12 @@ def test_device_code_matches_oracle_on_small_bands(emul, w):
     a = b.copy()
     oracle.oracle_batch(a, w=w)
     assert_same_outputs(emul(b, w), a.outputs(), b, f"emulated kernel vs oracle, w={w}")
+
+
+def test_simd_packers_match_the_scalar_packer(emul):
+    """pack_pair_avx2 / pack2bit_avx2 / pack2bit_pext (the host pass of bsw_gpu_batch) against the scalar
+    packer: every length 0..299 x 0..699 at random, ambiguous bases, tails that end at a protected page."""
+    assert emul.lib.bsw_emul_pack_check(200000, 12345) == 0
 
 
 def test_emulated_device_code_is_clean_under_asan(tmp_path):
