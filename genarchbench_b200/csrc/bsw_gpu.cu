@@ -693,9 +693,19 @@ void scatter_slab(bsw_handle *h, const Slab &s, const PairOut *out, bsw_seqpair 
 // pairs. The lengths are SAMPLED (every 64th record: one cache line in 72 instead of a sweep over the
 // whole array); blob_guess[i] is the pinned-blob capacity to try first for slab i -- prepare_slab
 // reports the exact need if the estimate was short.
+inline bool use_taper() {
+    static const bool v = !(getenv("BSW_TAPER") && getenv("BSW_TAPER")[0] == '0');
+    return v;
+}
+constexpr int64_t kCutGroup = 1 << 16;   // slab boundaries fall on multiples of this many pairs
+// pairs of the slab that starts with `rem` pairs still to go (streaming calls; see cut_slabs)
+inline int64_t slab_target(int64_t rem, int64_t full) {
+    if (!use_taper() || rem > full + full / 2) return full;
+    return std::max<int64_t>(2 * kCutGroup, (rem / 2 + kCutGroup - 1) / kCutGroup * kCutGroup);
+}
 void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts, std::vector<size_t> &blob_guess,
-               bool staged) {
-    constexpr int64_t G = 1 << 16, S = 64;
+               bool staged, std::vector<int64_t> *cuts_flat = nullptr, std::vector<size_t> *guess_flat = nullptr) {
+    constexpr int64_t G = kCutGroup, S = 64;
     const int64_t ng = (n + G - 1) / G;
     std::vector<int64_t> bases((size_t)ng, 0);
 #pragma omp parallel for schedule(static)
@@ -709,23 +719,33 @@ void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts, 
         }
         bases[(size_t)c] = cnt ? b * (hi - c * G) / cnt : 0;
     }
-    cuts.clear();
-    blob_guess.clear();
-    cuts.push_back(0);
-    int64_t acc = 0, cnt = 0;
-    auto close = [&](int64_t hi) {
-        cuts.push_back(hi);
-        // 2 bits per base + up to 19 bytes of padding per pair + 15 % for sampling error and wide pairs
-        blob_guess.push_back((size_t)((acc / 4 + 20 * cnt) * 115 / 100) + 65536);
-        acc = 0; cnt = 0;
+    // Streaming calls end with a taper: what follows the last slab's packing -- its upload, kernels, download
+    // and scatter -- is not overlapped with anything, so the last 1.5 slabs' worth of pairs is cut into
+    // halves, quarters, eighths (BSW_TAPER=0: off). That only pays while the host is the slower side, so the
+    // untapered plan is returned as well (cuts_flat) and bsw_gpu_batch picks where the two diverge.
+    const int64_t full = slab_pairs(staged);
+    auto plan = [&](bool taper, std::vector<int64_t> &cv, std::vector<size_t> &gv) {
+        cv.clear();
+        gv.clear();
+        cv.push_back(0);
+        int64_t acc = 0, cnt = 0, target = full;
+        auto close = [&](int64_t hi) {
+            cv.push_back(hi);
+            // 2 bits per base + up to 19 bytes of padding per pair + 15 % for sampling error and wide pairs
+            gv.push_back((size_t)((acc / 4 + 20 * cnt) * 115 / 100) + 65536);
+            acc = 0; cnt = 0;
+        };
+        for (int64_t c = 0; c < ng; ++c) {
+            const int64_t hi = std::min(n, (c + 1) * G);
+            if (taper && cnt == 0) target = slab_target(n - c * G, full);
+            acc += bases[(size_t)c];
+            cnt += hi - c * G;
+            if (cnt >= target || acc >= kSlabBases) close(hi);
+        }
+        if (cv.back() != n) close(n);
     };
-    for (int64_t c = 0; c < ng; ++c) {
-        const int64_t hi = std::min(n, (c + 1) * G);
-        acc += bases[(size_t)c];
-        cnt += hi - c * G;
-        if (cnt >= slab_pairs(staged) || acc >= kSlabBases) close(hi);
-    }
-    if (cuts.back() != n) close(n);
+    plan(!staged && use_taper(), cuts, blob_guess);
+    if (cuts_flat && guess_flat) plan(false, *cuts_flat, *guess_flat);
 }
 
 // Waits for a busy slab, books its kernel time, answers its trivial pairs and hands its result records
@@ -898,7 +918,11 @@ int bsw_gpu_reserve(bsw_handle *h, int64_t n_pairs, int64_t total_bases) {
     const double share = (double)slab / (double)n_pairs;
     const size_t blob = (size_t)(((double)total_bases * share / 4 + 20.0 * (double)slab) * 1.15) + 65536 +
                         (size_t)omp_get_max_threads() * kArenaWords * 4;
-    const int64_t nslabs = (n_pairs + slab - 1) / slab;
+    int64_t nslabs = 0;   // as cut_slabs will cut them (by pair count; its base-count limit only adds slabs)
+    for (int64_t done = 0; done < n_pairs; ++nslabs) {
+        const int64_t t = slab_target(n_pairs - done, slab_pairs(false));
+        done += (std::min(n_pairs - done, t) + kCutGroup - 1) / kCutGroup * kCutGroup;
+    }
     for (size_t d = 0; d < h->devs.size(); ++d) {
         Device &dev = h->devs[d];
         CU(cudaSetDevice(dev.id));
@@ -924,18 +948,28 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
     h->K.w = w;
     if (n == 0) { st.wall_ms = 0; return BSW_OK; }
 
-    std::vector<int64_t> cuts;
-    std::vector<size_t> guess;
+    std::vector<int64_t> cuts, cuts_flat;
+    std::vector<size_t> guess, guess_flat;
     {
         auto t0 = Clock::now();
-        cut_slabs(pairs, n, cuts, guess, false);
+        cut_slabs(pairs, n, cuts, guess, false, &cuts_flat, &guess_flat);
         st.host_cut_ms = ms_since(t0);
     }
-    const int nslabs = (int)cuts.size() - 1;
+    // the tapered and the untapered plan share their leading full slabs; where they part, the call keeps
+    // the taper only if the host has been the slower side so far (it hardly ever waited for a ring slot)
+    size_t common = 0;
+    while (common + 1 < cuts.size() && common + 1 < cuts_flat.size() && cuts[common + 1] == cuts_flat[common + 1]) ++common;
+    int nslabs = (int)cuts.size() - 1;
     std::vector<double> kms((size_t)ng, 0.0);
     int rc = BSW_OK;
 
     for (int sidx = 0; sidx < nslabs && rc == BSW_OK; ++sidx) {
+        if ((size_t)sidx == common && common > 0 && cuts != cuts_flat &&
+            st.host_wait_ms > 0.2 * ms_since(t_all)) {
+            cuts = cuts_flat;
+            guess = guess_flat;
+            nslabs = (int)cuts.size() - 1;
+        }
         const int d = sidx % ng, r = (sidx / ng) % kRing;
         Device &dev = h->devs[(size_t)d];
         Slab &s = dev.ring[r];
