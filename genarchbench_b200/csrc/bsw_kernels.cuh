@@ -790,9 +790,8 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
             m = max(mlo, mhi);
         }
         if (m == 0) break;
-        // LAST column reaching m
-        if (KEY) {
-        } else if (HIER) {
+        // LAST column reaching m (the keyed path has it already)
+        if (!KEY && HIER) {
             // H(i, j) now sits in Hs[j + 1]; the lane's last >= event happened in the (at most NB)
             // groups ending at ilo / ihi, so the scan below stops within them.
             // (the hi lane of the last group is column `end` when end is odd: never a candidate)
@@ -809,7 +808,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
                 for (int t = 0; t < NB - 1 && R.getH16(2 * gg + 2) != (uint32_t)mhi; ++t) --gg;
                 mj = max(mj, 2 * gg + 1);
             }
-        } else {
+        } else if (!KEY) {
             const int jlo = 2 * ilo, jhi = 2 * ihi + 1;
             mj = mlo > mhi ? jlo : (mhi > mlo ? jhi : max(jlo, jhi));
         }
