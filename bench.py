@@ -74,7 +74,48 @@ WORKLOADS = {
 WORKLOAD = WORKLOADS[3][0] + ", " + SCORING
 INSTR_PER_CELL = 2.5          # 5 packed-s16x2 DPX instructions per 2 cells
 BYTES_PER_PAIR_FMT = "ceil(len1/4)+ceil(len2/4)+12+24"
-DRAM_BYTES_PER_PAIR_NCU = 202.1   # measured, see roofline.traffic
+# ncu figures of the dominant kernel for the CURRENT build, written by scripts/ncu_counters.py from a committed
+# capture (the file names its source CSVs); absent -> `traffic` and `alu_instr_per_cell` are null
+NCU_COUNTERS = os.path.join(ROOT, "profiles", "r2_ncu_counters.json")
+# rough packed bytes per pair of each workload: decides, identically in both arms, whether a step's inputs
+# exceed the 126 MB L2 or the L2 is flushed between timed steps
+EST_BYTES_PER_PAIR = {1: 85, 2: 200, 3: 85, 4: 250, 5: 85}
+
+
+def l2_policy(workload: int, pairs: int):
+    flush = EST_BYTES_PER_PAIR[workload] * pairs < 2 * 126_000_000
+    return flush, ("L2 flushed between timed steps (256 MB written)" if flush
+                   else "inputs larger than L2 (126 MB): no flush needed")
+
+
+def run_config(args, world: int) -> dict:
+    """The `config` object: identical in both arms (`--impl ours` / `--impl reference`) for the same flags."""
+    n_dev = max(world, args.inproc_gpus, 1)
+    return {"workload": WORKLOAD, "pairs_per_gpu": args.pairs, "global_pairs": args.pairs * n_dev, "w": 100,
+            "parallelism": (f"pair-sharded x{n_dev}, no collective" +
+                            (" (one process, bsw_gpu_init(n_gpus))" if args.inproc_gpus > 1 else "")),
+            "l2": l2_policy(args.workload, args.pairs)[1]}
+
+
+def ncu_counters() -> dict:
+    try:
+        return json.load(open(NCU_COUNTERS))
+    except (OSError, ValueError):
+        return {}
+
+
+def parity_sample(work, rank: int, n_check: int):
+    """Compares a random sample of the e2e outputs with the oracle (checker only, outside every timed
+    region). -> (pairs checked, mismatching pairs)"""
+    import oracle
+    n = len(work)
+    rng = np.random.default_rng(4242 + rank)
+    idx = np.sort(rng.choice(n, size=min(n, n_check), replace=False))
+    from genarchbench_b200 import pairio
+    want = pairio.PairBatch(work.pairs[idx].copy(), work.ref, work.qer)
+    got = want.outputs()
+    oracle.oracle_batch(want)
+    return len(idx), int((got != want.outputs()).any(axis=1).sum())
 
 
 class ClockSampler:
@@ -184,6 +225,11 @@ def main():
     ap.add_argument("--steps-cpu", type=int, default=3)
     ap.add_argument("--warmup-cpu", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--inproc-gpus", type=int, default=0,
+                    help="ONE process driving N GPUs through bsw_gpu_init(n_gpus=N) (the library's own split; "
+                         "not under torchrun). The batch holds N x --pairs pairs")
+    ap.add_argument("--parity-sample", type=int, default=50_000,
+                    help="pairs per rank of the e2e outputs compared with the oracle after the timed regions")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: at least 3 warm-up steps
@@ -202,13 +248,14 @@ def main():
             return
         import oracle
         batch = pairio.generate(gen_cfg, min(args.pairs, args.cpu_sample), seed=bdist.shard_seed(gen_seed, 0))
-        args.steps_cpu, args.warmup_cpu = max(1, args.steps), max(1, min(args.warmup, 2))
+        args.steps_cpu, args.warmup_cpu = max(1, args.steps), max(0, args.warmup)
         cb = reference_arm(args, batch, lambda b: oracle.oracle_batch(b.copy()))
         line = {"impl": "reference", "metric": "bsw_gcups", "value": cb["value"], "unit": "GCUPS",
                 "n_gpus": args.gpus, "steps": args.steps_cpu, "warmup": args.warmup_cpu,
                 "ms_per_step": cb["ms_per_pass"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pairs_per_step": cb["pairs"], "w": 100},
+                "config": run_config(args, max(args.gpus, 1)),
+                "sample_pairs_per_step": cb["pairs"],
                 "pairs_per_s": cb["pairs_per_s"],
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -229,8 +276,18 @@ def main():
         bdist.barrier()
         torch.cuda.synchronize()
 
-    batch = pairio.generate(gen_cfg, args.pairs, seed=bdist.shard_seed(gen_seed, rank))
-    g = bsw.BswGpu(devices=[local_rank])
+    if args.inproc_gpus > 1:
+        if world > 1:
+            raise SystemExit("--inproc-gpus is a single-process mode: do not run it under torchrun")
+        # one process, N GPUs: the shards the N ranks of a torchrun job would own, concatenated
+        parts = [pairio.generate(gen_cfg, args.pairs, seed=bdist.shard_seed(gen_seed, r)) for r in range(args.inproc_gpus)]
+        batch = pairio.concat(parts)
+        del parts
+        g = bsw.BswGpu(n_gpus=args.inproc_gpus)
+    else:
+        batch = pairio.generate(gen_cfg, args.pairs, seed=bdist.shard_seed(gen_seed, rank))
+        g = bsw.BswGpu(devices=[local_rank])
+    n_dev = max(world, args.inproc_gpus, 1)
     g.stage(batch.pairs, batch.ref, batch.qer, 100)
     cells = g.count_staged()                      # unit of work, outside any timed region
     dpx_peak = bsw.dpx_peak(0, device=local_rank)  # Ginstr/s, measured live on this GPU
@@ -239,14 +296,17 @@ def main():
     # ---- value: device-resident kernel throughput
     # timing rule: inputs larger than L2, or L2 flushed between iterations (small workloads)
     alg_bytes = algorithmic_bytes(batch.pairs)
-    flush_buf = None
-    if alg_bytes < 2 * 126_000_000:
-        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    flush_bufs = []
+    if l2_policy(args.workload, args.pairs)[0]:
+        flush_bufs = [torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{d}")
+                      for d in (range(args.inproc_gpus) if args.inproc_gpus > 1 else [local_rank])]
 
     def flush_l2():
-        if flush_buf is not None:
-            flush_buf.zero_()
-            torch.cuda.synchronize()
+        for fb in flush_bufs:
+            fb.zero_()
+        if flush_bufs:
+            for fb in flush_bufs:
+                torch.cuda.synchronize(fb.device)
 
     for _ in range(args.warmup):
         g.run_staged()
@@ -286,6 +346,9 @@ def main():
     (sum_h2d, sum_d2h), (max_e2e_ms,) = bdist.reduce_stats([h2d, d2h], [e2e_ms])
     e2e_step_s = max_e2e_ms / e2e_steps * 1e-3
     checksum_ok = bool((work.outputs() != -1).any())
+    # parity of what the timed e2e calls wrote, on a random sample per rank, against the oracle
+    n_chk, n_bad = parity_sample(work, rank, args.parity_sample) if args.parity_sample > 0 else (0, 0)
+    (sum_chk, sum_bad), _ = bdist.reduce_stats([n_chk, n_bad], [0.0])
 
     if rank != 0:
         g.close()
@@ -293,20 +356,25 @@ def main():
         return
 
     peaks = measured_peaks()
+    ncu = ncu_counters()
     achieved_instr = cells / (dev_ms / args.steps * 1e-3) * INSTR_PER_CELL / 1e9   # this rank's GPU
     roofline = {
-        "bound": "dpx_int", "kernel": "bsw_short_kernel<1,1,0,1> (thread-per-pair, s16x2 DPX, keyed row argmax; > 93 % of the step)",
-        "achieved": achieved_instr, "peak": dpx_peak, "unit": "Ginstr/s (packed s16x2 thread-instructions)",
-        "frac": achieved_instr / dpx_peak, "instr_per_cell": INSTR_PER_CELL,
+        "bound": "dpx_int", "kernel": ncu.get("kernel", "the thread-per-pair s16x2 DPX kernel (see profiles/)"),
+        "achieved": achieved_instr / max(args.inproc_gpus, 1), "peak": dpx_peak, "unit": "Ginstr/s (packed s16x2 thread-instructions)",
+        "frac": achieved_instr / max(args.inproc_gpus, 1) / dpx_peak, "instr_per_cell": INSTR_PER_CELL,
         "peak_source": "measured live: VIADDMNMX.S16x2.RELU issue rate, all SMs (bsw_gpu_dpx_peak)",
         # second, tighter ceiling: the kernel's own inner-loop arithmetic (8 cells per trip) run on registers
         # only at full occupancy -- no shared memory, row bookkeeping or divergence (bsw_gpu_dpx_peak(9))
         "inner_loop_ceiling_gcups": trip_peak,
-        "frac_of_inner_loop_ceiling": (cells / (dev_ms / args.steps * 1e-3) / 1e9) / trip_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of the DP kernels, one ncu capture of this workload at
-        # 10 M pairs (profiles/r1_dram_bytes_per_launch_10Mpairs.csv): 202.1 bytes per pair, scaled to this run
-        "traffic": int(DRAM_BYTES_PER_PAIR_NCU * len(batch)), "traffic_unit": "bytes per step (DP kernels)",
-        "traffic_source": "ncu, profiles/r1_dram_bytes_per_launch_10Mpairs.csv, per pair x pairs of this run",
+        "frac_of_inner_loop_ceiling": (cells / max(args.inproc_gpus, 1) / (dev_ms / args.steps * 1e-3) / 1e9) / trip_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the DP kernels per pair, from the committed ncu capture
+        # of this build that profiles/r2_ncu_counters.json names, scaled to the pairs of this GPU's step
+        "traffic": (int(ncu["dram_bytes_per_pair"] * len(batch) / max(args.inproc_gpus, 1))
+                    if ncu.get("dram_bytes_per_pair") and args.workload in (3, 5) else None),
+        "traffic_unit": "bytes per step (DP kernels, one GPU)",
+        "traffic_source": ncu.get("source", "no ncu capture of this build committed: null"),
+        # ALU-pipe thread-instructions per visited cell (smsp__inst_executed_pipe_alu x 32 / cells), same capture
+        "alu_instr_per_cell": ncu.get("alu_instr_per_cell") if args.workload in (3, 5) else None,
         "hbm": {"algorithmic_bytes_per_step": alg_bytes, "bytes_per_pair": BYTES_PER_PAIR_FMT,
                 "achieved_gbs": alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9,
                 "frac": (alg_bytes / (dev_ms / args.steps * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
@@ -314,7 +382,7 @@ def main():
                 if peaks.get("hbm_gbs") else "unavailable"},
     }
     cpu_baseline = None
-    if world == 1:
+    if world == 1 and args.inproc_gpus <= 1:
         g2 = bsw.BswGpu(devices=[local_rank])
 
         def count(b):
@@ -325,15 +393,12 @@ def main():
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "pairs_per_s")}
 
     line = {
-        "metric": "bsw_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+        "metric": "bsw_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": n_dev, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_gpu": args.pairs, "global_pairs": int(sum_pairs),
-                   "cells_visited_per_step": int(sum_cells), "cells_rect_per_gpu": batch.cells_rect(),
-                   "w": 100, "parallelism": f"pair-sharded x{world}, no collective",
-                   "l2": (f"inputs larger than L2: {alg_bytes / 1e6:.0f} MB of packed pairs + results per step vs 126 MB"
-                          if flush_buf is None else
-                          f"L2 flushed between timed steps (256 MB written); {alg_bytes / 1e6:.0f} MB of inputs per step")},
+        "config": run_config(args, world),
+        "run": {"global_pairs": int(sum_pairs), "cells_visited_per_step": int(sum_cells),
+                "cells_rect_rank0": batch.cells_rect(), "algorithmic_input_mb_rank0": round(alg_bytes / 1e6, 1)},
         "pairs_per_s": pairs_per_s,
         "wall_ms_per_step": max_wall_ms / args.steps,
         "clocks": clocks,
@@ -343,6 +408,9 @@ def main():
                 "host_ms": {k[5:-3]: round(last[k], 3) for k in last if k.startswith("host_")},
                 "kernel_ms": last["kernel_ms"], "host_threads": int(os.environ["OMP_NUM_THREADS"]),
                 "api": "bsw_gpu_batch(SeqPair*, ref, qer, n, w) from host buffers", "results_written": checksum_ok},
+        # e2e outputs of every rank against the oracle on a random sample (checked after the timed regions)
+        "parity": {"pairs_checked": int(sum_chk), "mismatches": int(sum_bad), "against": "oracle/bsw_oracle.c",
+                   "fields": "score, qle, tle, gtle, gscore, max_off"},
         "gpu_launches": int(sum_launch),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
@@ -350,6 +418,8 @@ def main():
     emit(line)
     g.close()
     bdist.shutdown()
+    if sum_bad:
+        raise SystemExit(f"PARITY FAILURE: {int(sum_bad)} of {int(sum_chk)} sampled pairs differ from the oracle")
 
 
 if __name__ == "__main__":

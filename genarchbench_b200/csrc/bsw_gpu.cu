@@ -69,6 +69,7 @@ struct Launch {
     int n_wide;
     int row_el, qs_words;   // per pair: uint4 row elements, u32 selector words
     int duo_el;             // per duo thread: row elements of two columns
+    int duo2_blk;           // > 0: extend_duo2 launch, 4-column blocks per thread
     int win_nk;             // > 0: windowed rows of win_nk elements (long query, narrow band)
     size_t smem;     // 0 => long kernel
     int64_t work;    // sum len1*len2, for ordering
@@ -126,6 +127,7 @@ struct Device {
     bool attr_set_long[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_duo[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_win[8] = {false, false, false, false, false, false, false, false};
+    bool attr_set_duo2[8] = {false, false, false, false, false, false, false, false};
 };
 
 }  // namespace
@@ -154,6 +156,8 @@ namespace {
             return BSW_ERR_CUDA;                                                                 \
         }                                                                                        \
     } while (0)
+
+inline int cuda_rc(bsw_handle *h, cudaError_t e, const char *what);
 
 void free_slab(Slab &s) {
     if (s.pinned) {
@@ -223,6 +227,12 @@ int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
     return BSW_OK;
 }
 
+inline int cuda_rc(bsw_handle *h, cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return BSW_OK;
+    h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return BSW_ERR_CUDA;
+}
+
 // ---- host: per-slab preparation ----------------------------------------------------------------
 
 inline size_t smem_need(int row_el, int qs_words) {
@@ -244,6 +254,16 @@ inline bool use_key() {
 }
 inline bool use_duo() {
     static const bool v = getenv("BSW_DUO") && getenv("BSW_DUO")[0] == '1';
+    return v;
+}
+// extend_duo2 (two pairs per thread, bsw_duo.cuh) for the bins whose rows leave at least kDuo2MinWarps warps of it
+// on an SM; BSW_DUO2=0 turns it off (A/B against the one-pair-per-thread kernel), BSW_DUO2_MINWARPS overrides
+inline int duo2_min_warps() {
+    static const int v = [] {
+        if (!(getenv("BSW_DUO2") && getenv("BSW_DUO2")[0] == '1')) return 1 << 30;   // opt-in while it is being tuned
+        const char *e = getenv("BSW_DUO2_MINWARPS");
+        return e ? atoi(e) : 4;
+    }();
     return v;
 }
 
@@ -313,13 +333,17 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     uint8_t *blob = reinterpret_cast<uint8_t *>(s.h_blob);
     std::atomic<uint64_t> cursor{0};
     int bad = 0, maxq = 0, maxsc = 0, maxt = 0, maxh = 0, overflow = 0;
+    // exact blob need of the slab in 4-byte words (slots + 4-bit copies), summed over every pair whether it
+    // fitted or not: what a capacity retry asks for
+    uint64_t need_words = 0;
     h->hist.assign((size_t)T * 2 * kMaxBins, 0);
     std::vector<std::vector<uint32_t>> triv((size_t)T);
     const int packer = pack_have_avx2() ? 2 : (pack_have_pext() ? 1 : 0);
 
-#pragma omp parallel num_threads(T) reduction(| : bad) reduction(| : overflow) reduction(max : maxq) reduction(max : maxsc) reduction(max : maxt) reduction(max : maxh)
+#pragma omp parallel num_threads(T) reduction(| : bad) reduction(| : overflow) reduction(max : maxq) reduction(max : maxsc) reduction(max : maxt) reduction(max : maxh) reduction(+ : need_words)
     {
         const int t = omp_get_thread_num();
+        bool full = false;             // the blob ran out: this thread only sizes its remaining pairs
         uint32_t *hist = h->hist.data() + (size_t)t * 2 * kMaxBins;
         uint64_t aoff = 0, aend = 0;   // this thread's current arena of the blob, in 4-byte words
         // work items: the packing chunks, with the scatter chunks of `job` spread evenly between them
@@ -351,14 +375,27 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                 }
                 const uint32_t qb = seq_bytes((uint32_t)sp.len2, false);
                 const uint32_t sw = slot_words((uint32_t)sp.len2, (uint32_t)sp.len1);
+                need_words += sw + 1;
+                if (full) {
+                    // sizing only: a pair holding an ambiguous base needs its 4-bit copy as well
+                    bool amb = false;
+                    for (int32_t x = 0; x < sp.len2 && !amb; ++x) amb = qer[sp.idq + x] > 3;
+                    for (int32_t x = 0; x < sp.len1 && !amb; ++x) amb = ref[sp.idr + x] > 3;
+                    if (amb) need_words += ((uint64_t)seq_bytes((uint32_t)sp.len2, true) + seq_bytes((uint32_t)sp.len1, true) + 15) / 16 * 4;
+                    continue;
+                }
                 // (one spare word behind the slot: pack_pair_avx2 may write four zero bytes past it)
                 if (aoff + sw + 1 > aend) {
                     const uint64_t want = std::max<uint64_t>(kArenaWords, sw + 1);
                     aoff = cursor.fetch_add(want, std::memory_order_relaxed);
                     aend = aoff + want;
-                    if (aend > cap_words) { overflow |= 1; aend = aoff; }   // stays empty: every later slot retries and fails
+                    if (aend > cap_words) {   // no further reservations from this thread (they would only inflate the cursor)
+                        overflow |= 1; full = true; aend = aoff;
+                        --k;                  // size this pair again in `full` mode (its 4-bit copy included)
+                        need_words -= sw + 1;
+                        continue;
+                    }
                 }
-                if (aoff + sw + 1 > aend) continue;
                 const uint64_t off = aoff;
                 aoff += sw;
                 uint8_t *dst = blob + (size_t)off * 4;
@@ -377,6 +414,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                     wide = 1;
                     const uint32_t wq = seq_bytes((uint32_t)sp.len2, true), wt = seq_bytes((uint32_t)sp.len1, true);
                     const uint64_t ww = ((uint64_t)wq + wt + 15) / 16 * 4;
+                    need_words += ww;
                     const uint64_t woff = cursor.fetch_add(ww, std::memory_order_relaxed);
                     if (woff + ww > cap_words) {
                         overflow |= 1;
@@ -407,10 +445,17 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
         }
     }
     if (bad) return BSW_ERR_RANGE;
+    if (overflow) {
+        // the exact need plus what the threads' partly used arenas may waste; checked against the 32-bit word
+        // addressing of a slab blob only now (the cursor itself is meaningless after an overflow)
+        const uint64_t want = need_words + (uint64_t)T * kArenaWords + 64;
+        if (want > 0xFFFFFF00ull) return BSW_ERR_RANGE;
+        s.blob_bytes = (size_t)want * 4 + 16;
+        return kRetry;
+    }
     const uint64_t total_words = cursor.load();
     if (total_words > 0xFFFFFF00ull) return BSW_ERR_RANGE;   // slab blobs are addressed in 32-bit words
     s.blob_bytes = (size_t)total_words * 4 + 16;
-    if (overflow) return kRetry;
     memset(blob + (size_t)total_words * 4, 0, 16);
     s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
     s.max_sc = (int)std::min<int64_t>(maxsc, INT32_MAX);
@@ -457,7 +502,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                 if (b == s.long_bin0 && nw_long + nn_long > 0) {
                     Launch L;
                     L.first = 0; L.n = nw_long + nn_long; L.n_wide = nw_long; L.work = (int64_t)L.n * maxq * 2 * h->K.w;
-                    L.row_el = L.qs_words = L.duo_el = 0;
+                    L.row_el = L.qs_words = L.duo_el = L.duo2_blk = 0;
                     L.smem = ws; L.win_nk = nk;
                     s.launches.push_back(L);
                     p = L.n;
@@ -473,6 +518,14 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             L.duo_el = duo_elems(q_hi);
             L.smem = bin_smem(b);
             L.win_nk = 0;
+            L.duo2_blk = 0;
+            if (!use_duo()) {
+                const size_t d2 = (size_t)duo2_thread_bytes(q_hi) * kDuo2Threads;
+                if (d2 <= kMaxSmem && (int)(kMaxSmem / d2) * (kDuo2Threads / 32) >= duo2_min_warps()) {
+                    L.duo2_blk = duo_blocks(q_hi);
+                    L.smem = d2;
+                }
+            }
             if (L.smem > kMaxSmem) {
                 // whole rows do not fit and the band is too wide for a window: one warp per pair. Its shared
                 // memory per pair is small against the SM's, so neighbouring bins share a launch as long as
@@ -503,6 +556,18 @@ int prepare_slab_fit(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uin
                      int64_t lo, int n, size_t blob_guess, ScatterJobs jobs = ScatterJobs()) {
     auto t0 = Clock::now();
     blob_guess += (size_t)omp_get_max_threads() * kArenaWords * 4;   // every thread may leave an arena partly unused
+    if (n > s.cap_pairs && jobs.count > 0) {
+        // the slot's pair-sized buffers are about to be reallocated, and a queued scatter job may still read
+        // this slot's h_out: work the jobs off first
+        const int nc = jobs.chunks();
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < nc; ++c) {
+            int jj = 0;
+            while (c >= jobs.first_chunk[jj + 1]) ++jj;
+            scatter_chunk(jobs.j[jj], c - jobs.first_chunk[jj]);
+        }
+        jobs = ScatterJobs();
+    }
     int rc = ensure_slab(h, s, n, blob_guess);
     h->stats.host_alloc_ms += ms_since(t0);
     if (rc) return rc;
@@ -511,7 +576,7 @@ int prepare_slab_fit(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uin
         if (rc != kRetry) return rc;
         jobs = ScatterJobs();   // done (a scatter is idempotent anyway)
         t0 = Clock::now();
-        rc = ensure_slab(h, s, n, s.blob_bytes + (s.blob_bytes >> 3) + 4096);
+        rc = ensure_slab(h, s, n, s.blob_bytes + (s.blob_bytes >> 4) + 4096);
         h->stats.host_alloc_ms += ms_since(t0);
         if (rc) return rc;
     }
@@ -535,6 +600,7 @@ typedef void (*ShortFn)(const PairMeta *, const uint32_t *, const uint32_t *, Pa
 typedef void (*DuoFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int);
 typedef void (*WinFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int);
 typedef void (*LongFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
+typedef DuoFn Duo2Fn;
 template <int I> struct KernelTable {
     static void fill(ShortFn *sf, LongFn *lf, DuoFn *df, WinFn *wf) {
         wf[I] = bsw_win_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
@@ -559,8 +625,13 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
     static WinFn win_fn[8];
     static const ShortFn short_key_fn[2] = {bsw_short_kernel<true, false, false, true>,
                                             bsw_short_kernel<true, true, false, true>};
-    static bool filled = false;
-    if (!filled) { KernelTable<7>::fill(short_fn, long_fn, duo_fn, win_fn); filled = true; }
+    // [fastm * 2 + sym] and, keyed, [sym]
+    static const Duo2Fn duo2_fn[4] = {bsw_duo2_kernel<false, false, false>, bsw_duo2_kernel<false, true, false>,
+                                      bsw_duo2_kernel<true, false, false>, bsw_duo2_kernel<true, true, false>};
+    static const Duo2Fn duo2_key_fn[2] = {bsw_duo2_kernel<true, false, true>, bsw_duo2_kernel<true, true, true>};
+    // (a function-local static with an initialiser is filled exactly once, also with two handles on two threads)
+    static const bool filled = [] { KernelTable<7>::fill(short_fn, long_fn, duo_fn, win_fn); return true; }();
+    (void)filled;
     int rc = ensure_aux(h, dev);
     if (rc) return rc;
     CU(cudaEventRecord(dev.fork_ev, main));
@@ -580,6 +651,26 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                 cudaStream_t st = dev.aux[rr++ % kAux];
                 win_fn[ki]<<<wgrid, kWinBlockPairs, L.smem, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
                                                               s.d_out, L.n_wide, L.n - L.n_wide, h->K, L.win_nk);
+            } else if (L.smem && L.duo2_blk && !count) {
+                // keyed row argmax when the launch's scores and column indices (up to the end of the last block)
+                // share 16 bits
+                const int kbits = bits_for((uint32_t)(4 * L.duo2_blk - 1));
+                const bool keyed = s.fastm && use_key() && kbits < 16 && s.max_sc < (1 << (16 - kbits));
+                const int fi = keyed ? (h->sym ? 1 : 0) : ((s.fastm ? 2 : 0) | (h->sym ? 1 : 0));
+                Duo2Fn fn = keyed ? duo2_key_fn[fi] : duo2_fn[fi];
+                bool &attr = dev.attr_set_duo2[keyed ? 4 + fi : fi];
+                if (!attr) {
+                    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+                    attr = true;
+                }
+                KParams K = h->K;
+                if (keyed) { K.kbits = (uint32_t)kbits; K.kkey = 1u << kbits; }
+                cudaStream_t st = dev.aux[rr++ % kAux];
+                const int threads = (L.n + 1) / 2;
+                fn<<<(threads + kDuo2Threads - 1) / kDuo2Threads, kDuo2Threads, L.smem, st>>>(
+                    s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, K, L.duo2_blk);
+                if (keyed) h->stats.pairs_keyed += L.n;
+                h->stats.pairs_duo += L.n;
             } else if (L.smem && use_duo()) {
                 if (!dev.attr_set_duo[ki]) {
                     CU(cudaFuncSetAttribute(duo_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -598,6 +689,7 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                 const int kbits = bits_for((uint32_t)std::min<int64_t>(2 * L.row_el - 1, BSW_KEY_REL ? (int64_t)h->K.w + 2 : INT32_MAX));
                 const bool keyed = s.fastm && !count && use_key() && kbits < 16 && s.max_sc < (1 << (16 - kbits));
                 ShortFn fn = keyed ? short_key_fn[h->sym ? 1 : 0] : short_fn[ki];
+                const size_t smem1 = L.duo2_blk ? smem_need(L.row_el, L.qs_words) : L.smem;   // (a COUNT run of a duo2 bin)
                 bool &attr = keyed ? dev.attr_set_key[h->sym ? 1 : 0] : dev.attr_set[ki];
                 if (!attr) {
                     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
@@ -606,7 +698,7 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                 KParams K = h->K;
                 if (keyed) { K.kbits = (uint32_t)kbits; K.kkey = 1u << kbits; }
                 cudaStream_t st = dev.aux[rr++ % kAux];
-                fn<<<grid, kBlockPairs, L.smem, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
+                fn<<<grid, kBlockPairs, smem1, st>>>(s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob,
                                                       s.d_out, L.n_wide, L.n - L.n_wide, K, L.row_el, L.qs_words);
                 if (keyed) h->stats.pairs_keyed += L.n;
             } else {
@@ -639,7 +731,8 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
 int bin_slab(bsw_handle *h, Slab &s, cudaStream_t st) {
     if (s.n_dev == 0) return BSW_OK;
     const int n = s.n;
-    bsw_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_meta, n, s.d_keys, s.d_ord, s.key_b1, s.key_b0, s.long_bin0);
+    bsw_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_meta, n, s.d_keys, s.d_ord, s.key_b1, s.key_b0, s.long_bin0,
+                                                    s.d_out);
     CU(cudaGetLastError());
     h->stats.kernel_launches++;
     size_t tmp = s.sort_tmp_bytes;
@@ -942,7 +1035,7 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
     const int ng = (int)h->devs.size();
     bsw_gpu_stats &st = h->stats;
     st.pairs = n; st.kernel_launches = 0; st.h2d_bytes = 0; st.d2h_bytes = 0;
-    st.pairs_short = 0; st.pairs_long = 0; st.pairs_keyed = 0;
+    st.pairs_short = 0; st.pairs_long = 0; st.pairs_keyed = 0; st.pairs_duo = 0;
     st.host_bin_ms = st.host_pack_ms = st.host_scatter_ms = st.kernel_ms = 0;
     st.host_sort_ms = st.host_plan_ms = st.host_alloc_ms = st.host_cut_ms = st.host_wait_ms = 0;
     h->K.w = w;
@@ -973,7 +1066,7 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
         const int d = sidx % ng, r = (sidx / ng) % kRing;
         Device &dev = h->devs[(size_t)d];
         Slab &s = dev.ring[r];
-        CU(cudaSetDevice(dev.id));
+        if ((rc = cuda_rc(h, cudaSetDevice(dev.id), "cudaSetDevice"))) break;
         // results that are ready go into the caller's array while this slab is packed: the ring slot's
         // own older slab (wait for it if need be) and any other slab of this GPU that has finished
         ScatterJobs jobs;
@@ -989,15 +1082,18 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
                               guess[(size_t)sidx], jobs);
         if (rc) break;
         if (s.n_dev) {
+            // (an error after the first enqueue leaves work in flight on the slab's stream: the slab is marked
+            // busy all the same, so that the drain below waits for it before anything is freed or reused)
+            s.busy = true;
             if ((rc = upload_slab(h, s))) break;
-            CU(cudaEventRecord(s.ev_k0, s.stream));
+            if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k0, s.stream), "cudaEventRecord"))) break;
             if ((rc = bin_slab(h, s, s.stream))) break;
             if ((rc = launch_slab(h, dev, s))) break;
-            CU(cudaEventRecord(s.ev_k1, s.stream));
+            if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k1, s.stream), "cudaEventRecord"))) break;
             if ((rc = download_slab(h, s))) break;
         }
-        CU(cudaEventRecord(s.ev_done, s.stream));
         s.busy = true;
+        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_done, s.stream), "cudaEventRecord"))) break;
     }
     // drain (also on error, so that no stream still writes pinned memory we may free later)
     for (int d = 0; d < ng; ++d) {
@@ -1007,7 +1103,8 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
             Slab &s = dev.ring[r];
             if (!s.busy) continue;
             if (rc == BSW_OK) rc = finish_slab(h, s, pairs, &kms[(size_t)d]);
-            else { cudaEventSynchronize(s.ev_done); s.busy = false; }
+            else { cudaStreamSynchronize(s.stream); s.busy = false; }
+            if (rc != BSW_OK && s.busy) { cudaStreamSynchronize(s.stream); s.busy = false; }
         }
     }
     st.kernel_ms = *std::max_element(kms.begin(), kms.end());
@@ -1077,7 +1174,7 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
     drop_staged(h);
     bsw_gpu_stats &st = h->stats;
     st.pairs = n; st.h2d_bytes = 0; st.d2h_bytes = 0; st.kernel_launches = 0;
-    st.pairs_short = st.pairs_long = st.pairs_keyed = 0;
+    st.pairs_short = st.pairs_long = st.pairs_keyed = st.pairs_duo = 0;
     h->K.w = w;
     const int ng = (int)h->devs.size();
     std::vector<int64_t> cuts;
@@ -1105,7 +1202,7 @@ int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms) {
     if (h->staged_n < 0) return BSW_ERR_STATE;
     h->K.w = h->staged_w;
     h->stats.kernel_launches = 0;
-    h->stats.pairs_short = h->stats.pairs_long = h->stats.pairs_keyed = 0;
+    h->stats.pairs_short = h->stats.pairs_long = h->stats.pairs_keyed = h->stats.pairs_duo = 0;
     // all slabs of one GPU run back to back on that GPU's first stream; GPUs run concurrently
     for (Device &dev : h->devs) {
         if (dev.staged.empty()) continue;

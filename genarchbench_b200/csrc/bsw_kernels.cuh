@@ -865,6 +865,7 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
 
 }  // namespace bswk
 #include "bsw_pair2.cuh"
+#include "bsw_duo.cuh"
 namespace bswk {
 
 #ifndef BSW_HOST_EMUL
@@ -1005,6 +1006,53 @@ bsw_duo_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ o
     PairResult r[2];
     if (twide) extend_duo<FASTM, SYM, COUNT, true>(R, L, P, r);
     else extend_duo<FASTM, SYM, COUNT, false>(R, L, P, r);
+    store_result(out, mA.id, r[0]);
+    if (hasB) store_result(out, mB.id, r[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Short pairs, two per thread, second generation (extend_duo2, bsw_duo.cuh). Launch: block = kDuo2Threads, dynamic
+// smem = 40 * nblk * kDuo2Threads (nblk = duo_blocks(longest query of the launch)). Thread t takes the launch's
+// sorted pairs 2t and 2t + 1 (neighbours in (len2, len1, h0) order). A warp whose first thread still falls among
+// the n_wide pairs holding an ambiguous base runs the LOP3-selector instantiation for all of its threads.
+// ---------------------------------------------------------------------------------------------
+#ifndef BSW_DUO2_NT
+#define BSW_DUO2_NT 64
+#endif
+constexpr int kDuo2Threads = BSW_DUO2_NT;
+
+template <bool FASTM, bool SYM, bool KEY>
+__global__ void __launch_bounds__(kDuo2Threads)
+bsw_duo2_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
+                const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
+                KParams P, int nblk) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NT = kDuo2Threads;
+    const int tid = threadIdx.x;
+    const int t = blockIdx.x * NT + tid;
+    const int n = n_wide + n_narrow;
+    if (2 * t >= n) return;
+    const bool twide = 2 * (t & ~31) < n_wide;       // warp-uniform
+    const PairMeta mA = meta[ord[2 * t]];
+    const bool hasB = 2 * t + 1 < n;
+    PairMeta mB = mA;
+    if (hasB) mB = meta[ord[2 * t + 1]];
+
+    RowsD R;
+    R.stride = NT;
+    R.he4 = reinterpret_cast<uint4 *>(smem) + tid;
+    R.qs = reinterpret_cast<uint2 *>(smem + (size_t)32 * nblk * NT) + tid;
+
+    DuoIn L[2];
+    L[0].qlen = mA.len2; L[0].tlen = mA.len1; L[0].h0 = mA.h0; L[0].wide = mA.flags & 1;
+    L[1].qlen = hasB ? mB.len2 : 0; L[1].tlen = hasB ? mB.len1 : 0; L[1].h0 = hasB ? mB.h0 : 0;
+    L[1].wide = hasB && (mB.flags & 1);
+    L[0].blob = blob + mA.off; L[1].blob = blob + mB.off;
+    if (L[0].wide) L[0].blob = blob + L[0].blob[0];
+    if (L[1].wide) L[1].blob = blob + L[1].blob[0];
+    PairResult r[2];
+    if (twide) extend_duo2<FASTM, SYM, true, KEY>(R, L, P, r);
+    else extend_duo2<FASTM, SYM, false, KEY>(R, L, P, r);
     store_result(out, mA.id, r[0]);
     if (hasB) store_result(out, mB.id, r[1]);
 }
@@ -1334,12 +1382,21 @@ __host__ __device__ inline uint64_t sort_key(uint32_t len2, uint32_t len1, uint3
 }
 #ifndef BSW_HOST_EMUL
 __global__ void bsw_key_kernel(const PairMeta *__restrict__ meta, int n, uint64_t *__restrict__ keys,
-                               uint32_t *__restrict__ idx, int b1, int b0, int long_bin0) {
+                               uint32_t *__restrict__ idx, int b1, int b0, int long_bin0,
+                               PairOut *__restrict__ out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const PairMeta m = meta[k];
     keys[k] = sort_key(m.len2, m.len1, (uint32_t)m.h0, m.flags & 1u, b1, b0, long_bin0);
     idx[k] = (uint32_t)k;
+    // empty target or query: no DP kernel is launched for the pair (key 0 sorts behind every launch), the
+    // DP loop of the reference never runs (bandedSWA.cpp:181 with tlen == 0 / end == 0). Its answer is
+    // written here so that the slab's result records are complete on the device.
+    if (m.len2 == 0 || m.len1 == 0) {
+        PairResult r;
+        r.score = m.h0; r.qle = 0; r.tle = 0; r.gtle = 0; r.gscore = -1; r.max_off = 0; r.cells = 0;
+        store_result(out, m.id, r);
+    }
 }
 #endif
 

@@ -100,6 +100,22 @@ class PairBatch:
         return int((self.pairs["len1"].astype(np.int64) * self.pairs["len2"].astype(np.int64)).sum())
 
 
+def concat(batches) -> PairBatch:
+    """Concatenates batches into one (offsets rebased, ids renumbered)."""
+    batches = list(batches)
+    n = sum(len(b) for b in batches)
+    pairs = np.zeros(n, dtype=SEQPAIR_DTYPE)
+    lo = ro = qo = 0
+    for b in batches:
+        part = pairs[lo:lo + len(b)]
+        part[...] = b.pairs
+        part["idr"] += ro
+        part["idq"] += qo
+        lo += len(b); ro += len(b.ref); qo += len(b.qer)
+    pairs["id"] = np.arange(n)
+    return PairBatch(pairs, np.concatenate([b.ref for b in batches]), np.concatenate([b.qer for b in batches]))
+
+
 def _take(ptr: C.c_void_p, nbytes: int) -> np.ndarray:
     """Copies a malloc'd buffer (+64 bytes slack) into numpy and frees it."""
     buf = (C.c_uint8 * (nbytes + 64)).from_address(ptr.value)

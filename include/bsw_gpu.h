@@ -110,6 +110,7 @@ typedef struct bsw_gpu_stats {
     double  host_wait_ms;       /* last batch: host blocked on the GPU (ring slot not yet drained) */
     int64_t pairs_keyed;        /* of pairs_short: launched with the keyed row argmax (scores and group
                                    indices of the launch share 16 bits) */
+    int64_t pairs_duo;          /* of pairs_short: launched on the two-pairs-per-thread kernel */
 } bsw_gpu_stats;
 int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out);
 

@@ -188,6 +188,59 @@ def test_empty_single_and_ragged(gpu):
     assert_same_outputs(b.outputs(), a.outputs(), b, "ragged")
 
 
+def test_empty_sequences_spread_over_many_slabs(gpu):
+    """Pairs with an empty target or query are answered without a DP launch (bandedSWA.cpp:181 never runs its
+    loop). A streaming call of several slabs scatters a slab's results while the next one is packed: the
+    answers of the empty pairs must survive that deferred scatter (they did not: ADVICE r1, claim_slab)."""
+    b = pairio.generate(1, 700_000, seed=41)                   # the taper cuts this into >= 3 slabs
+    rng = np.random.default_rng(5)
+    k1 = rng.choice(len(b), 3000, replace=False)
+    b.pairs["len1"][k1[:1500]] = 0
+    b.pairs["len2"][k1[1500:]] = 0
+    a = b.copy()
+    oracle.oracle_batch(a)
+    for _ in range(2):                                         # second call: ring slots hold older results
+        for f in pairio.OUTPUT_FIELDS:
+            b.pairs[f] = -1
+        gpu.batch(b.pairs, b.ref, b.qer, 100)
+        assert_same_outputs(b.outputs(), a.outputs(), b, "empty sequences over several slabs")
+    want = np.array([[h0, 0, 0, 0, -1, 0] for h0 in b.pairs["h0"][k1]])
+    assert (b.outputs()[k1] == want).all()
+
+
+def test_blob_capacity_retry_with_many_ambiguous_pairs():
+    """Half of the pairs hold an ambiguous base, so their 4-bit copies triple the packed bytes and the first
+    capacity guess (sampled lengths + 15 %) is short: prepare_slab reports the exact need and runs again
+    (the reported size used to be inflated by an arena per remaining pair)."""
+    c = pairio.preset(1)
+    c.n_frac = 0.5
+    b = pairio.generate(c, 400_000, seed=43)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    with bsw.BswGpu() as g:                                    # fresh handle: ring slots sized by this call
+        g.batch(b.pairs, b.ref, b.qer, 100)
+    assert_same_outputs(b.outputs(), a.outputs(), b, "capacity retry")
+
+
+def test_growing_slabs_do_not_lose_queued_results():
+    """Early slabs cut by the base-count limit hold few (long) pairs, later slabs of the same call hold many
+    short ones: the ring slot's pair-sized buffers grow while a scatter job of the older slab is still queued
+    (use-after-free of h_out)."""
+    cl = pairio.preset(4)
+    cl.len2_min, cl.len2_max = 900, 1000
+    long_ = pairio.generate(cl, 300_000, seed=44)              # > 512 Mi bases: the first slab is cut by bases
+    short = pairio.generate(1, 2_600_000, seed=45)             # slots 1, 2, then slot 0 again with 4x the pairs
+    b = pairio.concat([long_, short])
+    with bsw.BswGpu() as g:
+        g.batch(b.pairs, b.ref, b.qer, 100)
+    idx = np.random.default_rng(6).choice(len(b), 40000, replace=False)
+    idx = np.concatenate([idx, np.arange(0, 300_000, 97)])
+    samp = pairio.PairBatch(b.pairs[idx].copy(), b.ref, b.qer)
+    got = samp.outputs()
+    oracle.oracle_batch(samp)
+    assert_same_outputs(got, samp.outputs(), samp, "growing slabs, sampled")
+
+
 def test_untouched_fields_and_padding(gpu):
     """Only the six outputs of entries < n are written (the reference also clobbers n..round)."""
     b = pairio.generate(1, 1000, seed=8)
