@@ -68,7 +68,6 @@ struct Launch {
     int n;           // pairs (the n_wide pairs holding an ambiguous base come first)
     int n_wide;
     int row_el, qs_words;   // per pair: uint4 row elements, u32 selector words
-    int duo_el;             // per duo thread: row elements of two columns
     int duo2_blk;           // > 0: extend_duo2 launch, 4-column blocks per thread
     int win_nk;             // > 0: windowed rows of win_nk elements (long query, narrow band)
     size_t smem;     // 0 => long kernel
@@ -125,7 +124,6 @@ struct Device {
     bool attr_set[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_key[2] = {false, false};
     bool attr_set_long[8] = {false, false, false, false, false, false, false, false};
-    bool attr_set_duo[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_win[8] = {false, false, false, false, false, false, false, false};
     bool attr_set_duo2[8] = {false, false, false, false, false, false, false, false};
 };
@@ -238,10 +236,6 @@ inline int cuda_rc(bsw_handle *h, cudaError_t e, const char *what) {
 inline size_t smem_need(int row_el, int qs_words) {
     return ((size_t)16 * row_el + (size_t)4 * qs_words) * kBlockPairs;
 }
-// BSW_DUO=1 routes the short bins to the two-pairs-per-thread kernel (bsw_pair2.cuh) instead of the
-// one-pair-per-thread kernel. It is bit-exact and issues fewer instructions per cell, but each thread
-// then owns two pairs' rows, the shared memory holds half as many warps, and on B200 it measured
-// 41.8 ms against 22.2 ms per 10 M config-3 pairs -- kept for A/B runs, not the default.
 // BSW_WINDOW=0 sends every long pair to the warp-per-pair kernel (A/B against the windowed rows)
 inline bool use_window() {
     static const bool v = !(getenv("BSW_WINDOW") && getenv("BSW_WINDOW")[0] == '0');
@@ -250,10 +244,6 @@ inline bool use_window() {
 // BSW_KEY=0: the short kernel's general argmax bookkeeping everywhere (A/B switch of extend_pair<.., KEY>)
 inline bool use_key() {
     static const bool v = !(getenv("BSW_KEY") && getenv("BSW_KEY")[0] == '0');
-    return v;
-}
-inline bool use_duo() {
-    static const bool v = getenv("BSW_DUO") && getenv("BSW_DUO")[0] == '1';
     return v;
 }
 // extend_duo2 (two pairs per thread, bsw_duo.cuh) for the bins whose rows leave at least kDuo2MinWarps warps of it
@@ -480,7 +470,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
         const bool can_window = (size_t)20 * nk * 128 <= kMaxSmem && use_window();
         auto bin_smem = [&](int b) {
             const int q_hi = std::min(maxq, (b + 1) * kBinCols);
-            return use_duo() ? (size_t)duo_thread_bytes(q_hi) * kDuoThreads : smem_need(row_elems(q_hi), sel_words(q_hi));
+            return smem_need(row_elems(q_hi), sel_words(q_hi));
         };
         // windowed rows from the first bin whose whole rows do not fit (BSW_WINDOW_EARLY=1, experiment: from
         // the first bin whose whole rows need more shared memory per pair than the window -- config 2
@@ -502,7 +492,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                 if (b == s.long_bin0 && nw_long + nn_long > 0) {
                     Launch L;
                     L.first = 0; L.n = nw_long + nn_long; L.n_wide = nw_long; L.work = (int64_t)L.n * maxq * 2 * h->K.w;
-                    L.row_el = L.qs_words = L.duo_el = L.duo2_blk = 0;
+                    L.row_el = L.qs_words = L.duo2_blk = 0;
                     L.smem = ws; L.win_nk = nk;
                     s.launches.push_back(L);
                     p = L.n;
@@ -515,11 +505,10 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             L.first = p; L.n = nw + nn; L.n_wide = nw; L.work = (int64_t)(nw + nn) * q_hi * q_hi;
             L.row_el = row_elems(q_hi);
             L.qs_words = sel_words(q_hi);
-            L.duo_el = duo_elems(q_hi);
             L.smem = bin_smem(b);
             L.win_nk = 0;
             L.duo2_blk = 0;
-            if (!use_duo()) {
+            {
                 const size_t d2 = (size_t)duo2_thread_bytes(q_hi) * kDuo2Threads;
                 if (d2 <= kMaxSmem && (int)(kMaxSmem / d2) * (kDuo2Threads / 32) >= duo2_min_warps()) {
                     L.duo2_blk = duo_blocks(q_hi);
@@ -597,20 +586,18 @@ int ensure_aux(bsw_handle *h, Device &dev) {
 
 // The kernel instantiations, indexed [fastm][sym][count].
 typedef void (*ShortFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
-typedef void (*DuoFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int);
 typedef void (*WinFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int);
 typedef void (*LongFn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int, int);
-typedef DuoFn Duo2Fn;
+typedef void (*Duo2Fn)(const PairMeta *, const uint32_t *, const uint32_t *, PairOut *, int, int, KParams, int);
 template <int I> struct KernelTable {
-    static void fill(ShortFn *sf, LongFn *lf, DuoFn *df, WinFn *wf) {
+    static void fill(ShortFn *sf, LongFn *lf, WinFn *wf) {
         wf[I] = bsw_win_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
         sf[I] = bsw_short_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
         lf[I] = bsw_long_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
-        df[I] = bsw_duo_kernel<(I & 4) != 0, (I & 2) != 0, (I & 1) != 0>;
-        KernelTable<I - 1>::fill(sf, lf, df, wf);
+        KernelTable<I - 1>::fill(sf, lf, wf);
     }
 };
-template <> struct KernelTable<-1> { static void fill(ShortFn *, LongFn *, DuoFn *, WinFn *) {} };
+template <> struct KernelTable<-1> { static void fill(ShortFn *, LongFn *, WinFn *) {} };
 inline int kernel_index(bool fastm, bool sym, bool count) {
     return (fastm ? 4 : 0) | (sym ? 2 : 0) | (count ? 1 : 0);
 }
@@ -621,7 +608,6 @@ inline int kernel_index(bool fastm, bool sym, bool count) {
 int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *slabs, int nslabs, bool count = false) {
     static ShortFn short_fn[8];
     static LongFn long_fn[8];
-    static DuoFn duo_fn[8];
     static WinFn win_fn[8];
     static const ShortFn short_key_fn[2] = {bsw_short_kernel<true, false, false, true>,
                                             bsw_short_kernel<true, true, false, true>};
@@ -630,7 +616,7 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                                       bsw_duo2_kernel<true, false, false>, bsw_duo2_kernel<true, true, false>};
     static const Duo2Fn duo2_key_fn[2] = {bsw_duo2_kernel<true, false, true>, bsw_duo2_kernel<true, true, true>};
     // (a function-local static with an initialiser is filled exactly once, also with two handles on two threads)
-    static const bool filled = [] { KernelTable<7>::fill(short_fn, long_fn, duo_fn, win_fn); return true; }();
+    static const bool filled = [] { KernelTable<7>::fill(short_fn, long_fn, win_fn); return true; }();
     (void)filled;
     int rc = ensure_aux(h, dev);
     if (rc) return rc;
@@ -671,16 +657,6 @@ int launch_slabs(bsw_handle *h, Device &dev, cudaStream_t main, Slab *const *sla
                     s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, K, L.duo2_blk);
                 if (keyed) h->stats.pairs_keyed += L.n;
                 h->stats.pairs_duo += L.n;
-            } else if (L.smem && use_duo()) {
-                if (!dev.attr_set_duo[ki]) {
-                    CU(cudaFuncSetAttribute(duo_fn[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-                    dev.attr_set_duo[ki] = true;
-                }
-                cudaStream_t st = dev.aux[rr++ % kAux];
-                const int threads = (L.n + 1) / 2;
-                duo_fn[ki]<<<(threads + kDuoThreads - 1) / kDuoThreads, kDuoThreads, L.smem, st>>>(
-                    s.d_meta, s.d_ord + s.cap_pairs + L.first, s.d_blob, s.d_out, L.n_wide, L.n - L.n_wide, h->K,
-                    L.duo_el);
             } else if (L.smem) {
                 // keyed row argmax when the launch's scores and group indices share 16 bits
                 // (a query of this launch has at most 4 * row_el - 1 bases: groups 0 .. 2 * row_el - 1)
@@ -1318,6 +1294,23 @@ int bsw_gpu_dpx_peak(int device, int which, double *ginstr_per_s, double *sm_mhz
             if (sm_mhz_est) *sm_mhz_est = (double)prop.clockRate / 1000.0;
             return BSW_OK;
         }
+        case 10: case 11: {   // one inner-loop trip of the two-pairs-per-thread kernel on registers: giga CELLS per second
+            const int b2 = which == 10 ? blocks : prop.multiProcessorCount * 5, t2 = which == 10 ? threads : 32;
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            bsw_duo_trip_peak_kernel<<<b2, t2>>>(sink, 16, 3u, 65536u, 2u, 1u, 256u);
+            cudaEventRecord(a);
+            bsw_duo_trip_peak_kernel<<<b2, t2>>>(sink, iters * 4, 3u, 65536u, 2u, 1u, 256u);
+            cudaEventRecord(b);
+            rc = cudaEventSynchronize(b) == cudaSuccess ? 0 : 1;
+            cudaEventElapsedTime(&ms, a, b);
+            cudaEventDestroy(a); cudaEventDestroy(b);
+            cudaFree(sink);
+            if (rc) return BSW_ERR_CUDA;
+            *ginstr_per_s = (double)iters * 4.0 * 8.0 * (double)t2 * (double)b2 / (ms * 1e-3) / 1e9;
+            if (sm_mhz_est) *sm_mhz_est = (double)prop.clockRate / 1000.0;
+            return BSW_OK;
+        }
         default: cudaFree(sink); return BSW_ERR_ARG;
     }
     cudaFree(sink);
@@ -1327,6 +1320,33 @@ int bsw_gpu_dpx_peak(int device, int which, double *ginstr_per_s, double *sm_mhz
     double total = per_thread * (double)threads * (double)blocks;
     *ginstr_per_s = total / (ms * 1e-3) / 1e9;
     if (sm_mhz_est) *sm_mhz_est = (double)prop.clockRate / 1000.0;
+    return BSW_OK;
+}
+
+// Developer probe: the register-only trip loops (kind 0: extend_pair's keyed trip, 1: extend_duo2's) at a given
+// number of one-warp blocks per SM -> giga cells per second. Shows how many warps each loop needs.
+int bsw_gpu_trip_probe(int device, int kind, int warps_per_sm, double *gcells_per_s) {
+    if (!gcells_per_s || warps_per_sm < 1 || warps_per_sm > 32) return BSW_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return BSW_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BSW_ERR_NO_DEVICE;
+    uint32_t *sink = nullptr;
+    if (cudaMalloc((void **)&sink, 4096) != cudaSuccess) return BSW_ERR_NOMEM;
+    const int blocks = prop.multiProcessorCount * warps_per_sm, iters = 1 << 16;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float ms = 0.f;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(a);
+        if (kind == 0) bsw_trip_peak_kernel<<<blocks, 32>>>(sink, iters, 3u, 65536u, 2u, 1u, 128u);
+        else bsw_duo_trip_peak_kernel<<<blocks, 32>>>(sink, iters, 3u, 65536u, 2u, 1u, 256u);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(sink);
+    *gcells_per_s = (double)iters * 8.0 * 32.0 * (double)blocks / (ms * 1e-3) / 1e9;
     return BSW_OK;
 }
 

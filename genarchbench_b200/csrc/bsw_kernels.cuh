@@ -24,8 +24,8 @@
 //  * packed sequences (2-bit, or 4-bit when a pair holds an ambiguous base) sit in 16-byte aligned
 //    slots of the slab blob; each thread expands its query into selector seeds once per pair and
 //    reads its target 16 rows at a time.
-//  * bsw_key_kernel + cub radix sort bin the pairs by length on the device; extend_duo
-//    (bsw_pair2.cuh) is an evaluated alternative with two pairs per thread.
+//  * bsw_key_kernel + cub radix sort bin the pairs by length on the device; extend_duo2
+//    (bsw_duo.cuh) is an evaluated alternative with two pairs per thread.
 // The BSW_* macros below are the A/B switches of the experiments recorded in DESIGN.md 5.6.
 #pragma once
 #include <stdint.h>
@@ -864,7 +864,6 @@ __device__ inline PairResult extend_pair(const Rows &R, int qlen, int tlen, int 
 }
 
 }  // namespace bswk
-#include "bsw_pair2.cuh"
 #include "bsw_duo.cuh"
 namespace bswk {
 
@@ -966,52 +965,7 @@ bsw_win_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ o
 }
 
 // ---------------------------------------------------------------------------------------------
-// Short pairs, two per thread (extend_duo, bsw_pair2.cuh). Launch: block = kDuoThreads, dynamic smem =
-// 20 * elems * kDuoThreads. Thread t takes the launch's sorted pairs 2t and 2t + 1 (neighbours in
-// (len2, len1, h0) order). A warp whose first thread still falls among the n_wide pairs holding an
-// ambiguous base runs the LOP3-selector instantiation for all of its threads.
-// ---------------------------------------------------------------------------------------------
-constexpr int kDuoThreads = 64;
-
-template <bool FASTM, bool SYM, bool COUNT>
-__global__ void __launch_bounds__(kDuoThreads)
-bsw_duo_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ ord,
-               const uint32_t *__restrict__ blob, PairOut *__restrict__ out, int n_wide, int n_narrow,
-               KParams P, int elems) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int NT = kDuoThreads;
-    const int tid = threadIdx.x;
-    const int t = blockIdx.x * NT + tid;
-    const int n = n_wide + n_narrow;
-    if (2 * t >= n) return;
-    const bool twide = 2 * (t & ~31) < n_wide;       // warp-uniform
-    const PairMeta mA = meta[ord[2 * t]];
-    const bool hasB = 2 * t + 1 < n;
-    PairMeta mB = mA;
-    if (hasB) mB = meta[ord[2 * t + 1]];
-
-    Rows2 R;
-    R.stride = NT;
-    R.he4 = reinterpret_cast<uint4 *>(smem) + tid;
-    R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)16 * elems * NT) + tid;
-
-    DuoLane L[2];
-    L[0].qlen = mA.len2; L[0].tlen = mA.len1; L[0].h0 = mA.h0; L[0].wide_blob = mA.flags & 1;
-    L[1].qlen = hasB ? mB.len2 : 0; L[1].tlen = hasB ? mB.len1 : 0; L[1].h0 = hasB ? mB.h0 : 0;
-    L[1].wide_blob = hasB && (mB.flags & 1);
-    const uint32_t *bA = blob + mA.off, *bB = blob + mB.off;
-    if (L[0].wide_blob) bA = blob + bA[0];
-    if (L[1].wide_blob) bB = blob + bB[0];
-    duo_unpack(bA, bB, L, R);
-    PairResult r[2];
-    if (twide) extend_duo<FASTM, SYM, COUNT, true>(R, L, P, r);
-    else extend_duo<FASTM, SYM, COUNT, false>(R, L, P, r);
-    store_result(out, mA.id, r[0]);
-    if (hasB) store_result(out, mB.id, r[1]);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Short pairs, two per thread, second generation (extend_duo2, bsw_duo.cuh). Launch: block = kDuo2Threads, dynamic
+// Short pairs, two per thread (extend_duo2, bsw_duo.cuh; an evaluated alternative). Launch: block = kDuo2Threads, dynamic
 // smem = 40 * nblk * kDuo2Threads (nblk = duo_blocks(longest query of the launch)). Thread t takes the launch's
 // sorted pairs 2t and 2t + 1 (neighbours in (len2, len1, h0) order). A warp whose first thread still falls among
 // the n_wide pairs holding an ambiguous base runs the LOP3-selector instantiation for all of its threads.
@@ -1042,6 +996,7 @@ bsw_duo2_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     R.stride = NT;
     R.he4 = reinterpret_cast<uint4 *>(smem) + tid;
     R.qs = reinterpret_cast<uint2 *>(smem + (size_t)32 * nblk * NT) + tid;
+    R.sbase = (uint32_t)__cvta_generic_to_shared(R.he4);
 
     DuoIn L[2];
     L[0].qlen = mA.len2; L[0].tlen = mA.len1; L[0].h0 = mA.h0; L[0].wide = mA.flags & 1;
@@ -1483,6 +1438,46 @@ __global__ void bsw_trip_peak_kernel(uint32_t *sink, int iters, uint32_t seed, u
         tsel += 0x01010101u & (uint32_t)it;
     }
     if ((rm ^ A) == 0x12345678u) sink[threadIdx.x] = rm;
+}
+
+// WHICH == 10 / 11 of bsw_gpu_dpx_peak: the arithmetic of one inner-loop trip of extend_duo2<.., KEY> (four
+// columns of two pairs = eight cells: selector, PRMT, M, T, E', H, F', keyed row max) on registers only; 10 at
+// full occupancy, 11 at five one-warp blocks per SM (what the shared memory of the longest config-3 bins allows).
+__global__ void bsw_duo_trip_peak_kernel(uint32_t *sink, int iters, uint32_t seed, uint32_t k16, uint32_t km, uint32_t k1,
+                                         uint32_t kk) {
+    uint32_t hd[4], ev[4], q[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hd[k] = (seed * (k + 3) + threadIdx.x) & 0x00FF00FFu; ev[k] = (seed * (k + 7)) & 0x003F003Fu; }
+    q[0] = 0x11002233u & (seed | 0x33333333u); q[1] = 0x22113300u;
+    const uint32_t LUT_LO = 0xFCFCFCFCu, LUT_HI = 0xFCFCFC01u, NEG_OE = pack2(-7), NEG_E = pack2(-1);
+    uint32_t rm = 0, F = 0, hprev = 0, tsel = 0x94949494u, J2 = 0;
+    {
+        const uint32_t z = *reinterpret_cast<const volatile uint32_t *>(&g_zero);
+        k16 ^= z; km ^= z; k1 ^= z; kk ^= z;
+    }
+    for (int it = 0; it < iters; ++it) {
+        uint32_t s[4], hv[4];
+        s[0] = q[0] * k1 + tsel; s[1] = __umulhi(s[0], k16);
+        s[2] = q[1] * k1 + tsel; s[3] = __umulhi(s[2], k16);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t sc = prmt_sx(LUT_LO, LUT_HI, s[u]);
+            const uint32_t M = __viaddmin_s16x2(hd[u], sc, hd[u] * km);
+            const uint32_t T = __viaddmax_s16x2_relu(M, NEG_OE, NEG_OE);
+            const uint32_t En = __viaddmax_s16x2(ev[u], NEG_E, T);
+            hv[u] = __vimax3_s16x2(M, ev[u], F);
+            F = __viaddmax_s16x2(F, NEG_E, T);
+            hd[u] = hprev;          // next "row" reads what this one stored
+            hprev = hv[u];
+            ev[u] = En;
+        }
+        const uint32_t t3 = __vimax3_u16x2(hv[0] * kk, hv[1] * kk + 0x00010001u, hv[2] * kk + 0x00020002u);
+        const uint32_t t4 = __vmaxu2(t3, hv[3] * kk + 0x00030003u);
+        rm = __viaddmax_u16x2(t4, J2, rm);
+        J2 += 0x00040004u;
+        tsel += 0x01010101u & (uint32_t)it;
+    }
+    if ((rm ^ F) == 0x12345678u) sink[threadIdx.x] = rm;
 }
 
 #endif  // !BSW_HOST_EMUL

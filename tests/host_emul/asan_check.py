@@ -13,7 +13,7 @@ from genarchbench_b200 import pairio  # noqa: E402
 
 L = C.CDLL(sys.argv[1])
 total = 0
-for name in ("bsw_emul_batch", "bsw_emul_batch_key", "bsw_emul_batch_win", "bsw_emul_batch_duo"):
+for name in ("bsw_emul_batch", "bsw_emul_batch_key", "bsw_emul_batch_win", "bsw_emul_batch_duo", "bsw_emul_batch_duo_key"):
     fn = getattr(L, name)
     fn.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_int32]
     for w in (1, 3, 17, 100):

@@ -9,6 +9,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __align__(n) alignas(n)
 #define __restrict__
 

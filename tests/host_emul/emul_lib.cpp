@@ -10,67 +10,7 @@
 
 using namespace bswk;
 
-// Two pairs per thread (extend_duo): consecutive pairs of the caller's order share a "thread".
-extern "C" int bsw_emul_batch_duo(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
-                                  const uint8_t *qer, int64_t n, int32_t w) {
-    KParams K{p->o_del, p->e_del, p->o_ins, p->e_ins, p->zdrop, p->end_bonus, p->match, p->mismatch, p->ambig, w,
-              max_score_of(p->match, p->mismatch, p->ambig), 65536u, (uint32_t)(p->match + 1), 1u};
-    const bool sym = p->o_del == p->o_ins && p->e_del == p->e_ins;
-#pragma omp parallel
-    {
-        std::vector<uint4> he;
-        std::vector<uint32_t> qs, blob[2];
-#pragma omp for schedule(dynamic, 128)
-        for (int64_t k = 0; k < n; k += 2) {
-            DuoLane L[2];
-            bool anywide = false, fast = true;
-            int qmax = 0;
-            for (int a = 0; a < 2; ++a) {
-                const bool has = k + a < n;
-                bsw_seqpair sp = has ? pairs[k + a] : bsw_seqpair{};
-                L[a].qlen = has ? sp.len2 : 0; L[a].tlen = has ? sp.len1 : 0; L[a].h0 = has ? sp.h0 : 0;
-                blob[a].assign((size_t)(seq_bytes(sp.len2, true) + seq_bytes(sp.len1, true)) / 4 + 4, 0);
-                uint8_t *b = reinterpret_cast<uint8_t *>(blob[a].data());
-                bool wide = false;
-                if (has) {
-                    wide = pack2bit(qer + sp.idq, sp.len2, b);
-                    wide |= pack2bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, false));
-                    if (wide) {
-                        pack4bit(qer + sp.idq, sp.len2, b);
-                        pack4bit(ref + sp.idr, sp.len1, b + seq_bytes(sp.len2, true));
-                    }
-                    fast = fast && (int64_t)(sp.h0 + sp.len2 * p->match) * (p->match + 1) <= 32767;
-                }
-                L[a].wide_blob = wide;
-                anywide |= wide;
-                qmax = std::max(qmax, L[a].qlen);
-            }
-            if (getenv("BSW_EMUL_SLOWM")) fast = false;
-            he.assign((size_t)duo_elems(qmax), uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
-            qs.assign((size_t)duo_elems(qmax), 0xDEADBEEFu);
-            Rows2 R{he.data(), qs.data(), 1};
-            duo_unpack(blob[0].data(), blob[1].data(), L, R);
-            PairResult r[2];
-#define ED(F, S) (anywide ? extend_duo<F, S, true, true>(R, L, K, r) : extend_duo<F, S, true, false>(R, L, K, r))
-            if (fast) { if (sym) ED(true, true); else ED(true, false); }
-            else { if (sym) ED(false, true); else ED(false, false); }
-#undef ED
-            for (int a = 0; a < 2 && k + a < n; ++a) {
-                bsw_seqpair &sp = pairs[k + a];
-                if (sp.len1 == 0 || sp.len2 == 0) {
-                    sp.score = sp.h0; sp.qle = sp.tle = sp.gtle = 0; sp.gscore = -1; sp.max_off = 0;
-                    continue;
-                }
-                sp.score = r[a].score; sp.qle = r[a].qle; sp.tle = r[a].tle; sp.gtle = r[a].gtle;
-                sp.gscore = r[a].gscore; sp.max_off = r[a].max_off;
-                sp.seqid = (int32_t)r[a].cells;
-            }
-        }
-    }
-    return 0;
-}
-
-// Two pairs per thread, second generation (extend_duo2, bsw_duo.cuh): consecutive pairs of the caller's order
+// Two pairs per thread (extend_duo2, bsw_duo.cuh): consecutive pairs of the caller's order
 // share a "thread". key = true: threads whose scores and column indices fit the 16-bit key run the KEY variant
 // (seqid = -1 marks those pairs).
 extern "C" int bsw_emul_batch_duo2(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
@@ -117,7 +57,7 @@ extern "C" int bsw_emul_batch_duo2(const bsw_params *p, bsw_seqpair *pairs, cons
             // never initialised shows up as a mismatch
             he.assign((size_t)2 * duo_blocks(qmax), uint4{0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu});
             qs.assign((size_t)duo_blocks(qmax), uint2{0xDEADBEEFu, 0xDEADBEEFu});
-            RowsD R{he.data(), qs.data(), 1};
+            RowsD R{he.data(), qs.data(), 1, 0u};
             PairResult r[2];
             KParams K = K0;
             const int kbits = bits_for((uint32_t)(4 * duo_blocks(qmax) - 1));   // masked blocks index up to the block end
@@ -141,6 +81,15 @@ extern "C" int bsw_emul_batch_duo2(const bsw_params *p, bsw_seqpair *pairs, cons
         }
     }
     return 0;
+}
+
+extern "C" int bsw_emul_batch_duo(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
+                                  const uint8_t *qer, int64_t n, int32_t w) {
+    return bsw_emul_batch_duo2(p, pairs, ref, qer, n, w, 0);
+}
+extern "C" int bsw_emul_batch_duo_key(const bsw_params *p, bsw_seqpair *pairs, const uint8_t *ref,
+                                      const uint8_t *qer, int64_t n, int32_t w) {
+    return bsw_emul_batch_duo2(p, pairs, ref, qer, n, w, 1);
 }
 
 // key = true: pairs whose scores and group indices fit the 16-bit key run extend_pair<.., KEY> (with the

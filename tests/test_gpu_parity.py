@@ -370,6 +370,28 @@ def test_in_process_multi_gpu_split():
     assert_same_outputs(out[idx], samp.outputs(), samp, "multi-GPU split, sampled")
 
 
+def test_two_pairs_per_thread_kernel_matches_oracle():
+    """BSW_DUO2=1 routes the short bins to extend_duo2 (bsw_duo.cuh: the two DPX lanes are the same cell of two
+    neighbouring pairs; an evaluated alternative, off by default). The switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import numpy as np, oracle\n"
+        "from genarchbench_b200 import bsw, pairio\n"
+        "bad = 0\n"
+        "for cfg, n, w in ((1, 200000, 100), (4, 20000, 100), (4, 20000, 7)):\n"
+        "    b = pairio.generate(cfg, n, seed=90 + cfg); a = b.copy(); oracle.oracle_batch(a, w=w)\n"
+        "    g = bsw.BswGpu(); g.batch(b.pairs, b.ref, b.qer, w); st = g.stats(); g.close()\n"
+        "    assert st['pairs_duo'] > 0, st\n"
+        "    bad += int((a.outputs() != b.outputs()).any(axis=1).sum())\n"
+        "print('MISMATCHES', bad)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, BSW_DUO2="1", BSW_DUO2_MINWARPS="1"))
+    assert r.returncode == 0 and "MISMATCHES 0" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
 def test_dpx_peak_is_measurable():
     v = bsw.dpx_peak(0)
     assert 5e3 < v < 1e5                                        # giga thread-instructions / s

@@ -25,6 +25,7 @@ def emul():
     L = C.CDLL(so)
     L.bsw_emul_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
     L.bsw_emul_batch_duo.argtypes = L.bsw_emul_batch.argtypes
+    L.bsw_emul_batch_duo_key.argtypes = L.bsw_emul_batch.argtypes
     L.bsw_emul_batch_win.argtypes = L.bsw_emul_batch.argtypes
     L.bsw_emul_batch_key.argtypes = L.bsw_emul_batch.argtypes
     L.bsw_emul_pack_check.argtypes = [C.c_int64, C.c_uint32]
@@ -33,7 +34,7 @@ def emul():
     def run(b, w=100, params=None, duo=False, win=False, key=False):
         fn = L.bsw_emul_batch_duo if duo else (L.bsw_emul_batch_win if win else L.bsw_emul_batch)
         if key:
-            fn = L.bsw_emul_batch_key
+            fn = L.bsw_emul_batch_duo_key if duo else L.bsw_emul_batch_key
         fn(oracle._params_array(params), b.pairs.ctypes.data, b.ref.ctypes.data, b.qer.ctypes.data, len(b), w)
         return b.outputs()
     run.lib = L
@@ -87,22 +88,43 @@ def test_keyed_argmax_matches_oracle(emul, w):
     assert 0.3 * len(b) < keyed < len(b), keyed      # both the keyed and the general path were exercised
 
 
+@pytest.mark.parametrize("key", [False, True])
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_duo_code_matches_golden(emul, name):
-    """Two pairs per thread (extend_duo): neighbours in the fixture's order share the DPX lanes."""
+def test_duo_code_matches_golden(emul, name, key):
+    """Two pairs per thread (extend_duo2): neighbours in the fixture's order share the DPX lanes."""
     b, w, params, want = load_golden(name)
-    assert_same_outputs(emul(b, w, params, duo=True), want, b, f"emulated duo kernel vs golden[{name}]")
+    assert_same_outputs(emul(b, w, params, duo=True, key=key), want, b, f"emulated duo kernel vs golden[{name}]")
 
 
+@pytest.mark.parametrize("key", [False, True])
+@pytest.mark.parametrize("sort", [False, True])
 @pytest.mark.parametrize("w", [1, 2, 5, 17, 100])
-def test_duo_code_matches_oracle_on_small_bands(emul, w):
+def test_duo_code_matches_oracle_on_small_bands(emul, w, sort, key):
+    """Unsorted neighbours (lengths, seeds and ends all differ: masked blocks, ghost lanes) and neighbours
+    in the device's (len2, len1, h0) launch order (equal ends, the fast trips)."""
     c = pairio.preset(4)
     c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 200, 0, 60, 0.3, 0.2
     b = pairio.generate(c, 6001, seed=300 + w)                # odd count: the last thread has one pair
+    if sort:
+        o = np.lexsort((b.pairs["h0"], b.pairs["len1"], b.pairs["len2"]))
+        b = pairio.PairBatch(b.pairs[o].copy(), b.ref, b.qer)
     a = b.copy()
-    cells = oracle.oracle_batch(a, w=w)
-    assert_same_outputs(emul(b, w, duo=True), a.outputs(), b, f"emulated duo kernel vs oracle, w={w}")
-    assert int(b.pairs["seqid"].astype(np.int64).sum()) == cells  # COUNT variant: the reference's cells
+    oracle.oracle_batch(a, w=w)
+    assert_same_outputs(emul(b, w, duo=True, key=key), a.outputs(), b, f"emulated duo kernel vs oracle, w={w}")
+    if key:
+        assert int((b.pairs["seqid"] == -1).sum()) > 0.9 * len(b)
+
+
+def test_duo_code_nondefault_scoring(emul):
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 150, 0, 100, 0.2, 0.2
+    b0 = pairio.generate(c, 5000, seed=11)
+    for params in (dict(o_del=5, e_del=2, o_ins=7, e_ins=1, zdrop=40, end_bonus=9, match=2, mismatch=3, ambig=-1),
+                   dict(o_del=6, e_del=1, o_ins=6, e_ins=1, zdrop=0, end_bonus=5, match=1, mismatch=4, ambig=-1)):
+        for key in (False, True):
+            a = b0.copy(); b = b0.copy()
+            oracle.oracle_batch(a, w=30, params=params)
+            assert_same_outputs(emul(b, 30, params, duo=True, key=key), a.outputs(), b, f"emulated duo kernel, {params}")
 
 
 @pytest.mark.parametrize("w", [1, 2, 5, 17, 100])
