@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .pairio import PairBatch, SEQPAIR_DTYPE
+from .pairio import PairBatch, SEQPAIR_DTYPE, PACKED_REC_DTYPE, RESULT_DTYPE
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # BSW_GPU_LIB: developer override used by scripts/ to A/B kernel builds; the product loads lib/libbsw_gpu.so
@@ -28,7 +28,8 @@ ERRORS = {1: "BSW_ERR_ARG", 2: "BSW_ERR_NO_DEVICE", 3: "BSW_ERR_CUDA", 4: "BSW_E
           5: "BSW_ERR_RANGE", 6: "BSW_ERR_STATE"}
 
 # every symbol include/bsw_gpu.h declares
-EXPORTS = ("bsw_gpu_init", "bsw_gpu_init_devices", "bsw_gpu_free", "bsw_gpu_reserve", "bsw_gpu_batch", "bsw_gpu_batch_retry", "bsw_gpu_stage",
+EXPORTS = ("bsw_gpu_init", "bsw_gpu_init_devices", "bsw_gpu_free", "bsw_gpu_reserve", "bsw_gpu_batch", "bsw_gpu_batch_retry",
+           "bsw_gpu_batch_packed", "bsw_gpu_host_alloc", "bsw_gpu_host_free", "bsw_gpu_stage",
            "bsw_gpu_run_staged", "bsw_gpu_fetch_staged", "bsw_gpu_count_staged", "bsw_gpu_get_stats", "bsw_gpu_dpx_peak",
            "bsw_gpu_strerror", "bsw_gpu_last_error", "bsw_gpu_version")
 
@@ -77,6 +78,11 @@ def lib() -> C.CDLL:
         L.bsw_gpu_reserve.argtypes = [vp, i64, i64]
         L.bsw_gpu_batch.argtypes = [vp, vp, vp, vp, i64, i32]
         L.bsw_gpu_batch_retry.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp]
+        L.bsw_gpu_batch_packed.argtypes = [vp, vp, vp, i64, i64, i32, vp]
+        L.bsw_gpu_host_alloc.argtypes = [C.c_size_t]
+        L.bsw_gpu_host_alloc.restype = vp
+        L.bsw_gpu_host_free.argtypes = [vp]
+        L.bsw_gpu_host_free.restype = None
         L.bsw_gpu_stage.argtypes = [vp, vp, vp, vp, i64, i32]
         L.bsw_gpu_run_staged.argtypes = [vp, C.POINTER(C.c_float)]
         L.bsw_gpu_fetch_staged.argtypes = [vp, vp, i64]
@@ -139,6 +145,17 @@ class BswGpu:
         self._check(self._L.bsw_gpu_batch_retry(self._h, a, b, c, len(pairs), w, max_tries, tries.ctypes.data))
         return tries
 
+    def batch_packed(self, rec: np.ndarray, data: np.ndarray, w: int = DEFAULT_W,
+                     out: Optional[np.ndarray] = None) -> np.ndarray:
+        """bsw_gpu_batch_packed: packed records + 2-bit / 4-bit sequences in, 16-byte result records out."""
+        assert rec.dtype == PACKED_REC_DTYPE and rec.flags["C_CONTIGUOUS"] and data.dtype == np.uint8
+        if out is None:
+            out = np.zeros(len(rec), dtype=RESULT_DTYPE)
+        assert out.dtype == RESULT_DTYPE and len(out) >= len(rec)
+        self._check(self._L.bsw_gpu_batch_packed(self._h, rec.ctypes.data, data.ctypes.data, data.nbytes, len(rec), w,
+                                                 out.ctypes.data))
+        return out
+
     def stage(self, pairs: np.ndarray, ref: np.ndarray, qer: np.ndarray, w: int = DEFAULT_W) -> None:
         a, b, c = self._ptrs(pairs, ref, qer)
         self._check(self._L.bsw_gpu_stage(self._h, a, b, c, len(pairs), w))
@@ -178,6 +195,37 @@ class BswGpu:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class _Pinned:
+    """Keeps a bsw_gpu_host_alloc block alive for the numpy array that views it."""
+    def __init__(self, nbytes: int):
+        self.ptr = lib().bsw_gpu_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError(f"bsw_gpu_host_alloc({nbytes})")
+
+    def __del__(self):
+        try:
+            lib().bsw_gpu_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def host_alloc(nbytes: int) -> np.ndarray:
+    """Page-locked uint8 array (bsw_gpu_host_alloc): packed inputs / result arrays placed here are DMA'd in place."""
+    blk = _Pinned(max(nbytes, 1))
+    arr = np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(blk.ptr))
+    arr = arr[:nbytes]
+    _keep[arr.ctypes.data] = blk
+    return arr
+
+
+_keep: dict = {}
+
+
+def results_to_outputs(res: np.ndarray) -> np.ndarray:
+    """bsw_result records -> [n, 6] int32 in the order of pairio.OUTPUT_FIELDS."""
+    return np.stack([res[f].astype(np.int32) for f in ("score", "qle", "tle", "gtle", "gscore", "max_off")], axis=1)
 
 
 def dpx_peak(which: int = 0, device: int = 0) -> float:

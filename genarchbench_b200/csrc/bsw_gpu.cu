@@ -79,6 +79,7 @@ struct Slab {
     // capacity
     int64_t cap_pairs = 0;
     size_t cap_blob = 0, cap_scratch = 0;
+    size_t cap_dblob = 0;            // capacity of d_blob (>= cap_blob: packed input with page-locked data grows it alone)
     // pinned host
     PairMeta *h_meta = nullptr;
     uint32_t *h_blob = nullptr;
@@ -217,11 +218,25 @@ int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
             s.h_blob = nullptr;
             CU(cudaHostAlloc((void **)&s.h_blob, cap, cudaHostAllocDefault));
         }
-        if (s.d_blob) cudaFree(s.d_blob);
-        s.d_blob = nullptr;
-        CU(cudaMalloc((void **)&s.d_blob, cap));
+        if (cap > s.cap_dblob) {
+            if (s.d_blob) cudaFree(s.d_blob);
+            s.d_blob = nullptr; s.cap_dblob = 0;
+            CU(cudaMalloc((void **)&s.d_blob, cap));
+            s.cap_dblob = cap;
+        }
         s.cap_blob = cap;
     }
+    return BSW_OK;
+}
+
+// device blob only (packed input read in place from page-locked memory needs no pinned staging copy)
+int ensure_dblob(bsw_handle *h, Slab &s, size_t bytes) {
+    if (bytes <= s.cap_dblob) return BSW_OK;
+    if (s.d_blob) cudaFree(s.d_blob);
+    s.d_blob = nullptr; s.cap_dblob = 0;
+    const size_t cap = bytes + (bytes >> 4) + 4096;
+    CU(cudaMalloc((void **)&s.d_blob, cap));
+    s.cap_dblob = cap;
     return BSW_OK;
 }
 
@@ -303,6 +318,8 @@ inline void scatter_chunk(const ScatterJob &j, int c) {
         p.gtle = o.gtle; p.gscore = o.gscore; p.max_off = o.max_off;
     }
 }
+
+void plan_slab(bsw_handle *h, Slab &s, int T, int maxq);
 
 int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t *ref,
                  const uint8_t *qer, int64_t lo, int n, const ScatterJobs &jobs) {
@@ -455,7 +472,15 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     s.n_dev = n - (int)s.trivial.size();
     st.host_pack_ms += ms_since(t0);
     t0 = Clock::now();
+    plan_slab(h, s, T, maxq);
+    st.host_plan_ms += ms_since(t0);
+    return BSW_OK;
+}
 
+// The launch plan of a slab from the per-thread (wide, len2 bin) histograms in h->hist (T threads) and the slab's
+// longest query; also fixes the sort key layout (s.key_b1 / key_b0 must be set).
+void plan_slab(bsw_handle *h, Slab &s, int T, int maxq) {
+    s.launches.clear();
     // ---- plan: one launch per query-length bin, longest first, the wide pairs of a bin in front
     // (== the device sort order: key descending). The bins that run on windowed rows need the same
     // shared memory whatever their query length, so they are merged into ONE launch at the front (the sort
@@ -535,8 +560,6 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     }
     // sort key layout (see sort_key)
     s.key_bits = s.key_b1 + s.key_b0 + (s.long_bin0 != 0x7FFFFFFF ? 17 : bits_for(((((uint32_t)std::max(maxq, 1) - 1) >> 4) << 5) | 31u));
-    st.host_plan_ms += ms_since(t0);
-    return BSW_OK;
 }
 
 // prepare_slab with the (rare) capacity retry: the first pass over a slab whose blob does not fit the
@@ -1140,6 +1163,233 @@ int bsw_gpu_batch_retry(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, c
     total.pairs = n;
     h->stats = total;
     return BSW_OK;
+}
+
+// ---- packed input (the pair-file ingest path) -----------------------------------------
+// The caller hands over what a BSWPAIR1 file holds (include/bsw_pairio.h) -- 12-byte records and the sequences at
+// 2 bits per base (4 for a pair holding an ambiguous base), query then target, each padded to 4 bytes -- and gets
+// 16-byte result records back. The packed data IS the device blob: the host only turns the records into PairMeta
+// (a prefix sum of the pairs' sizes, the launch histogram) and starts the copies. When `data` / `out` are
+// page-locked (bsw_gpu_host_alloc, or registered by the caller) they are DMA'd in place; otherwise they go
+// through the slab's pinned staging buffers.
+
+namespace {
+
+inline bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+inline uint32_t rec_words(const bsw_packed_rec &r) {
+    const bool wide = r.flags & 1u;
+    return (seq_bytes(r.len2, wide) + seq_bytes(r.len1, wide)) >> 2;
+}
+
+struct PackedSlabOut {       // where a slab's results go once its stream is done
+    bsw_result *dst = nullptr;   // null: the device wrote straight into the caller's (pinned) array
+    int n = 0;
+};
+
+}  // namespace
+
+void *bsw_gpu_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void bsw_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t *data, int64_t data_bytes,
+                         int64_t n, int32_t w, bsw_result *out) {
+    static_assert(sizeof(bsw_packed_rec) == 12 && sizeof(bsw_result) == sizeof(PairOut), "packed layouts");
+    if (!h || n < 0 || w < 0 || data_bytes < 0 || (n > 0 && (!rec || !out || (!data && data_bytes > 0)))) return BSW_ERR_ARG;
+    if (((uintptr_t)data & 3u) != 0) return BSW_ERR_ARG;
+    auto t_all = Clock::now();
+    const int ng = (int)h->devs.size();
+    bsw_gpu_stats &st = h->stats;
+    st.pairs = n; st.kernel_launches = 0; st.h2d_bytes = 0; st.d2h_bytes = 0;
+    st.pairs_short = 0; st.pairs_long = 0; st.pairs_keyed = 0; st.pairs_duo = 0;
+    st.host_bin_ms = st.host_pack_ms = st.host_scatter_ms = st.kernel_ms = 0;
+    st.host_sort_ms = st.host_plan_ms = st.host_alloc_ms = st.host_cut_ms = st.host_wait_ms = 0;
+    h->K.w = w;
+    if (n == 0) { st.wall_ms = 0; return BSW_OK; }
+    const int T = omp_get_max_threads();
+    const int match = h->P.match;
+
+    // ---- sizes: words per chunk of 4096 pairs (validated on the way), prefix over the chunks
+    constexpr int64_t kChunk = 4096;
+    const int64_t nchunks = (n + kChunk - 1) / kChunk;
+    std::vector<uint64_t> cw((size_t)nchunks + 1, 0);
+    int bad = 0;
+    auto t0 = Clock::now();
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t c = 0; c < nchunks; ++c) {
+        uint64_t wsum = 0;
+        const int64_t hi = std::min(n, (c + 1) * kChunk);
+        for (int64_t k = c * kChunk; k < hi; ++k) {
+            const bsw_packed_rec &r = rec[k];
+            if (r.len1 > BSW_MAX_SEQ_LEN || r.len2 > BSW_MAX_SEQ_LEN || r.h0 < 0 ||
+                (int64_t)r.h0 + (int64_t)r.len2 * match > 32767) bad |= 1;
+            wsum += rec_words(r);
+        }
+        cw[(size_t)c + 1] = wsum;
+    }
+    if (bad) return BSW_ERR_RANGE;
+    for (int64_t c = 0; c < nchunks; ++c) cw[(size_t)c + 1] += cw[(size_t)c];
+    if ((int64_t)cw[(size_t)nchunks] * 4 > data_bytes) return BSW_ERR_ARG;
+    // ---- slabs: whole chunks, at most slab_pairs(false) pairs and kSlabBases / 4 packed bytes
+    std::vector<int64_t> cuts{0};
+    {
+        const int64_t full = slab_pairs(false);
+        int64_t c0 = 0;
+        for (int64_t c = 1; c <= nchunks; ++c) {
+            const int64_t pairs_in = std::min(n, c * kChunk) - c0 * kChunk;
+            const uint64_t bytes_in = (cw[(size_t)c] - cw[(size_t)c0]) * 4;
+            if (c == nchunks || pairs_in + kChunk > full || bytes_in >= (uint64_t)kSlabBases / 4) { cuts.push_back(c); c0 = c; }
+        }
+    }
+    st.host_cut_ms = ms_since(t0);
+    const bool data_pinned = is_pinned(data), out_pinned = is_pinned(out);
+    const int nslabs = (int)cuts.size() - 1;
+    std::vector<double> kms((size_t)ng, 0.0);
+    std::vector<PackedSlabOut> pending((size_t)ng * kRing);
+    int rc = BSW_OK;
+
+    // waits for a ring slot's previous slab and delivers its results
+    auto finish = [&](int d, int r) -> int {
+        Slab &s = h->devs[(size_t)d].ring[r];
+        if (!s.busy) return BSW_OK;
+        auto tw = Clock::now();
+        const int e = cuda_rc(h, cudaEventSynchronize(s.ev_done), "cudaEventSynchronize");
+        st.host_wait_ms += ms_since(tw);
+        s.busy = false;
+        if (e) return e;
+        if (s.n_dev) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) kms[(size_t)d] += ms;
+        }
+        PackedSlabOut &po = pending[(size_t)d * kRing + r];
+        if (po.dst) {
+            auto ts = Clock::now();
+            const char *src = reinterpret_cast<const char *>(s.h_out);
+            char *dst = reinterpret_cast<char *>(po.dst);
+            const size_t bytes = sizeof(PairOut) * (size_t)po.n;
+#pragma omp parallel for schedule(static)
+            for (int t = 0; t < T; ++t) {
+                const size_t a = bytes * (size_t)t / T & ~(size_t)63, b = t + 1 == T ? bytes : (bytes * (size_t)(t + 1) / T & ~(size_t)63);
+                memcpy(dst + a, src + a, b - a);
+            }
+            st.host_scatter_ms += ms_since(ts);
+            po.dst = nullptr;
+        }
+        return BSW_OK;
+    };
+
+    for (int sidx = 0; sidx < nslabs && rc == BSW_OK; ++sidx) {
+        const int d = sidx % ng, r = (sidx / ng) % kRing;
+        Device &dev = h->devs[(size_t)d];
+        Slab &s = dev.ring[r];
+        if ((rc = cuda_rc(h, cudaSetDevice(dev.id), "cudaSetDevice"))) break;
+        if ((rc = finish(d, r))) break;
+        const int64_t c_lo = cuts[(size_t)sidx], c_hi = cuts[(size_t)sidx + 1];
+        const int64_t lo = c_lo * kChunk;
+        const int ns = (int)(std::min(n, c_hi * kChunk) - lo);
+        const uint64_t w_lo = cw[(size_t)c_lo], words = cw[(size_t)c_hi] - w_lo;
+        if (words > 0xFFFFFF00ull) { rc = BSW_ERR_RANGE; break; }
+        t0 = Clock::now();
+        rc = ensure_slab(h, s, ns, data_pinned ? 0 : (size_t)words * 4 + 64);
+        if (!rc) rc = ensure_dblob(h, s, (size_t)words * 4 + 64);
+        st.host_alloc_ms += ms_since(t0);
+        if (rc) break;
+        // ---- records -> PairMeta in the caller's order (offsets: running sums inside each chunk), histograms
+        t0 = Clock::now();
+        s.lo = lo; s.n = ns; s.trivial.clear();
+        h->hist.assign((size_t)T * 2 * kMaxBins, 0);
+        int maxq = 0, maxsc = 0, maxt = 0, maxh = 0, ntriv = 0;
+#pragma omp parallel num_threads(T) reduction(max : maxq) reduction(max : maxsc) reduction(max : maxt) reduction(max : maxh) reduction(+ : ntriv)
+        {
+            uint32_t *hist = h->hist.data() + (size_t)omp_get_thread_num() * 2 * kMaxBins;
+#pragma omp for schedule(static)
+            for (int64_t c = c_lo; c < c_hi; ++c) {
+                uint64_t off = cw[(size_t)c] - w_lo;
+                const int64_t hi = std::min(n, (c + 1) * kChunk);
+                for (int64_t k = c * kChunk; k < hi; ++k) {
+                    const bsw_packed_rec &rr = rec[k];
+                    const uint32_t wide = rr.flags & 1u;
+                    PairMeta &m = s.h_meta[k - lo];
+                    m.off = (uint32_t)off;
+                    m.id = (uint32_t)(k - lo);
+                    m.len2 = rr.len2; m.len1 = rr.len1;
+                    m.h0 = (int16_t)rr.h0;
+                    m.flags = (uint16_t)(wide ? 3u : 0u);
+                    off += rec_words(rr);
+                    if (rr.len1 == 0 || rr.len2 == 0) { ++ntriv; continue; }
+                    hist[wide * kMaxBins + (uint32_t)(rr.len2 - 1) / kBinCols] += 1;
+                    maxq = std::max(maxq, (int)rr.len2);
+                    maxsc = std::max(maxsc, rr.h0 + (int)rr.len2 * match);
+                    maxt = std::max(maxt, (int)rr.len1);
+                    maxh = std::max(maxh, rr.h0);
+                }
+            }
+        }
+        s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
+        s.max_sc = maxsc;
+        s.key_b1 = bits_for((uint32_t)maxt);
+        s.key_b0 = bits_for((uint32_t)maxh);
+        s.n_dev = ns - ntriv;
+        s.blob_bytes = (size_t)words * 4;
+        plan_slab(h, s, T, maxq);
+        st.host_plan_ms += ms_since(t0);
+        // ---- the packed sequences: in place if page-locked, else through the slab's pinned blob
+        const uint8_t *src = data + (size_t)w_lo * 4;
+        if (!data_pinned && words) {
+            t0 = Clock::now();
+            char *dst = reinterpret_cast<char *>(s.h_blob);
+            const size_t bytes = (size_t)words * 4;
+#pragma omp parallel for schedule(static)
+            for (int t = 0; t < T; ++t) {
+                const size_t a = bytes * (size_t)t / T & ~(size_t)63, b = t + 1 == T ? bytes : (bytes * (size_t)(t + 1) / T & ~(size_t)63);
+                memcpy(dst + a, src + a, b - a);
+            }
+            src = reinterpret_cast<const uint8_t *>(s.h_blob);
+            st.host_pack_ms += ms_since(t0);
+        }
+        s.busy = true;      // (from here on work may be in flight on the slab's stream: see bsw_gpu_batch)
+        if ((rc = cuda_rc(h, cudaMemcpyAsync(s.d_meta, s.h_meta, sizeof(PairMeta) * (size_t)ns, cudaMemcpyHostToDevice, s.stream), "H2D meta"))) break;
+        if (words && (rc = cuda_rc(h, cudaMemcpyAsync(s.d_blob, src, (size_t)words * 4, cudaMemcpyHostToDevice, s.stream), "H2D blob"))) break;
+        // (the kernels read one word past a pair's target a refill period ahead)
+        if ((rc = cuda_rc(h, cudaMemsetAsync(reinterpret_cast<char *>(s.d_blob) + (size_t)words * 4, 0, 16, s.stream), "memset"))) break;
+        st.h2d_bytes += (int64_t)(sizeof(PairMeta) * (size_t)ns + (size_t)words * 4);
+        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k0, s.stream), "cudaEventRecord"))) break;
+        if (s.n_dev) {
+            if ((rc = bin_slab(h, s, s.stream))) break;
+            if ((rc = launch_slab(h, dev, s))) break;
+        } else if (ns) {   // only pairs with an empty sequence: the key kernel answers them
+            bsw_key_kernel<<<(ns + 255) / 256, 256, 0, s.stream>>>(s.d_meta, ns, s.d_keys, s.d_ord, s.key_b1, s.key_b0, s.long_bin0, s.d_out);
+        }
+        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k1, s.stream), "cudaEventRecord"))) break;
+        PackedSlabOut &po = pending[(size_t)d * kRing + r];
+        po.n = ns;
+        po.dst = out_pinned ? nullptr : out + lo;
+        if ((rc = cuda_rc(h, cudaMemcpyAsync(out_pinned ? reinterpret_cast<void *>(out + lo) : reinterpret_cast<void *>(s.h_out), s.d_out,
+                                             sizeof(PairOut) * (size_t)ns, cudaMemcpyDeviceToHost, s.stream), "D2H out"))) break;
+        st.d2h_bytes += (int64_t)(sizeof(PairOut) * (size_t)ns);
+        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_done, s.stream), "cudaEventRecord"))) break;
+    }
+    // drain (also on error, so that no stream still touches memory we or the caller may free)
+    for (int d = 0; d < ng; ++d) {
+        cudaSetDevice(h->devs[(size_t)d].id);
+        for (int r = 0; r < kRing; ++r) {
+            Slab &s = h->devs[(size_t)d].ring[r];
+            if (!s.busy) continue;
+            if (rc == BSW_OK) rc = finish(d, r);
+            if (s.busy) { cudaStreamSynchronize(s.stream); s.busy = false; }
+        }
+    }
+    st.kernel_ms = *std::max_element(kms.begin(), kms.end());
+    st.wall_ms = ms_since(t_all);
+    return rc;
 }
 
 // ---- staged API --------------------------------------------------------------------------------

@@ -125,7 +125,15 @@ struct __align__(16) PairMeta {
     uint16_t len1;    // target length
     int16_t  h0;
     uint16_t flags;   // bit0: blob is 4-bit ("wide": the pair contains an ambiguous base)
+                      // bit1: the 4-bit blob sits AT off (packed input); otherwise the 2-bit slot at off holds,
+                      //       in its first word, the word offset of the 4-bit copy
 };
+// start of the packed [query | target] a pair's kernel reads (2-bit for plain pairs, 4-bit for wide ones)
+__device__ __forceinline__ const uint32_t *pair_blob(const uint32_t *__restrict__ blob, const PairMeta &m) {
+    const uint32_t *src = blob + m.off;
+    if ((m.flags & 3) == 1) src = blob + src[0];
+    return src;
+}
 
 struct __align__(16) PairOut {  // one STG.128 per pair
     int16_t score, qle, tle, gtle, gscore, max_off;
@@ -912,10 +920,9 @@ bsw_short_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__
     R.kmask = -1; R.qb = nullptr;
     (void)qs_words;
 
-    const uint32_t *src = blob + m.off;
+    const uint32_t *src = pair_blob(blob, m);
     PairResult r;
     if (wide) {
-        src = blob + src[0];
         unpack_pair<true>(src, m.len2, R);
         r = extend_pair<FASTM, SYM, COUNT, true, false, BSW_SHORT_GROUPS, KEY>(R, m.len2, m.len1, m.h0, P);
     } else {
@@ -951,10 +958,9 @@ bsw_win_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ o
     R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)16 * nk * NT) + tid;
     R.kmask = nk - 1; R.qb = nullptr;
 
-    const uint32_t *src = blob + m.off;
+    const uint32_t *src = pair_blob(blob, m);
     PairResult r;
     if (wide) {
-        src = blob + src[0];
         unpack_pair<true>(src, m.len2, R);
         r = extend_pair<FASTM, SYM, COUNT, true, true, BSW_WIN_GROUPS>(R, m.len2, m.len1, m.h0, P);
     } else {
@@ -1002,9 +1008,7 @@ bsw_duo2_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     L[0].qlen = mA.len2; L[0].tlen = mA.len1; L[0].h0 = mA.h0; L[0].wide = mA.flags & 1;
     L[1].qlen = hasB ? mB.len2 : 0; L[1].tlen = hasB ? mB.len1 : 0; L[1].h0 = hasB ? mB.h0 : 0;
     L[1].wide = hasB && (mB.flags & 1);
-    L[0].blob = blob + mA.off; L[1].blob = blob + mB.off;
-    if (L[0].wide) L[0].blob = blob + L[0].blob[0];
-    if (L[1].wide) L[1].blob = blob + L[1].blob[0];
+    L[0].blob = pair_blob(blob, mA); L[1].blob = pair_blob(blob, mB);
     PairResult r[2];
     if (twide) extend_duo2<FASTM, SYM, true, KEY>(R, L, P, r);
     else extend_duo2<FASTM, SYM, false, KEY>(R, L, P, r);
@@ -1305,11 +1309,11 @@ bsw_long_kernel(const PairMeta *__restrict__ meta, const uint32_t *__restrict__ 
     R.he4 = reinterpret_cast<uint4 *>(smem + (size_t)warp * pair_bytes);
     R.qs = reinterpret_cast<uint32_t *>(smem + (size_t)warp * pair_bytes + (size_t)16 * row_el);
     R.tb = nullptr; R.kmask = -1; R.qb = nullptr;
-    const uint32_t *src = blob + m.off;
+    const uint32_t *src = pair_blob(blob, m);
     PairResult r;
     // one pair per warp: the pair's own flag picks the instantiation (launches of this kernel merge several
     // length bins, so the pairs holding an ambiguous base are not all in front)
-    if (m.flags & 1) r = warp_extend_pair<FASTM, SYM, COUNT, true>(R, blob + src[0], m.len2, m.len1, m.h0, P);
+    if (m.flags & 1) r = warp_extend_pair<FASTM, SYM, COUNT, true>(R, src, m.len2, m.len1, m.h0, P);
     else r = warp_extend_pair<FASTM, SYM, COUNT, false>(R, src, m.len2, m.len1, m.h0, P);
     if ((threadIdx.x & 31) == 0) store_result(out, m.id, r);
 }

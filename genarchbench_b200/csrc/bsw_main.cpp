@@ -8,6 +8,8 @@
 // unchanged. Differences: the whole pair set goes to ONE bsw_gpu_batch call (the library batches
 // internally; -b is accepted and ignored), -t sets host packing threads, -gpus N selects GPUs, and
 // only the numPairs real entries are printed (the reference also prints its uninitialised padding).
+// A packed binary pair file (include/bsw_pairio.h) is read straight into page-locked memory and handed to
+// bsw_gpu_batch_packed as it is: that input never exists at one byte per base.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -60,55 +62,97 @@ int main(int argc, char *argv[]) {
         return EXIT_FAILURE;
     }
     printf("Number of input pairs: %ld\n", (long)numPairs);
-    std::vector<bsw_seqpair> pairs((size_t)numPairs);
-    uint8_t *ref = nullptr, *qer = nullptr;
-    int64_t refBytes = 0, qerBytes = 0;
-    int64_t got = packed ? bsw_read_pairs_packed(pairFileName, numPairs, pairs.data(), &ref, &qer, &refBytes, &qerBytes)
-                         : bsw_read_pairs_text(pairFileName, numPairs, pairs.data(), &ref, &qer, &refBytes, &qerBytes);
-    if (got < 0) {
-        fprintf(stderr, "Malformed pair file: %s\n", pairFileName);
-        return EXIT_FAILURE;
-    }
-    numPairs = got;
-    double readSec = std::chrono::duration<double>(clk::now() - t0).count();
-
     bsw_handle *h = nullptr;
     int rc = bsw_gpu_init(&P, gpus, &h);
     if (rc != BSW_OK) {
         fprintf(stderr, "bsw_gpu_init: %s\n", bsw_gpu_strerror(rc));
         return EXIT_FAILURE;
     }
-    {
-        int64_t bases = 0;
-        for (int64_t i = 0; i < numPairs; ++i) bases += (int64_t)pairs[(size_t)i].len1 + pairs[(size_t)i].len2;
-        bsw_gpu_reserve(h, numPairs, bases);
-    }
-    // warm the context, streams and pinned rings outside the ROI (the reference constructs its
-    // BandedPairWiseSW objects, 6 MiB of scratch each, before its ROI as well: main_banded.cpp:271-276)
-    {
-        int64_t nwarm = numPairs < 4096 ? numPairs : 4096;
-        std::vector<bsw_seqpair> tmp(pairs.begin(), pairs.begin() + nwarm);
-        bsw_gpu_batch(h, tmp.data(), ref, qer, nwarm, w);
-    }
-
-    auto r0 = clk::now();
-    rc = bsw_gpu_batch(h, pairs.data(), ref, qer, numPairs, w);   // == main_banded.cpp:345, whole set
-    double roiSec = std::chrono::duration<double>(clk::now() - r0).count();
-    if (rc != BSW_OK) {
-        fprintf(stderr, "bsw_gpu_batch: %s (%s)\n", bsw_gpu_strerror(rc), bsw_gpu_last_error(h));
-        return EXIT_FAILURE;
+    std::vector<bsw_seqpair> pairs;
+    std::vector<int32_t> scores;       // what the writer prints
+    uint8_t *ref = nullptr, *qer = nullptr;
+    int64_t rect = 0;
+    double readSec = 0, roiSec = 0;
+    if (packed) {
+        // ---- packed pair file: records and 2-bit / 4-bit sequences go from the file into page-locked memory and
+        // from there to the GPU as they are (bsw_gpu_batch_packed); no byte-per-base buffers, no SeqPair records
+        int64_t dataBytes = 0;
+        if (bsw_packed_file_info(pairFileName, &numPairs, &dataBytes) != 0) {
+            fprintf(stderr, "Malformed pair file: %s\n", pairFileName);
+            return EXIT_FAILURE;
+        }
+        bsw_packed_rec *rec = (bsw_packed_rec *)bsw_gpu_host_alloc(sizeof(bsw_packed_rec) * (size_t)numPairs + 64);
+        uint8_t *data = (uint8_t *)bsw_gpu_host_alloc((size_t)dataBytes + 64);
+        bsw_result *res = (bsw_result *)bsw_gpu_host_alloc(sizeof(bsw_result) * (size_t)numPairs + 64);
+        if (!rec || !data || !res) { fprintf(stderr, "out of page-locked memory\n"); return EXIT_FAILURE; }
+        const int64_t got = bsw_read_packed_raw(pairFileName, numPairs, rec, data, dataBytes);
+        if (got < 0) {
+            fprintf(stderr, "Malformed pair file: %s\n", pairFileName);
+            return EXIT_FAILURE;
+        }
+        numPairs = got;
+        readSec = std::chrono::duration<double>(clk::now() - t0).count();
+        {   // warm the context, streams and buffers outside the ROI (as below)
+            const int64_t nwarm = numPairs < 4096 ? numPairs : 4096;
+            bsw_gpu_batch_packed(h, rec, data, dataBytes, nwarm, w, res);
+        }
+        auto r0 = clk::now();
+        rc = bsw_gpu_batch_packed(h, rec, data, dataBytes, numPairs, w, res);
+        roiSec = std::chrono::duration<double>(clk::now() - r0).count();
+        if (rc != BSW_OK) {
+            fprintf(stderr, "bsw_gpu_batch_packed: %s (%s)\n", bsw_gpu_strerror(rc), bsw_gpu_last_error(h));
+            return EXIT_FAILURE;
+        }
+        scores.resize((size_t)numPairs);
+        for (int64_t i = 0; i < numPairs; ++i) {
+            scores[(size_t)i] = res[i].score;
+            rect += (int64_t)rec[i].len1 * rec[i].len2;
+        }
+        bsw_gpu_host_free(rec); bsw_gpu_host_free(data); bsw_gpu_host_free(res);
+    } else {
+        pairs.resize((size_t)numPairs);
+        int64_t refBytes = 0, qerBytes = 0;
+        const int64_t got = bsw_read_pairs_text(pairFileName, numPairs, pairs.data(), &ref, &qer, &refBytes, &qerBytes);
+        if (got < 0) {
+            fprintf(stderr, "Malformed pair file: %s\n", pairFileName);
+            return EXIT_FAILURE;
+        }
+        numPairs = got;
+        readSec = std::chrono::duration<double>(clk::now() - t0).count();
+        {
+            int64_t bases = 0;
+            for (int64_t i = 0; i < numPairs; ++i) bases += (int64_t)pairs[(size_t)i].len1 + pairs[(size_t)i].len2;
+            bsw_gpu_reserve(h, numPairs, bases);
+        }
+        // warm the context, streams and pinned rings outside the ROI (the reference constructs its
+        // BandedPairWiseSW objects, 6 MiB of scratch each, before its ROI as well: main_banded.cpp:271-276)
+        {
+            int64_t nwarm = numPairs < 4096 ? numPairs : 4096;
+            std::vector<bsw_seqpair> tmp(pairs.begin(), pairs.begin() + nwarm);
+            bsw_gpu_batch(h, tmp.data(), ref, qer, nwarm, w);
+        }
+        auto r0 = clk::now();
+        rc = bsw_gpu_batch(h, pairs.data(), ref, qer, numPairs, w);   // == main_banded.cpp:345, whole set
+        roiSec = std::chrono::duration<double>(clk::now() - r0).count();
+        if (rc != BSW_OK) {
+            fprintf(stderr, "bsw_gpu_batch: %s (%s)\n", bsw_gpu_strerror(rc), bsw_gpu_last_error(h));
+            return EXIT_FAILURE;
+        }
+        scores.resize((size_t)numPairs);
+        for (int64_t i = 0; i < numPairs; ++i) {
+            scores[(size_t)i] = pairs[(size_t)i].score;
+            rect += (int64_t)pairs[(size_t)i].len1 * pairs[(size_t)i].len2;
+        }
     }
     bsw_gpu_stats st;
     bsw_gpu_get_stats(h, &st);
 
     printf("Executed B200 sm_100a DPX code on %d GPU(s)...\n", st.n_gpus);
     if (!quiet)
-        for (int64_t i = 0; i < numPairs; ++i) fprintf(stderr, "[%ld] score=%d\n", (long)i, pairs[(size_t)i].score);
+        for (int64_t i = 0; i < numPairs; ++i) fprintf(stderr, "[%ld] score=%d\n", (long)i, scores[(size_t)i]);
     printf("Read time = %0.2lf s\n", readSec);
     printf("Overall SW cycles = %ld, %0.2lf s\n", (long)(roiSec * 1e9), roiSec);
     printf("Total Pairs processed: %ld\n", (long)numPairs);
-    int64_t rect = 0;
-    for (int64_t i = 0; i < numPairs; ++i) rect += (int64_t)pairs[(size_t)i].len1 * pairs[(size_t)i].len2;
     printf("ROI = %.6f s, kernel = %.3f ms, pack = %.3f ms, scatter = %.3f ms, launches = %ld, H2D = %ld B, D2H = %ld B\n",
            roiSec, st.kernel_ms, st.host_pack_ms, st.host_scatter_ms, (long)st.kernel_launches,
            (long)st.h2d_bytes, (long)st.d2h_bytes);

@@ -373,13 +373,8 @@ int bsw_write_pairs_packed(const char *path, const bsw_seqpair *pairs, const uin
 }
 
 int64_t bsw_count_pairs_packed(const char *path) {
-    FILE *f = fopen(path, "rb");
-    if (!f) return -1;
-    char m[8];
-    uint64_t hdr[2];
-    const bool ok = fread(m, 1, 8, f) == 8 && memcmp(m, kMagic, 8) == 0 && fread(hdr, 8, 2, f) == 2;
-    fclose(f);
-    return ok ? (int64_t)hdr[0] : -1;
+    int64_t n = 0;
+    return bsw_packed_file_info(path, &n, nullptr) == 0 ? n : -1;   // (header checked against the file size)
 }
 
 int64_t bsw_read_pairs_packed(const char *path, int64_t n, bsw_seqpair *pairs, uint8_t **ref_out,
@@ -389,9 +384,19 @@ int64_t bsw_read_pairs_packed(const char *path, int64_t n, bsw_seqpair *pairs, u
     char m[8];
     uint64_t hdr[2];
     if (fread(m, 1, 8, f) != 8 || memcmp(m, kMagic, 8) != 0 || fread(hdr, 8, 2, f) != 2) { fclose(f); return -1; }
+    // a truncated or corrupt header must not drive the allocations below
+    {
+        const long pos = ftell(f);
+        fseek(f, 0, SEEK_END);
+        const long fsize = ftell(f);
+        fseek(f, pos, SEEK_SET);
+        if (pos < 0 || fsize < 0 || hdr[0] > (uint64_t)fsize / sizeof(PackedRec) ||
+            hdr[1] > (uint64_t)fsize || hdr[0] * sizeof(PackedRec) + hdr[1] + 24 > (uint64_t)fsize) { fclose(f); return -1; }
+    }
     const int64_t total = (int64_t)hdr[0], np = std::min<int64_t>(n, total);
-    std::vector<PackedRec> rec((size_t)total);
-    std::vector<uint8_t> data((size_t)hdr[1]);
+    std::vector<PackedRec> rec;
+    std::vector<uint8_t> data;
+    try { rec.resize((size_t)total); data.resize((size_t)hdr[1]); } catch (...) { fclose(f); return -1; }
     if ((total && fread(rec.data(), sizeof(PackedRec), (size_t)total, f) != (size_t)total) ||
         (!data.empty() && fread(data.data(), 1, data.size(), f) != data.size())) { fclose(f); return -1; }
     fclose(f);
@@ -432,6 +437,91 @@ int64_t bsw_read_pairs_packed(const char *path, int64_t n, bsw_seqpair *pairs, u
     if (ref_bytes) *ref_bytes = (int64_t)roff[(size_t)np];
     if (qer_bytes) *qer_bytes = (int64_t)qoff[(size_t)np];
     return np;
+}
+
+// ---- the packed form in memory (bsw_gpu_batch_packed) ------------------------------------------------------
+static_assert(sizeof(bsw_packed_rec) == sizeof(PackedRec), "the file's record is bsw_packed_rec");
+
+int64_t bsw_packed_bytes(const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer, int64_t n) {
+    if (n < 0 || (n > 0 && (!pairs || !ref || !qer))) return -1;
+    int64_t total = 0;
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : total) reduction(| : bad)
+    for (int64_t k = 0; k < n; ++k) {
+        const bsw_seqpair &p = pairs[k];
+        if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN) { bad = 1; continue; }
+        bool wide = false;
+        for (int i = 0; i < p.len1 && !wide; ++i) wide = ref[p.idr + i] > 3;
+        for (int j = 0; j < p.len2 && !wide; ++j) wide = qer[p.idq + j] > 3;
+        total += (int64_t)(seq_bytes_io((uint32_t)p.len2, wide) + seq_bytes_io((uint32_t)p.len1, wide));
+    }
+    return bad ? -1 : total;
+}
+
+int bsw_pack_pairs(const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer, int64_t n,
+                   bsw_packed_rec *rec, uint8_t *data, int64_t data_cap) {
+    if (n < 0 || (n > 0 && (!pairs || !ref || !qer || !rec || !data))) return 1;
+    std::vector<uint64_t> off((size_t)n + 1, 0);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t k = 0; k < n; ++k) {
+        const bsw_seqpair &p = pairs[k];
+        if (p.len1 < 0 || p.len2 < 0 || p.len1 > BSW_MAX_SEQ_LEN || p.len2 > BSW_MAX_SEQ_LEN) { bad = 1; continue; }
+        bool wide = false;
+        for (int i = 0; i < p.len1 && !wide; ++i) wide = ref[p.idr + i] > 3;
+        for (int j = 0; j < p.len2 && !wide; ++j) wide = qer[p.idq + j] > 3;
+        rec[k] = bsw_packed_rec{(uint16_t)p.len1, (uint16_t)p.len2, p.h0, wide ? 1u : 0u};
+        off[(size_t)k + 1] = seq_bytes_io((uint32_t)p.len2, wide) + seq_bytes_io((uint32_t)p.len1, wide);
+    }
+    if (bad) return 1;
+    for (int64_t k = 0; k < n; ++k) off[(size_t)k + 1] += off[(size_t)k];
+    if ((int64_t)off[(size_t)n] > data_cap) return 2;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n; ++k) {
+        const bsw_seqpair &p = pairs[k];
+        const bool wide = rec[k].flags & 1u;
+        uint8_t *d = data + off[(size_t)k];
+        pack_seq(qer + p.idq, p.len2, wide, d);
+        pack_seq(ref + p.idr, p.len1, wide, d + seq_bytes_io((uint32_t)p.len2, wide));
+    }
+    return 0;
+}
+
+int bsw_packed_file_info(const char *path, int64_t *n, int64_t *data_bytes) {
+    FILE *f = path ? fopen(path, "rb") : nullptr;
+    if (!f) return 1;
+    char m[8];
+    uint64_t hdr[2];
+    bool ok = fread(m, 1, 8, f) == 8 && memcmp(m, kMagic, 8) == 0 && fread(hdr, 8, 2, f) == 2;
+    if (ok) {
+        fseek(f, 0, SEEK_END);
+        const long fsize = ftell(f);
+        ok = fsize >= 24 && hdr[0] <= (uint64_t)fsize / sizeof(PackedRec) && hdr[1] <= (uint64_t)fsize &&
+             hdr[0] * sizeof(PackedRec) + hdr[1] + 24 <= (uint64_t)fsize;
+    }
+    fclose(f);
+    if (!ok) return 1;
+    if (n) *n = (int64_t)hdr[0];
+    if (data_bytes) *data_bytes = (int64_t)hdr[1];
+    return 0;
+}
+
+int64_t bsw_read_packed_raw(const char *path, int64_t n, bsw_packed_rec *rec, uint8_t *data, int64_t data_cap) {
+    int64_t total = 0, dbytes = 0;
+    if (!rec || (!data && data_cap > 0) || bsw_packed_file_info(path, &total, &dbytes) != 0) return -1;
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    const int64_t np = std::min(n, total);
+    bool ok = fseek(f, 24, SEEK_SET) == 0 && (np == 0 || fread(rec, sizeof(PackedRec), (size_t)np, f) == (size_t)np);
+    int64_t need = 0;
+    for (int64_t k = 0; ok && k < np; ++k) {
+        if (rec[k].len1 > BSW_MAX_SEQ_LEN || rec[k].len2 > BSW_MAX_SEQ_LEN) ok = false;
+        need += (int64_t)(seq_bytes_io(rec[k].len2, rec[k].flags & 1u) + seq_bytes_io(rec[k].len1, rec[k].flags & 1u));
+    }
+    ok = ok && need <= dbytes && need <= data_cap && fseek(f, 24 + (long)(total * (int64_t)sizeof(PackedRec)), SEEK_SET) == 0 &&
+         (need == 0 || fread(data, 1, (size_t)need, f) == (size_t)need);
+    fclose(f);
+    return ok ? np : -1;
 }
 
 }  // extern "C"

@@ -26,6 +26,10 @@ SEQPAIR_DTYPE = np.dtype(
     }
 )
 OUTPUT_FIELDS = ("score", "qle", "tle", "gtle", "gscore", "max_off")
+# numpy mirrors of bsw_packed_rec (12 bytes) and bsw_result (16 bytes), include/bsw_types.h
+PACKED_REC_DTYPE = np.dtype([("len1", "<u2"), ("len2", "<u2"), ("h0", "<i4"), ("flags", "<u4")])
+RESULT_DTYPE = np.dtype([("score", "<i2"), ("qle", "<i2"), ("tle", "<i2"), ("gtle", "<i2"), ("gscore", "<i2"),
+                         ("max_off", "<i2"), ("reserved", "<u4")])
 
 
 class GenConfig(C.Structure):
@@ -73,6 +77,14 @@ def lib() -> C.CDLL:
         L.bsw_count_pairs_packed.restype = C.c_int64
         L.bsw_read_pairs_packed.argtypes = L.bsw_read_pairs_text.argtypes
         L.bsw_read_pairs_packed.restype = C.c_int64
+        L.bsw_packed_bytes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.bsw_packed_bytes.restype = C.c_int64
+        L.bsw_pack_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+        L.bsw_pack_pairs.restype = C.c_int
+        L.bsw_packed_file_info.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.bsw_packed_file_info.restype = C.c_int
+        L.bsw_read_packed_raw.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+        L.bsw_read_packed_raw.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -189,6 +201,38 @@ def write_packed(path: str, b: PairBatch) -> None:
                                       b.qer.ctypes.data, len(b))
     if rc != 0:
         raise OSError(f"bsw_write_pairs_packed({path}) failed ({rc})")
+
+
+def pack(b: PairBatch, alloc=None):
+    """The packed in-memory form of a batch (what a BSWPAIR1 file holds): (records, data). `alloc(nbytes)` may
+    return page-locked uint8 arrays (bsw.host_alloc) so that bsw_gpu_batch_packed DMAs them in place."""
+    n = len(b)
+    nbytes = lib().bsw_packed_bytes(b.pairs.ctypes.data, b.ref.ctypes.data, b.qer.ctypes.data, n)
+    if nbytes < 0:
+        raise ValueError("a sequence length is out of range")
+    alloc = alloc or (lambda k: np.zeros(k, dtype=np.uint8))
+    rec = alloc(max(n, 1) * PACKED_REC_DTYPE.itemsize)[:n * PACKED_REC_DTYPE.itemsize].view(PACKED_REC_DTYPE)
+    data = alloc(nbytes + 64)
+    data[nbytes:] = 0
+    rc = lib().bsw_pack_pairs(b.pairs.ctypes.data, b.ref.ctypes.data, b.qer.ctypes.data, n, rec.ctypes.data,
+                              data.ctypes.data, nbytes)
+    if rc != 0:
+        raise RuntimeError(f"bsw_pack_pairs failed ({rc})")
+    return rec, data[:nbytes]
+
+
+def read_packed_raw(path: str, alloc=None):
+    """Records and packed data of a BSWPAIR1 file exactly as stored (no unpacking to one byte per base)."""
+    n, nbytes = C.c_int64(), C.c_int64()
+    if lib().bsw_packed_file_info(path.encode(), C.byref(n), C.byref(nbytes)) != 0:
+        raise OSError(f"{path} is not a packed pair file")
+    alloc = alloc or (lambda k: np.zeros(k, dtype=np.uint8))
+    rec = alloc(max(n.value, 1) * PACKED_REC_DTYPE.itemsize)[:n.value * PACKED_REC_DTYPE.itemsize].view(PACKED_REC_DTYPE)
+    data = alloc(nbytes.value + 64)
+    got = lib().bsw_read_packed_raw(path.encode(), n.value, rec.ctypes.data, data.ctypes.data, nbytes.value)
+    if got < 0:
+        raise OSError(f"malformed packed pair file {path}")
+    return rec[:got], data[:nbytes.value]
 
 
 def read_packed(path: str) -> PairBatch:

@@ -21,6 +21,7 @@
 #ifndef BSW_GPU_H
 #define BSW_GPU_H
 #include "bsw_types.h"
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -74,6 +75,22 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
  * Same domain / error rules as bsw_gpu_batch. */
 int bsw_gpu_batch_retry(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
                         int64_t n, int32_t w, int32_t max_tries, int32_t *tries);
+
+/* ---- packed input: the pair-file ingest path ----
+ * What a packed pair file (include/bsw_pairio.h, "BSWPAIR1") holds, handed over as is: n records and the pairs'
+ * sequences at 2 bits per base (4 bits for a pair that holds an ambiguous base, flags bit 0), per pair the query
+ * then the target, each padded to 4 bytes, pairs back to back in record order. Replaces, for such input, the
+ * reference driver's loader + per-batch call (main_banded.cpp:164-206, 283-287, 338-350): no byte-per-base
+ * buffers and no 72-byte records exist on this path. Results come back as 16-byte records in the same order.
+ * `data` (4-byte aligned) and `out` are DMA'd in place when they are page-locked (bsw_gpu_host_alloc, or memory the
+ * caller registered with CUDA); pageable memory works too and is staged through the library's pinned buffers.
+ * Same domain rules as bsw_gpu_batch (BSW_ERR_RANGE, nothing written). */
+/* (bsw_packed_rec, 12 bytes, and bsw_result, 16 bytes: include/bsw_types.h) */
+int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t *data, int64_t data_bytes,
+                         int64_t n, int32_t w, bsw_result *out);
+/* Page-locked host memory (portable across the handle's GPUs) for the packed arrays; free with bsw_gpu_host_free. */
+void *bsw_gpu_host_alloc(size_t bytes);
+void bsw_gpu_host_free(void *p);
 
 /* ---- staged variant of the same path, for measurement (bench.py `value` vs `e2e`) ----
  * stage:  bin + pack + host->device; inputs stay resident in HBM.

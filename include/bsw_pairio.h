@@ -61,6 +61,18 @@ int64_t bsw_count_pairs_packed(const char *path);
 int64_t bsw_read_pairs_packed(const char *path, int64_t n, bsw_seqpair *pairs, uint8_t **ref_out,
                               uint8_t **qer_out, int64_t *ref_bytes, int64_t *qer_bytes);
 
+/* The same packed form in memory, for bsw_gpu_batch_packed (include/bsw_gpu.h):
+ *   bsw_packed_bytes    : bytes the packed sequences of pairs[0..n) take (-1: a length out of range);
+ *   bsw_pack_pairs      : fills rec[0..n) and data[0..data_cap) (caller-allocated, e.g. page-locked); 0 on success;
+ *   bsw_packed_file_info: n and the data bytes of a packed pair file (0 on success);
+ *   bsw_read_packed_raw : reads the file's records and data as they are into caller-allocated arrays
+ *                         (no unpacking to one byte per base); returns the pairs read or -1. */
+int64_t bsw_packed_bytes(const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer, int64_t n);
+int bsw_pack_pairs(const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer, int64_t n,
+                   bsw_packed_rec *rec, uint8_t *data, int64_t data_cap);
+int bsw_packed_file_info(const char *path, int64_t *n, int64_t *data_bytes);
+int64_t bsw_read_packed_raw(const char *path, int64_t n, bsw_packed_rec *rec, uint8_t *data, int64_t data_cap);
+
 #ifdef __cplusplus
 }
 #endif

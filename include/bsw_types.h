@@ -33,6 +33,12 @@ typedef struct bsw_params {
     int32_t match, mismatch, ambig;
 } bsw_params;
 
+/* Packed pair input (include/bsw_pairio.h "BSWPAIR1", bsw_gpu_batch_packed): one 12-byte record per pair;
+ * flags bit 0 = the pair's sequences are stored at 4 bits per base (it holds an ambiguous base), else 2 bits. */
+typedef struct bsw_packed_rec { uint16_t len1, len2; int32_t h0; uint32_t flags; } bsw_packed_rec;
+/* The six per-pair outputs of the reference (bandedSWA.cpp:3336-3362) as one 16-byte record. */
+typedef struct bsw_result { int16_t score, qle, tle, gtle, gscore, max_off; uint32_t reserved; } bsw_result;
+
 #define BSW_DEFAULT_PARAMS { 6, 1, 6, 1, 100, 5, 1, 4, -1 }
 #define BSW_DEFAULT_BAND 100
 #define BSW_MAX_SEQ_LEN 32767 /* MAX_SEQ_LEN16 - 1, bandedSWA.h:97 */

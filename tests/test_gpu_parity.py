@@ -370,6 +370,54 @@ def test_in_process_multi_gpu_split():
     assert_same_outputs(out[idx], samp.outputs(), samp, "multi-GPU split, sampled")
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_packed_entry_point_matches_oracle(gpu, pinned):
+    """bsw_gpu_batch_packed: what a BSWPAIR1 file holds goes to the GPU as it is (no byte-per-base buffers, no
+    SeqPair records), from pageable memory (staged through the pinned rings) and from page-locked memory (DMA'd in
+    place); configs 1 / 2 / 4, ambiguous bases (4-bit blobs read directly), empty sequences, several slabs."""
+    alloc = bsw.host_alloc if pinned else None
+    for cfg, n, w in ((1, 1_300_000, 100), (2, 20_000, 100), (4, 30_000, 100), (4, 20_000, 7)):
+        c = pairio.preset(cfg)
+        c.n_frac = 0.2
+        b = pairio.generate(c, n, seed=70 + cfg)
+        b.pairs["len1"][5::997] = 0
+        b.pairs["len2"][7::991] = 0
+        rec, data = pairio.pack(b, alloc)
+        out = None
+        if pinned:
+            out = bsw.host_alloc(len(b) * pairio.RESULT_DTYPE.itemsize).view(pairio.RESULT_DTYPE)
+        res = gpu.batch_packed(rec, data, w, out)
+        if n > 100_000:                                        # the oracle on a sample of the large case
+            idx = np.sort(np.random.default_rng(9).choice(n, 60_000, replace=False))
+            idx = np.union1d(idx, np.arange(5, n, 997)[:50])
+        else:
+            idx = np.arange(n)
+        a = pairio.PairBatch(b.pairs[idx].copy(), b.ref, b.qer)
+        oracle.oracle_batch(a, w=w)
+        assert_same_outputs(bsw.results_to_outputs(res[idx]), a.outputs(), a, f"packed input, config {cfg}, w={w}")
+        st = gpu.stats()
+        assert st["pairs"] == n and st["kernel_launches"] > 0
+
+
+def test_packed_file_through_the_driver(tmp_path):
+    """bsw_main on a packed pair file: file -> page-locked memory -> bsw_gpu_batch_packed; same score lines."""
+    import os
+    import re
+    import subprocess
+    from conftest import ROOT
+    b = pairio.generate(1, 30000, seed=6)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    path = str(tmp_path / "pairs.bswp")
+    pairio.write_packed(path, b)
+    exe = os.path.join(ROOT, "genarchbench_b200", "bin", "bsw_main")
+    r = subprocess.run([exe, "-pairs", path, "-t", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    scores = [int(m.group(2)) for m in re.finditer(r"^\[(\d+)\] score=(-?\d+)$", r.stderr, re.M)]
+    assert scores == a.pairs["score"].tolist()
+    assert "Total Pairs processed: 30000" in r.stdout
+
+
 def test_two_pairs_per_thread_kernel_matches_oracle():
     """BSW_DUO2=1 routes the short bins to extend_duo2 (bsw_duo.cuh: the two DPX lanes are the same cell of two
     neighbouring pairs; an evaluated alternative, off by default). The switch is read once per process."""

@@ -1,5 +1,8 @@
 """Pair generator and the reference's 3-line text pair format (main_banded.cpp:152-206)."""
+import os
+
 import numpy as np
+import pytest
 
 from genarchbench_b200 import pairio
 
@@ -84,3 +87,27 @@ def test_text_and_packed_files_round_trip(tmp_path):
     g = pairio.read_text(str(tmp_path / "no_newline.txt"))
     assert g.pairs["len1"].tolist() == [4, 4] and g.pairs["len2"].tolist() == [3, 2] and g.pairs["h0"].tolist() == [7, 5]
     assert g.qer[g.pairs["idq"][1]:g.pairs["idq"][1] + 2].tolist() == [3, 2]
+
+
+def test_packed_in_memory_form_equals_the_file(tmp_path):
+    """pairio.pack (bsw_pack_pairs) produces exactly the records and data of a BSWPAIR1 file; a truncated or
+    corrupt file is refused instead of driving huge allocations."""
+    c = pairio.preset(4)
+    c.n_frac = 0.3
+    b = pairio.generate(c, 3000, seed=12)
+    rec, data = pairio.pack(b)
+    path = str(tmp_path / "p.bswp")
+    pairio.write_packed(path, b)
+    r2, d2 = pairio.read_packed_raw(path)
+    assert (r2 == rec).all() and (d2 == data).all()
+    assert os.path.getsize(path) == 24 + rec.nbytes + data.nbytes
+    raw = open(path, "rb").read()
+    bad = str(tmp_path / "bad.bswp")
+    open(bad, "wb").write(raw[: len(raw) // 2])                # truncated
+    with pytest.raises(OSError):
+        pairio.read_packed_raw(bad)
+    with pytest.raises(OSError):
+        pairio.read_packed(bad)
+    open(bad, "wb").write(raw[:8] + (2 ** 60).to_bytes(8, "little") + raw[16:])   # absurd pair count
+    with pytest.raises(OSError):
+        pairio.read_packed(bad)
