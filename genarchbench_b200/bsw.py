@@ -53,7 +53,8 @@ class Stats(C.Structure):
                 ("n_gpus", C.c_int32), ("reserved", C.c_int32),
                 ("host_sort_ms", C.c_double), ("host_plan_ms", C.c_double), ("host_alloc_ms", C.c_double),
                 ("host_cut_ms", C.c_double), ("host_wait_ms", C.c_double), ("pairs_keyed", C.c_int64),
-                ("pairs_duo", C.c_int64)]
+                ("pairs_duo", C.c_int64), ("pairs_scalar", C.c_int64), ("pairs_invalid", C.c_int64),
+                ("first_invalid", C.c_int64)]
 
     def asdict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

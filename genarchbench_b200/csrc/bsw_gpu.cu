@@ -143,6 +143,9 @@ struct bsw_handle {
     int32_t staged_w = 0;
     // host scratch reused across slabs: per-thread (wide, bin) histograms
     std::vector<uint32_t> hist;
+    // per call: pairs of the scalar class (score bound beyond int16) and invalid records, by index into the caller's
+    // array; both are left out of the slabs and settled at the end of the call
+    std::vector<int64_t> big, invalid;
 };
 
 namespace {
@@ -345,6 +348,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     uint64_t need_words = 0;
     h->hist.assign((size_t)T * 2 * kMaxBins, 0);
     std::vector<std::vector<uint32_t>> triv((size_t)T);
+    std::vector<std::vector<int64_t>> bigv((size_t)T), badv((size_t)T);
     const int packer = pack_have_avx2() ? 2 : (pack_have_pext() ? 1 : 0);
 
 #pragma omp parallel num_threads(T) reduction(| : bad) reduction(| : overflow) reduction(max : maxq) reduction(max : maxsc) reduction(max : maxt) reduction(max : maxh) reduction(+ : need_words)
@@ -370,9 +374,14 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             // uploaded with the rest): no sizing pass over the records.
             for (int k = k0; k < k1; ++k) {
                 const bsw_seqpair &sp = pp[k];
-                if (sp.len1 < 0 || sp.len2 < 0 || sp.len1 > BSW_MAX_SEQ_LEN || sp.len2 > BSW_MAX_SEQ_LEN ||
-                    sp.h0 < 0 || (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767) {
-                    bad |= 1;
+                const bool invalid = sp.len1 < 0 || sp.len2 < 0 || sp.len1 > BSW_MAX_SEQ_LEN || sp.len2 > BSW_MAX_SEQ_LEN || sp.h0 < 0;
+                if (invalid || (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767) {
+                    // not for the int16 kernels: the slab carries an empty pair in its place (answered by the key
+                    // kernel, overwritten when the call settles its scalar class / invalid records)
+                    (invalid ? badv : bigv)[(size_t)t].push_back(lo + k);
+                    PairMeta &m = s.h_meta[k];
+                    m.off = 0; m.id = (uint32_t)k; m.len2 = 0; m.len1 = 0; m.h0 = 0; m.flags = 0;
+                    triv[(size_t)t].push_back((uint32_t)k);
                     continue;
                 }
                 if (k + 4 < k1) {   // the records are read in order; pull the next sequences in early
@@ -468,7 +477,11 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     s.max_sc = (int)std::min<int64_t>(maxsc, INT32_MAX);
     s.key_b1 = bits_for((uint32_t)maxt);
     s.key_b0 = bits_for((uint32_t)maxh);
-    for (int t = 0; t < T; ++t) s.trivial.insert(s.trivial.end(), triv[(size_t)t].begin(), triv[(size_t)t].end());
+    for (int t = 0; t < T; ++t) {
+        s.trivial.insert(s.trivial.end(), triv[(size_t)t].begin(), triv[(size_t)t].end());
+        h->big.insert(h->big.end(), bigv[(size_t)t].begin(), bigv[(size_t)t].end());
+        h->invalid.insert(h->invalid.end(), badv[(size_t)t].begin(), badv[(size_t)t].end());
+    }
     s.n_dev = n - (int)s.trivial.size();
     st.host_pack_ms += ms_since(t0);
     t0 = Clock::now();
@@ -888,6 +901,69 @@ int finish_slab(bsw_handle *h, Slab &s, bsw_seqpair *pairs, double *kernel_ms_ac
 
 }  // namespace
 
+// End of a bsw_gpu_batch call: the pairs its slabs left out.
+//   * scalar class (score bound beyond int16; bwamem.cpp:2218-2228, 2384-2390): one launch of bsw_big_kernel over
+//     byte-per-base copies of their sequences, int32 outputs;
+//   * invalid records (negative length, length > BSW_MAX_SEQ_LEN, negative h0): the six outputs are set to -1,
+//     every other pair of the batch is computed, the call reports BSW_ERR_RANGE.
+static int settle_classes(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer) {
+    bsw_gpu_stats &st = h->stats;
+    int rc = BSW_OK;
+    if (!h->big.empty()) {
+        std::sort(h->big.begin(), h->big.end());
+        const size_t nb = h->big.size();
+        std::vector<BigMeta> meta(nb);
+        uint64_t sbytes = 0, rows = 0;
+        for (size_t a = 0; a < nb; ++a) {
+            const bsw_seqpair &sp = pairs[h->big[a]];
+            BigMeta &m = meta[a];
+            m.toff = sbytes; sbytes += (uint64_t)sp.len1;
+            m.qoff = sbytes; sbytes += (uint64_t)sp.len2;
+            m.soff = rows; rows += 2ull * ((uint64_t)sp.len2 + 2);
+            m.len1 = sp.len1; m.len2 = sp.len2; m.h0 = sp.h0; m.pad = 0;
+        }
+        std::vector<uint8_t> seq(sbytes + 16);
+        for (size_t a = 0; a < nb; ++a) {
+            const bsw_seqpair &sp = pairs[h->big[a]];
+            memcpy(seq.data() + meta[a].toff, ref + sp.idr, (size_t)sp.len1);
+            memcpy(seq.data() + meta[a].qoff, qer + sp.idq, (size_t)sp.len2);
+        }
+        std::vector<BigOut> out(nb);
+        BigMeta *d_meta = nullptr; uint8_t *d_seq = nullptr; int32_t *d_rows = nullptr; BigOut *d_out = nullptr;
+        cudaSetDevice(h->devs[0].id);
+        cudaError_t e = cudaMalloc((void **)&d_meta, sizeof(BigMeta) * nb);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&d_seq, seq.size());
+        if (e == cudaSuccess) e = cudaMalloc((void **)&d_rows, sizeof(int32_t) * (size_t)rows + 16);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, sizeof(BigOut) * nb);
+        if (e == cudaSuccess) e = cudaMemcpy(d_meta, meta.data(), sizeof(BigMeta) * nb, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_seq, seq.data(), seq.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            bsw_big_kernel<<<(int)((nb + 63) / 64), 64>>>(d_meta, (int)nb, d_seq, d_rows, d_out, h->K);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(out.data(), d_out, sizeof(BigOut) * nb, cudaMemcpyDeviceToHost);
+        cudaFree(d_meta); cudaFree(d_seq); cudaFree(d_rows); cudaFree(d_out);
+        if (e != cudaSuccess) return cuda_rc(h, e, "scalar-class pass");
+        for (size_t a = 0; a < nb; ++a) {
+            bsw_seqpair &sp = pairs[h->big[a]];
+            const BigOut &o = out[a];
+            sp.score = o.score; sp.qle = o.qle; sp.tle = o.tle; sp.gtle = o.gtle; sp.gscore = o.gscore; sp.max_off = o.max_off;
+        }
+        st.kernel_launches++;
+        st.pairs_scalar = (int64_t)nb;
+    }
+    if (!h->invalid.empty()) {
+        for (int64_t k : h->invalid) {
+            bsw_seqpair &sp = pairs[k];
+            sp.score = sp.qle = sp.tle = sp.gtle = sp.gscore = sp.max_off = -1;
+        }
+        st.pairs_invalid = (int64_t)h->invalid.size();
+        st.first_invalid = *std::min_element(h->invalid.begin(), h->invalid.end());
+        rc = BSW_ERR_RANGE;
+    }
+    return rc;
+}
+
 template <int W>
 static int run_peak(int iters, int blocks, int threads, uint32_t *sink, float *ms) {
     cudaEvent_t a, b;
@@ -1038,6 +1114,8 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
     st.host_bin_ms = st.host_pack_ms = st.host_scatter_ms = st.kernel_ms = 0;
     st.host_sort_ms = st.host_plan_ms = st.host_alloc_ms = st.host_cut_ms = st.host_wait_ms = 0;
     h->K.w = w;
+    h->big.clear(); h->invalid.clear();
+    st.pairs_scalar = st.pairs_invalid = 0; st.first_invalid = -1;
     if (n == 0) { st.wall_ms = 0; return BSW_OK; }
 
     std::vector<int64_t> cuts, cuts_flat;
@@ -1107,6 +1185,7 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
         }
     }
     st.kernel_ms = *std::max_element(kms.begin(), kms.end());
+    if (rc == BSW_OK) rc = settle_classes(h, pairs, ref, qer);
     st.wall_ms = ms_since(t_all);
     return rc;
 }
@@ -1398,6 +1477,7 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
                   int64_t n, int32_t w) {
     if (!h || n < 0 || (n > 0 && (!pairs || !ref || !qer)) || w < 0) return BSW_ERR_ARG;
     drop_staged(h);
+    h->big.clear(); h->invalid.clear();
     bsw_gpu_stats &st = h->stats;
     st.pairs = n; st.h2d_bytes = 0; st.d2h_bytes = 0; st.kernel_launches = 0;
     st.pairs_short = st.pairs_long = st.pairs_keyed = st.pairs_duo = 0;
@@ -1418,6 +1498,10 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
         if (rc) { drop_staged(h); return rc; }
         if ((rc = upload_slab(h, *s))) { drop_staged(h); return rc; }
         CU(cudaStreamSynchronize(s->stream));
+    }
+    if (!h->big.empty() || !h->invalid.empty()) {   // the resident (measurement) path is the int16 kernels only
+        drop_staged(h);
+        return BSW_ERR_RANGE;
     }
     h->staged_n = n; h->staged_w = w;
     return BSW_OK;

@@ -1360,6 +1360,95 @@ __global__ void bsw_key_kernel(const PairMeta *__restrict__ meta, int n, uint64_
 #endif
 
 // ---------------------------------------------------------------------------------------------
+// The scalar class: pairs whose score bound h0 + len2 * match leaves int16. bwa-mem2 sorts them out a priori
+// (bwamem.cpp:2218-2228, the third class of sortPairsLenExt :1846-1925) and runs them through the SCALAR kernel
+// (scalarBandedSWAWrapper, bwamem.cpp:2384-2390 -> bandedSWA.cpp:132-276), so its rules apply, not the vector
+// path's: int32 arithmetic, the band of :164-172, the z-drop test WITH the gap-extend factor and the zdrop > 0 guard
+// (:226-231), ambiguous bases scored from the matrix (= P.ambig), no row budget. One thread per pair over
+// byte-per-base sequences and int32 rows in global memory: the class is rare by construction (a seed score above
+// ~32 000), so this path is about not failing the batch, not about speed.
+// ---------------------------------------------------------------------------------------------
+struct BigMeta {
+    uint64_t toff, qoff;   // byte offsets of target / query in `seq`
+    uint64_t soff;         // int32 offset of this pair's rows in `scratch` (2 * (len2 + 2) entries)
+    int32_t len1, len2, h0;
+    uint32_t pad;
+};
+struct BigOut { int32_t score, qle, tle, gtle, gscore, max_off; };
+
+#ifndef BSW_HOST_EMUL
+__global__ void bsw_big_kernel(const BigMeta *__restrict__ meta, int n, const uint8_t *__restrict__ seq,
+                               int32_t *__restrict__ scratch, BigOut *__restrict__ out, KParams P) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const BigMeta m = meta[k];
+    const uint8_t *tgt = seq + m.toff, *qry = seq + m.qoff;
+    const int qlen = m.len2, tlen = m.len1, h0 = m.h0;
+    int32_t *Hd = scratch + m.soff, *Ev = Hd + (qlen + 2);
+    const int oe_del = P.o_del + P.e_del, oe_ins = P.o_ins + P.e_ins;
+    for (int j = 0; j < qlen + 2; ++j) { Hd[j] = 0; Ev[j] = 0; }
+    // row "-1" (bandedSWA.cpp:159-161)
+    Hd[0] = h0;
+    if (qlen >= 1) Hd[1] = h0 > oe_ins ? h0 - oe_ins : 0;
+    for (int j = 2; j <= qlen && Hd[j - 1] > P.e_ins; ++j) Hd[j] = Hd[j - 1] - P.e_ins;
+    // band (:164-172)
+    int band = P.w;
+    {
+        const int mx = P.max_score;
+        int max_ins = (int)((double)(qlen * mx + P.end_bonus - P.o_ins) / P.e_ins + 1.);
+        int max_del = (int)((double)(qlen * mx + P.end_bonus - P.o_del) / P.e_del + 1.);
+        band = min(min(band, max(max_ins, 1)), max(max_del, 1));
+    }
+    int best = h0, best_i = -1, best_j = -1, g_i = -1, g = -1, off = 0;
+    int beg = 0, end = qlen;
+    for (int i = 0; i < tlen; ++i) {
+        if (beg < i - band) beg = i - band;
+        if (end > i + band + 1) end = i + band + 1;
+        if (end > qlen) end = qlen;
+        int hleft = 0;                                  // H(i, beg-1)
+        if (beg == 0) hleft = max(h0 - (P.o_del + P.e_del * (i + 1)), 0);
+        const int t = tgt[i];
+        int f = 0, rowmax = 0, rowarg = -1, j;
+        for (j = beg; j < end; ++j) {
+            const int d = Hd[j], e = Ev[j];
+            Hd[j] = hleft;
+            const int q = qry[j];
+            const int sc = (t >= 4 || q >= 4) ? P.ambig : (t == q ? P.match : -P.mismatch);
+            const int M = d ? d + sc : 0;
+            const int h = max(max(M, e), f);
+            hleft = h;
+            if (h >= rowmax) { rowmax = h; rowarg = j; }   // LAST column reaching the row max (:204-205)
+            int tt = max(M - oe_del, 0);
+            Ev[j] = max(e - P.e_del, tt);
+            tt = max(M - oe_ins, 0);
+            f = max(f - P.e_ins, tt);
+        }
+        Hd[end] = hleft; Ev[end] = 0;
+        if (j == qlen) {                                 // :218-221
+            if (!(g > hleft)) g_i = i;
+            g = max(g, hleft);
+        }
+        if (rowmax == 0) break;
+        if (rowmax > best) {
+            best = rowmax; best_i = i; best_j = rowarg;
+            off = max(off, abs(rowarg - i));
+        } else if (P.zdrop > 0) {                        // :226-231
+            const int di = i - best_i, dj = rowarg - best_j;
+            const int pen = di > dj ? (di - dj) * P.e_del : (dj - di) * P.e_ins;
+            if (best - rowmax - pen > P.zdrop) break;
+        }
+        for (j = beg; j < end && Hd[j] == 0 && Ev[j] == 0; ++j) {}
+        beg = j;
+        for (j = end; j >= beg && Hd[j] == 0 && Ev[j] == 0; --j) {}
+        end = min(j + 2, qlen);
+    }
+    BigOut r;
+    r.score = best; r.qle = best_j + 1; r.tle = best_i + 1; r.gtle = g_i + 1; r.gscore = g; r.max_off = off;
+    out[k] = r;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // Integer-pipe microbenchmark: `iters` x 8 independent chains of one instruction kind per thread.
 // ---------------------------------------------------------------------------------------------
 template <int WHICH>

@@ -58,11 +58,16 @@ int bsw_gpu_reserve(bsw_handle *h, int64_t n_pairs, int64_t total_bases);
 /* == getScores16 (bandedSWA.cpp:2679-2703) over n pairs with band width w.
  * pairs[k].idr / .idq are byte offsets into ref / qer, .len1 / .len2 the lengths, .h0 the seed score.
  * Writes only score, tle, gtle, qle, gscore, max_off of pairs[0..n).
- * Valid domain (the reference's int16 kernel, SURVEY.md 8a note 4):
- *   0 <= len1, len2 <= BSW_MAX_SEQ_LEN, 0 <= h0, h0 + len2*match <= 32767; otherwise BSW_ERR_RANGE.
- *   Validation runs slab by slab (~1 M pairs) together with packing: on BSW_ERR_RANGE the slab holding
- *   the offending pair and every later slab are untouched; earlier slabs may already hold results. One call at a time per handle (same rule as one object per thread in
- *   the reference, bandedSWA.cpp:2771). */
+ * Domain: 0 <= len1, len2 <= BSW_MAX_SEQ_LEN and 0 <= h0.
+ *   - h0 + len2*match <= 32767 (the reference's int16 kernel, SURVEY.md 8a note 4): the DPX kernels, results
+ *     bit-identical to getScores16.
+ *   - beyond that bound: the pair belongs to what bwa-mem2 calls the scalar class (bwamem.cpp:2218-2228) and is
+ *     computed like there, by the rules of scalarBandedSWA (bandedSWA.cpp:132-253) in int32, in one extra launch at
+ *     the end of the call (stats.pairs_scalar). The call never fails for such input.
+ *   - a record outside the domain above (the reference asserts or reads out of bounds): its six outputs are set to
+ *     -1, EVERY OTHER pair of the batch is computed as usual, and the call returns BSW_ERR_RANGE with
+ *     stats.pairs_invalid / stats.first_invalid saying how many and where.
+ * One call at a time per handle (same rule as one object per thread in the reference, bandedSWA.cpp:2771). */
 int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
                   int64_t n, int32_t w);
 
@@ -128,6 +133,9 @@ typedef struct bsw_gpu_stats {
     int64_t pairs_keyed;        /* of pairs_short: launched with the keyed row argmax (scores and group
                                    indices of the launch share 16 bits) */
     int64_t pairs_duo;          /* of pairs_short: launched on the two-pairs-per-thread kernel */
+    int64_t pairs_scalar;       /* last batch: pairs of the scalar class (score bound beyond int16; int32 kernel) */
+    int64_t pairs_invalid;      /* last batch: invalid records (outputs set to -1; the call returned BSW_ERR_RANGE) */
+    int64_t first_invalid;      /* index of the first of them, -1 if none */
 } bsw_gpu_stats;
 int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out);
 

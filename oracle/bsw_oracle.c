@@ -18,7 +18,7 @@
  *     zdrop == 0 (ZSCORE16 has no `zdrop > 0` guard, bandedSWA.cpp:3239 vs the scalar :226)
  *   rules=0 selects these vector rules (== getScores16), rules=1 the scalar kernel's (:132-253).
  * Pinned against the compiled reference itself (oracle/_ref, built by oracle/Makefile) by
- * tests/test_oracle_vs_reference.py and against the committed fixtures in tests/golden/.
+ * tests/test_oracle.py and against the committed fixtures in tests/golden/.
  *
  * Arithmetic is int32 here; the reference's vector kernel is wrapping int16, so the two agree on the
  * reference's valid domain h0 + len2*match < 32768, len1,len2 < 32768 (SURVEY.md 8a note 4).
@@ -45,12 +45,18 @@ static inline int sub_score(const oracle_params *P, int t, int q, int rules) {
     return t == q ? P->match : -P->mismatch;
 }
 
-/* band per pair, vector-wrapper rule (bandedSWA.cpp:2898-2919) */
-static int pair_band(const oracle_params *P, int qlen, int w) {
+/* band per pair: the vector wrapper's rule (bandedSWA.cpp:2898-2919; uint16 arithmetic), or, rules == 1, the scalar
+ * kernel's (bandedSWA.cpp:164-172; int arithmetic through a double) */
+static int pair_band(const oracle_params *P, int qlen, int w, int rules) {
     int mx = 0;
     if (mx < P->match) mx = P->match;
     if (mx < -P->mismatch) mx = -P->mismatch;
     if (mx < P->ambig) mx = P->ambig;
+    if (rules == 1) {
+        int max_ins = (int)((double)(qlen * mx + P->end_bonus - P->o_ins) / P->e_ins + 1.);
+        int max_del = (int)((double)(qlen * mx + P->end_bonus - P->o_del) / P->e_del + 1.);
+        return imin(imin(w, imax(max_ins, 1)), imax(max_del, 1));
+    }
     uint16_t q = (uint16_t)(qlen * mx);
     uint16_t a = (uint16_t)(q + (uint16_t)(int16_t)(P->end_bonus - P->o_ins));
     int band = imin(w, imax((int)(a / P->e_ins + 1.0), 1));
@@ -73,7 +79,7 @@ static void extend_one(const oracle_params *P, const uint8_t *tgt, int tlen, con
     if (qlen >= 1) Hd[1] = h0 > oe_ins ? h0 - oe_ins : 0;
     for (int j = 2; j <= qlen && Hd[j - 1] > P->e_ins; ++j) Hd[j] = Hd[j - 1] - P->e_ins;
 
-    const int band = pair_band(P, qlen, w);
+    const int band = pair_band(P, qlen, w, zdrop_rule);
     /* rows the vector kernel grants this lane (:3035-3036, :3130-3144) */
     const int row_budget = imin(qlen + band, tlen);
 

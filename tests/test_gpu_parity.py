@@ -251,11 +251,53 @@ def test_untouched_fields_and_padding(gpu):
     assert (b.pairs["score"][900:] == -1).all() and (b.pairs["score"][:900] >= 0).all()
 
 
-def test_out_of_domain_is_rejected(gpu):
-    b = pairio.from_sequences([([0, 1], [0, 1], 32767)])       # h0 + len2*match overflows int16
+def test_scalar_class_pairs_are_computed_not_rejected(gpu):
+    """A pair whose score bound h0 + len2 * match leaves int16 belongs to bwa-mem2's scalar class (bwamem.cpp:
+    2218-2228) and runs, as there (:2384-2390), by the rules of scalarBandedSWA in int32 -- the call does not fail.
+    Replayed with the oracle: scalar rules for that class, the vector rules (getScores16) for everything else."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 600, 0, 200, 0.2, 0.1
+    b = pairio.generate(c, 300_000, seed=21)                   # several slabs (taper)
+    rng = np.random.default_rng(8)
+    big = np.sort(rng.choice(len(b), 400, replace=False))
+    b.pairs["h0"][big] = rng.integers(32768, 60000, len(big))
+    b.pairs["h0"][big[:50]] = 32767 - b.pairs["len2"][big[:50]] + 1       # just beyond the bound
+    edge = big[50:80]
+    b.pairs["h0"][edge] = 32767 - b.pairs["len2"][edge]                    # exactly on it: still the int16 kernels
+    is_big = b.pairs["h0"].astype(np.int64) + b.pairs["len2"] > 32767
+    assert is_big.sum() == len(big) - len(edge)
+    want = b.copy()
+    oracle.oracle_batch(want)
+    sc = pairio.PairBatch(b.pairs[is_big].copy(), b.ref, b.qer)
+    oracle.oracle_batch(sc, scalar_zdrop=True)
+    wo = want.outputs()
+    wo[is_big] = sc.outputs()
+    gpu.batch(b.pairs, b.ref, b.qer, 100)
+    assert_same_outputs(b.outputs(), wo, b, "batch with scalar-class pairs")
+    st = gpu.stats()
+    assert st["pairs_scalar"] == int(is_big.sum()) and st["pairs_invalid"] == 0
+    assert b.pairs["score"][is_big].max() > 40000               # beyond what an int16 lane could hold
+
+
+def test_invalid_record_does_not_poison_the_batch(gpu):
+    """One record outside the domain (negative length) in the middle of a multi-slab batch: every other pair is
+    computed, the record's outputs are -1, the call reports BSW_ERR_RANGE and where."""
+    b = pairio.generate(1, 600_000, seed=22)
+    a = b.copy()
+    oracle.oracle_batch(a)
+    k = 333_333
+    b.pairs["len1"][k] = -5
+    b.pairs["h0"][k + 1000] = -1
     with pytest.raises(bsw.BswError) as e:
         gpu.batch(b.pairs, b.ref, b.qer, 100)
-    assert e.value.code == 5 and (b.pairs["score"] == -1).all()
+    assert e.value.code == 5
+    st = gpu.stats()
+    assert st["pairs_invalid"] == 2 and st["first_invalid"] == k
+    ok = np.ones(len(b), bool)
+    ok[[k, k + 1000]] = False
+    assert (b.outputs()[~ok] == -1).all()
+    assert_same_outputs(b.outputs()[ok], a.outputs()[ok], None, "valid pairs around an invalid record")
+    gpu.batch(a.pairs, a.ref, a.qer, 100)                       # the handle is fine afterwards
 
 
 def test_reserve_presizes_the_rings():

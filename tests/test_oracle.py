@@ -57,6 +57,22 @@ def test_vector_and_scalar_reference_agree_at_default_scoring():
     assert_same_outputs(v.outputs(), s.outputs(), b, "getScores16 vs scalarBandedSWA")
 
 
+@needs_ref
+def test_oracle_scalar_rules_match_the_reference_scalar_kernel():
+    """rules = 1 of the oracle == scalarBandedSWA (bandedSWA.cpp:132-253), the kernel bwa-mem2 gives the pairs whose
+    score bound leaves int16 (bwamem.cpp:2218-2228, 2384-2390): seed scores up to 50 000, non-default scoring with a
+    gap-extend factor in the z-drop test, ambiguous bases scored from the matrix."""
+    c = pairio.preset(4)
+    c.len2_min, c.len2_max, c.h0_min, c.h0_max, c.n_frac, c.random_frac = 1, 400, 0, 50000, 0.2, 0.1
+    b = pairio.generate(c, 4000, seed=123)
+    for params, w in ((None, 100), (dict(o_del=5, e_del=2, o_ins=7, e_ins=3, zdrop=40, end_bonus=9, match=2, mismatch=3, ambig=-1), 30),
+                      (dict(zdrop=0), 7)):
+        a, r = b.copy(), b.copy()
+        oracle.oracle_batch(a, w=w, params=params, scalar_zdrop=True)
+        oracle.reference_batch(r, w=w, params=params, scalar=True)
+        assert_same_outputs(a.outputs(), r.outputs(), b, f"oracle scalar rules vs scalarBandedSWA, {params}, w={w}")
+
+
 def test_oracle_scalar_rule_differs_only_with_gap_extend_factor():
     """The vector z-drop rule drops the e_del/e_ins factor (bandedSWA.cpp:1889-1902): no effect at e=1."""
     b = pairio.generate(4, 3000, seed=5)
