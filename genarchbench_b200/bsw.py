@@ -29,7 +29,8 @@ ERRORS = {1: "BSW_ERR_ARG", 2: "BSW_ERR_NO_DEVICE", 3: "BSW_ERR_CUDA", 4: "BSW_E
 
 # every symbol include/bsw_gpu.h declares
 EXPORTS = ("bsw_gpu_init", "bsw_gpu_init_devices", "bsw_gpu_free", "bsw_gpu_reserve", "bsw_gpu_batch", "bsw_gpu_batch_retry",
-           "bsw_gpu_batch_packed", "bsw_gpu_host_alloc", "bsw_gpu_host_free", "bsw_gpu_stage",
+           "bsw_gpu_batch_packed", "bsw_gpu_host_alloc", "bsw_gpu_host_free", "bsw_gpu_classify", "bsw_gpu_trip_probe",
+           "bsw_gpu_stage",
            "bsw_gpu_run_staged", "bsw_gpu_fetch_staged", "bsw_gpu_count_staged", "bsw_gpu_get_stats", "bsw_gpu_dpx_peak",
            "bsw_gpu_strerror", "bsw_gpu_last_error", "bsw_gpu_version")
 
@@ -84,6 +85,8 @@ def lib() -> C.CDLL:
         L.bsw_gpu_host_alloc.restype = vp
         L.bsw_gpu_host_free.argtypes = [vp]
         L.bsw_gpu_host_free.restype = None
+        L.bsw_gpu_classify.argtypes = [vp, i64, i32, C.POINTER(i64), vp]
+        L.bsw_gpu_trip_probe.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.bsw_gpu_stage.argtypes = [vp, vp, vp, vp, i64, i32]
         L.bsw_gpu_run_staged.argtypes = [vp, C.POINTER(C.c_float)]
         L.bsw_gpu_fetch_staged.argtypes = [vp, vp, i64]
@@ -227,6 +230,16 @@ _keep: dict = {}
 def results_to_outputs(res: np.ndarray) -> np.ndarray:
     """bsw_result records -> [n, 6] int32 in the order of pairio.OUTPUT_FIELDS."""
     return np.stack([res[f].astype(np.int32) for f in ("score", "qle", "tle", "gtle", "gscore", "max_off")], axis=1)
+
+
+def classify(pairs: np.ndarray, match: int = 1):
+    """bsw_gpu_classify: bwa-mem2's a-priori 8-bit / 16-bit / scalar classes -> (counts[3], class per pair)."""
+    cls = np.zeros(len(pairs), dtype=np.uint8)
+    counts = (C.c_int64 * 3)()
+    rc = lib().bsw_gpu_classify(pairs.ctypes.data, len(pairs), match, counts, cls.ctypes.data)
+    if rc != 0:
+        raise BswError(rc)
+    return list(counts), cls
 
 
 def dpx_peak(which: int = 0, device: int = 0) -> float:

@@ -375,7 +375,8 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
             for (int k = k0; k < k1; ++k) {
                 const bsw_seqpair &sp = pp[k];
                 const bool invalid = sp.len1 < 0 || sp.len2 < 0 || sp.len1 > BSW_MAX_SEQ_LEN || sp.len2 > BSW_MAX_SEQ_LEN || sp.h0 < 0;
-                if (invalid || (int64_t)sp.h0 + (int64_t)sp.len2 * match > 32767) {
+                // (the class rule of bwa-mem2, bwamem.cpp:2218-2228: minval = h0 + min(len1, len2) * a bounds every H)
+                if (invalid || (int64_t)sp.h0 + (int64_t)std::min(sp.len1, sp.len2) * match > 32767) {
                     // not for the int16 kernels: the slab carries an empty pair in its place (answered by the key
                     // kernel, overwritten when the call settles its scalar class / invalid records)
                     (invalid ? badv : bigv)[(size_t)t].push_back(lo + k);
@@ -453,7 +454,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
                 } else {
                     hist[wide * kMaxBins + (uint32_t)(sp.len2 - 1) / kBinCols] += 1;
                     maxq = std::max(maxq, sp.len2);
-                    maxsc = std::max(maxsc, sp.h0 + sp.len2 * match);
+                    maxsc = std::max(maxsc, sp.h0 + std::min(sp.len1, sp.len2) * match);
                     maxt = std::max(maxt, sp.len1);
                     maxh = std::max(maxh, sp.h0);
                 }
@@ -1072,6 +1073,24 @@ void bsw_gpu_free(bsw_handle *h) {
     delete h;
 }
 
+// == the a-priori classification of bwa-mem2 (bwamem.cpp:2218-2228; the three groups sortPairsLenExt forms, :1846-1925)
+int bsw_gpu_classify(const bsw_seqpair *pairs, int64_t n, int32_t match, int64_t counts[3], uint8_t *cls) {
+    if (n < 0 || (n > 0 && !pairs) || !counts || match <= 0) return BSW_ERR_ARG;
+    int64_t c0 = 0, c1 = 0, c2 = 0;
+#pragma omp parallel for schedule(static) reduction(+ : c0) reduction(+ : c1) reduction(+ : c2)
+    for (int64_t k = 0; k < n; ++k) {
+        const bsw_seqpair &sp = pairs[k];
+        const int64_t minval = (int64_t)sp.h0 + (int64_t)std::min(sp.len1, sp.len2) * match;
+        int c;
+        if (sp.len1 < 128 && sp.len2 < 128 && minval < 128) { c = 0; ++c0; }                  // MAX_SEQ_LEN8
+        else if (sp.len1 < 32768 && sp.len2 < 32768 && minval < 32768) { c = 1; ++c1; }        // MAX_SEQ_LEN16
+        else { c = 2; ++c2; }
+        if (cls) cls[k] = (uint8_t)c;
+    }
+    counts[0] = c0; counts[1] = c1; counts[2] = c2;
+    return BSW_OK;
+}
+
 int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out) {
     if (!h || !out) return BSW_ERR_ARG;
     *out = h->stats;
@@ -1309,7 +1328,7 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
         for (int64_t k = c * kChunk; k < hi; ++k) {
             const bsw_packed_rec &r = rec[k];
             if (r.len1 > BSW_MAX_SEQ_LEN || r.len2 > BSW_MAX_SEQ_LEN || r.h0 < 0 ||
-                (int64_t)r.h0 + (int64_t)r.len2 * match > 32767) bad |= 1;
+                (int64_t)r.h0 + (int64_t)std::min(r.len1, r.len2) * match > 32767) bad |= 1;
             wsum += rec_words(r);
         }
         cw[(size_t)c + 1] = wsum;
@@ -1406,7 +1425,7 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
                     if (rr.len1 == 0 || rr.len2 == 0) { ++ntriv; continue; }
                     hist[wide * kMaxBins + (uint32_t)(rr.len2 - 1) / kBinCols] += 1;
                     maxq = std::max(maxq, (int)rr.len2);
-                    maxsc = std::max(maxsc, rr.h0 + (int)rr.len2 * match);
+                    maxsc = std::max(maxsc, rr.h0 + (int)std::min(rr.len1, rr.len2) * match);
                     maxt = std::max(maxt, (int)rr.len1);
                     maxh = std::max(maxh, rr.h0);
                 }

@@ -59,8 +59,8 @@ int bsw_gpu_reserve(bsw_handle *h, int64_t n_pairs, int64_t total_bases);
  * pairs[k].idr / .idq are byte offsets into ref / qer, .len1 / .len2 the lengths, .h0 the seed score.
  * Writes only score, tle, gtle, qle, gscore, max_off of pairs[0..n).
  * Domain: 0 <= len1, len2 <= BSW_MAX_SEQ_LEN and 0 <= h0.
- *   - h0 + len2*match <= 32767 (the reference's int16 kernel, SURVEY.md 8a note 4): the DPX kernels, results
- *     bit-identical to getScores16.
+ *   - h0 + min(len1, len2)*match <= 32767 (bwa-mem2's rule for its 8- and 16-bit classes, bwamem.cpp:2218-2228;
+ *     SURVEY.md 8a note 4): the DPX kernels, results bit-identical to getScores16.
  *   - beyond that bound: the pair belongs to what bwa-mem2 calls the scalar class (bwamem.cpp:2218-2228) and is
  *     computed like there, by the rules of scalarBandedSWA (bandedSWA.cpp:132-253) in int32, in one extra launch at
  *     the end of the call (stats.pairs_scalar). The call never fails for such input.
@@ -70,6 +70,14 @@ int bsw_gpu_reserve(bsw_handle *h, int64_t n_pairs, int64_t total_bases);
  * One call at a time per handle (same rule as one object per thread in the reference, bandedSWA.cpp:2771). */
 int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
                   int64_t n, int32_t w);
+
+/* == the a-priori classification bwa-mem2 applies before it calls the kernels (bwamem.cpp:2218-2228; the three
+ * groups sortPairsLenExt then forms, :1846-1925): with minval = h0 + min(len1, len2) * match,
+ *   class 0 (8-bit):  len1, len2, minval < 128;   class 1 (16-bit): all three < 32768;   class 2: scalar.
+ * counts[c] = pairs per class; cls (nullable) receives the class of every pair. bsw_gpu_batch applies the same
+ * rule itself (classes 0 and 1 share its exact int16 DPX kernels, class 2 runs its int32 kernel), so a caller
+ * need not split its batch; the counts are what its own bookkeeping (numPairs128 / 16 / 1) expects. */
+int bsw_gpu_classify(const bsw_seqpair *pairs, int64_t n, int32_t match, int64_t counts[3], uint8_t *cls);
 
 /* == the band-doubling retry loop the production caller wraps around getScores16
  * (bwa-mem2, benchmarks/fmi/bwa-mem2/x86_64/src/bwamem.cpp:2448-2508, MAX_BAND_TRY at :51):
@@ -147,6 +155,10 @@ int bsw_gpu_get_stats(const bsw_handle *h, bsw_gpu_stats *out);
  *   kernel if shared memory, row bookkeeping and divergence were free).
  *   Used by bench.py for the `dpx_peak` roofline denominator. */
 int bsw_gpu_dpx_peak(int device, int which, double *ginstr_per_s, double *sm_mhz_est);
+
+/* Developer probe: the register-only inner-loop trips (kind 0: one pair per thread, 1: two pairs per thread) at
+ * warps_per_sm one-warp blocks per SM, in giga cells per second. */
+int bsw_gpu_trip_probe(int device, int kind, int warps_per_sm, double *gcells_per_s);
 
 const char *bsw_gpu_strerror(int code);
 /* Text of the last CUDA error seen by this handle (empty string if none). */

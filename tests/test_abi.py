@@ -55,3 +55,17 @@ def test_product_does_not_import_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "libbsw_oracle" not in src and "oracle/_ref" not in src and "libbsw_ref" not in src, f
+
+
+def test_a_priori_classes_follow_bwa_mem2():
+    """bsw_gpu_classify == bwamem.cpp:2218-2228 (host-only, no device needed)."""
+    import numpy as np
+    from genarchbench_b200 import pairio
+    p = np.zeros(6, dtype=pairio.SEQPAIR_DTYPE)
+    #            len1  len2   h0      -> class
+    cases = [(100, 100, 27, 0), (100, 100, 28, 1), (128, 10, 0, 1), (300, 200, 32567, 1), (300, 200, 32568, 2),
+             (10, 32767, 32757, 1)]
+    for k, (l1, l2, h0, _) in enumerate(cases):
+        p[k]["len1"], p[k]["len2"], p[k]["h0"] = l1, l2, h0
+    counts, cls = bsw.classify(p, 1)
+    assert cls.tolist() == [c[3] for c in cases] and counts == [1, 4, 1]

@@ -264,7 +264,8 @@ def test_scalar_class_pairs_are_computed_not_rejected(gpu):
     b.pairs["h0"][big[:50]] = 32767 - b.pairs["len2"][big[:50]] + 1       # just beyond the bound
     edge = big[50:80]
     b.pairs["h0"][edge] = 32767 - b.pairs["len2"][edge]                    # exactly on it: still the int16 kernels
-    is_big = b.pairs["h0"].astype(np.int64) + b.pairs["len2"] > 32767
+    is_big = b.pairs["h0"].astype(np.int64) + np.minimum(b.pairs["len1"], b.pairs["len2"]) > 32767
+    assert (bsw.classify(b.pairs, 1)[1] == 2).sum() == is_big.sum()
     assert is_big.sum() == len(big) - len(edge)
     want = b.copy()
     oracle.oracle_batch(want)
