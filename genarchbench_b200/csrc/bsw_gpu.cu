@@ -19,6 +19,7 @@
 
 #include <omp.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges show up in Nsight Systems / ncu --nvtx (no-ops otherwise)
 
 #include <atomic>
 
@@ -57,6 +58,13 @@ constexpr int kVersion = 3;
 // at most 17 + 15 + 15 bits
 constexpr int kKeyBits = 47;
 constexpr int kMaxBins = BSW_MAX_SEQ_LEN / kBinCols + 2;
+
+// NVTX range for the scope: the profiler-side view of the reference's ROI markers (main_banded.cpp:290-333 brackets
+// its kernel loop for perf / VTune / FAPP / DynamoRIO; here the call and its per-slab host steps are named ranges)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 using Clock = std::chrono::steady_clock;
 inline double ms_since(Clock::time_point t0) {
@@ -810,20 +818,25 @@ inline int64_t slab_target(int64_t rem, int64_t full) {
     return std::max<int64_t>(2 * kCutGroup, (rem / 2 + kCutGroup - 1) / kCutGroup * kCutGroup);
 }
 void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts, std::vector<size_t> &blob_guess,
-               bool staged, std::vector<int64_t> *cuts_flat = nullptr, std::vector<size_t> *guess_flat = nullptr) {
+               bool staged, std::vector<int64_t> *cuts_flat = nullptr, std::vector<size_t> *guess_flat = nullptr,
+               int n_gpus = 1) {
     constexpr int64_t G = kCutGroup, S = 64;
     const int64_t ng = (n + G - 1) / G;
     std::vector<int64_t> bases((size_t)ng, 0);
+    std::vector<double> work((size_t)ng, 0.0);   // estimated DP cells (len1 * len2) per group
 #pragma omp parallel for schedule(static)
     for (int64_t c = 0; c < ng; ++c) {
         int64_t b = 0, cnt = 0;
+        double wk = 0;
         const int64_t hi = std::min(n, (c + 1) * G);
         for (int64_t k = c * G; k < hi; k += S, ++cnt) {
-            const int64_t l1 = pairs[k].len1, l2 = pairs[k].len2;
-            b += std::min<int64_t>(std::max<int64_t>(l1, 0), BSW_MAX_SEQ_LEN) +
-                 std::min<int64_t>(std::max<int64_t>(l2, 0), BSW_MAX_SEQ_LEN);
+            const int64_t l1 = std::min<int64_t>(std::max<int64_t>(pairs[k].len1, 0), BSW_MAX_SEQ_LEN);
+            const int64_t l2 = std::min<int64_t>(std::max<int64_t>(pairs[k].len2, 0), BSW_MAX_SEQ_LEN);
+            b += l1 + l2;
+            wk += (double)l1 * (double)l2;
         }
         bases[(size_t)c] = cnt ? b * (hi - c * G) / cnt : 0;
+        work[(size_t)c] = cnt ? wk * (double)(hi - c * G) / (double)cnt : 0.0;
     }
     // Streaming calls end with a taper: what follows the last slab's packing -- its upload, kernels, download
     // and scatter -- is not overlapped with anything, so the last 1.5 slabs' worth of pairs is cut into
@@ -850,6 +863,33 @@ void cut_slabs(const bsw_seqpair *pairs, int64_t n, std::vector<int64_t> &cuts, 
         }
         if (cv.back() != n) close(n);
     };
+    if (staged && n_gpus > 1) {
+        // Resident batch over several GPUs: contiguous slabs of (estimated) equal DP work, a multiple of
+        // the GPU count of them, dealt round-robin -- every GPU gets the same number of slabs and the same work.
+        double total = 0;
+        for (double x : work) total += x;
+        int64_t nsl = std::max<int64_t>((n + full - 1) / full, 1);
+        nsl = (nsl + n_gpus - 1) / n_gpus * n_gpus;
+        cuts.clear(); blob_guess.clear();
+        cuts.push_back(0);
+        int64_t acc = 0, cnt = 0;
+        double wacc = 0;
+        auto close = [&](int64_t hi) {
+            cuts.push_back(hi);
+            blob_guess.push_back((size_t)((acc / 4 + 20 * cnt) * 115 / 100) + 65536);
+            acc = 0; cnt = 0;
+        };
+        for (int64_t c = 0; c < ng; ++c) {
+            const int64_t hi = std::min(n, (c + 1) * G);
+            acc += bases[(size_t)c];
+            cnt += hi - c * G;
+            wacc += work[(size_t)c];
+            const int64_t k = (int64_t)cuts.size();     // closing would end slab k - 1
+            if ((k < nsl && wacc >= total * (double)k / (double)nsl) || acc >= kSlabBases || cnt >= 2 * full) close(hi);
+        }
+        if (cuts.back() != n) close(n);
+        return;
+    }
     plan(!staged && use_taper(), cuts, blob_guess);
     if (cuts_flat && guess_flat) plan(false, *cuts_flat, *guess_flat);
 }
@@ -1125,6 +1165,7 @@ int bsw_gpu_reserve(bsw_handle *h, int64_t n_pairs, int64_t total_bases) {
 int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
                   int64_t n, int32_t w) {
     if (!h || n < 0 || (n > 0 && (!pairs || !ref || !qer)) || w < 0) return BSW_ERR_ARG;
+    NvtxRange nvtx_call("bsw_gpu_batch");
     auto t_all = Clock::now();
     const int ng = (int)h->devs.size();
     bsw_gpu_stats &st = h->stats;
@@ -1174,9 +1215,13 @@ int bsw_gpu_batch(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, const u
                 rc = claim_slab(h, o, pairs, &kms[(size_t)d], jobs);
         }
         if (rc) break;
-        rc = prepare_slab_fit(h, s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]),
-                              guess[(size_t)sidx], jobs);
+        {
+            NvtxRange nvtx_pack("slab: validate + 2-bit pack + scatter of older results");
+            rc = prepare_slab_fit(h, s, pairs, ref, qer, cuts[(size_t)sidx], (int)(cuts[(size_t)sidx + 1] - cuts[(size_t)sidx]),
+                                  guess[(size_t)sidx], jobs);
+        }
         if (rc) break;
+        NvtxRange nvtx_enq("slab: enqueue H2D, binning, DP launches, D2H");
         if (s.n_dev) {
             // (an error after the first enqueue leaves work in flight on the slab's stream: the slab is marked
             // busy all the same, so that the drain below waits for it before anything is freed or reused)
@@ -1303,6 +1348,7 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
     static_assert(sizeof(bsw_packed_rec) == 12 && sizeof(bsw_result) == sizeof(PairOut), "packed layouts");
     if (!h || n < 0 || w < 0 || data_bytes < 0 || (n > 0 && (!rec || !out || (!data && data_bytes > 0)))) return BSW_ERR_ARG;
     if (((uintptr_t)data & 3u) != 0) return BSW_ERR_ARG;
+    NvtxRange nvtx_call("bsw_gpu_batch_packed");
     auto t_all = Clock::now();
     const int ng = (int)h->devs.size();
     bsw_gpu_stats &st = h->stats;
@@ -1504,7 +1550,7 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
     const int ng = (int)h->devs.size();
     std::vector<int64_t> cuts;
     std::vector<size_t> guess;
-    cut_slabs(pairs, n, cuts, guess, true);
+    cut_slabs(pairs, n, cuts, guess, true, nullptr, nullptr, ng);
     const int nslabs = (int)cuts.size() - 1;
     for (int sidx = 0; sidx < nslabs; ++sidx) {
         Device &dev = h->devs[(size_t)(sidx % ng)];
@@ -1529,6 +1575,7 @@ int bsw_gpu_stage(bsw_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, c
 int bsw_gpu_run_staged(bsw_handle *h, float *kernel_ms) {
     if (!h) return BSW_ERR_ARG;
     if (h->staged_n < 0) return BSW_ERR_STATE;
+    NvtxRange nvtx_call("bsw_gpu_run_staged");
     h->K.w = h->staged_w;
     h->stats.kernel_launches = 0;
     h->stats.pairs_short = h->stats.pairs_long = h->stats.pairs_keyed = h->stats.pairs_duo = 0;

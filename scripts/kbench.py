@@ -31,7 +31,7 @@ if a.check:
     bad = int((got != s.outputs()).any(axis=1).sum())
 best = min(ms)
 print(json.dumps({"tag": a.tag, "workload": a.workload, "pairs": a.pairs, "ms_min": round(best, 3), "ms_mean": round(float(np.mean(ms)), 3),
-                  "gcups": round(cells / (best * 1e-3) / 1e9, 1), "mismatches": bad, "launches": st["kernel_launches"],
+                  "gcups": round(cells / (best * 1e-3) / 1e9, 1), "cells": cells, "runs": a.steps + 2, "mismatches": bad, "launches": st["kernel_launches"],
                   "duo": st["pairs_duo"], "keyed": st["pairs_keyed"], "short": st["pairs_short"], "long": st["pairs_long"],
                   "env": {k: v for k, v in os.environ.items() if k.startswith("BSW_")}}), flush=True)
 g.close()
