@@ -1361,41 +1361,13 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
     const int T = omp_get_max_threads();
     const int match = h->P.match;
 
-    // ---- sizes: words per chunk of 4096 pairs (validated on the way), prefix over the chunks
+    // Slabs are cut, sized and validated one at a time (whole chunks of 4096 pairs, at most slab_pairs(false) pairs and
+    // kSlabBases / 4 packed bytes), so the first slab is on its way before the rest of the records has been looked at.
     constexpr int64_t kChunk = 4096;
-    const int64_t nchunks = (n + kChunk - 1) / kChunk;
-    std::vector<uint64_t> cw((size_t)nchunks + 1, 0);
-    int bad = 0;
+    const int64_t full = std::max<int64_t>(slab_pairs(false) / kChunk * kChunk, kChunk);
+    std::vector<uint64_t> cw((size_t)(full / kChunk) + 1, 0);
     auto t0 = Clock::now();
-#pragma omp parallel for schedule(static) reduction(| : bad)
-    for (int64_t c = 0; c < nchunks; ++c) {
-        uint64_t wsum = 0;
-        const int64_t hi = std::min(n, (c + 1) * kChunk);
-        for (int64_t k = c * kChunk; k < hi; ++k) {
-            const bsw_packed_rec &r = rec[k];
-            if (r.len1 > BSW_MAX_SEQ_LEN || r.len2 > BSW_MAX_SEQ_LEN || r.h0 < 0 ||
-                (int64_t)r.h0 + (int64_t)std::min(r.len1, r.len2) * match > 32767) bad |= 1;
-            wsum += rec_words(r);
-        }
-        cw[(size_t)c + 1] = wsum;
-    }
-    if (bad) return BSW_ERR_RANGE;
-    for (int64_t c = 0; c < nchunks; ++c) cw[(size_t)c + 1] += cw[(size_t)c];
-    if ((int64_t)cw[(size_t)nchunks] * 4 > data_bytes) return BSW_ERR_ARG;
-    // ---- slabs: whole chunks, at most slab_pairs(false) pairs and kSlabBases / 4 packed bytes
-    std::vector<int64_t> cuts{0};
-    {
-        const int64_t full = slab_pairs(false);
-        int64_t c0 = 0;
-        for (int64_t c = 1; c <= nchunks; ++c) {
-            const int64_t pairs_in = std::min(n, c * kChunk) - c0 * kChunk;
-            const uint64_t bytes_in = (cw[(size_t)c] - cw[(size_t)c0]) * 4;
-            if (c == nchunks || pairs_in + kChunk > full || bytes_in >= (uint64_t)kSlabBases / 4) { cuts.push_back(c); c0 = c; }
-        }
-    }
-    st.host_cut_ms = ms_since(t0);
     const bool data_pinned = is_pinned(data), out_pinned = is_pinned(out);
-    const int nslabs = (int)cuts.size() - 1;
     std::vector<double> kms((size_t)ng, 0.0);
     std::vector<PackedSlabOut> pending((size_t)ng * kRing);
     int rc = BSW_OK;
@@ -1430,17 +1402,47 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
         return BSW_OK;
     };
 
-    for (int sidx = 0; sidx < nslabs && rc == BSW_OK; ++sidx) {
+    int64_t lo = 0;          // first pair of the next slab
+    uint64_t w_lo = 0;       // its first word in `data`
+    for (int sidx = 0; lo < n && rc == BSW_OK; ++sidx) {
         const int d = sidx % ng, r = (sidx / ng) % kRing;
         Device &dev = h->devs[(size_t)d];
         Slab &s = dev.ring[r];
         if ((rc = cuda_rc(h, cudaSetDevice(dev.id), "cudaSetDevice"))) break;
-        if ((rc = finish(d, r))) break;
-        const int64_t c_lo = cuts[(size_t)sidx], c_hi = cuts[(size_t)sidx + 1];
-        const int64_t lo = c_lo * kChunk;
-        const int ns = (int)(std::min(n, c_hi * kChunk) - lo);
-        const uint64_t w_lo = cw[(size_t)c_lo], words = cw[(size_t)c_hi] - w_lo;
+        // ---- sizes of the slab's chunks (validated on the way), prefix, cut at the byte limit
+        t0 = Clock::now();
+        // slab sizes ramp up from 128 Ki pairs (the GPU starts after a fraction of a millisecond of host work and
+        // copying instead of a whole slab's) and taper off at the end (the last download and hand-over are short)
+        int64_t target = std::min<int64_t>(full, (int64_t)131072 << std::min(sidx / ng, 6));
+        if (use_taper() && n - lo <= target + target / 2 && n - lo > 2 * 131072)
+            target = std::max<int64_t>(131072, ((n - lo) / 2 + kChunk - 1) / kChunk * kChunk);
+        int64_t nch = (std::min(n - lo, target) + kChunk - 1) / kChunk;
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int64_t c = 0; c < nch; ++c) {
+            uint64_t wsum = 0;
+            const int64_t hi = std::min(n, lo + (c + 1) * kChunk);
+            for (int64_t k = lo + c * kChunk; k < hi; ++k) {
+                const bsw_packed_rec &rr = rec[k];
+                if (rr.len1 > BSW_MAX_SEQ_LEN || rr.len2 > BSW_MAX_SEQ_LEN || rr.h0 < 0 ||
+                    (int64_t)rr.h0 + (int64_t)std::min(rr.len1, rr.len2) * match > 32767) bad |= 1;
+                wsum += rec_words(rr);
+            }
+            cw[(size_t)c + 1] = wsum;
+        }
+        if (bad) { rc = BSW_ERR_RANGE; break; }
+        cw[0] = 0;
+        for (int64_t c = 0; c < nch; ++c) {
+            cw[(size_t)c + 1] += cw[(size_t)c];
+            if (cw[(size_t)c + 1] * 4 >= (uint64_t)kSlabBases / 4) { nch = c + 1; break; }
+        }
+        const int ns = (int)(std::min(n, lo + nch * kChunk) - lo);
+        const uint64_t words = cw[(size_t)nch];
+        if ((w_lo + words) * 4 > (uint64_t)data_bytes) { rc = BSW_ERR_ARG; break; }
         if (words > 0xFFFFFF00ull) { rc = BSW_ERR_RANGE; break; }
+        st.host_cut_ms += ms_since(t0);
+        if ((rc = finish(d, r))) break;
+        const int64_t c_lo = 0, c_hi = nch;
         t0 = Clock::now();
         rc = ensure_slab(h, s, ns, data_pinned ? 0 : (size_t)words * 4 + 64);
         if (!rc) rc = ensure_dblob(h, s, (size_t)words * 4 + 64);
@@ -1456,9 +1458,9 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
             uint32_t *hist = h->hist.data() + (size_t)omp_get_thread_num() * 2 * kMaxBins;
 #pragma omp for schedule(static)
             for (int64_t c = c_lo; c < c_hi; ++c) {
-                uint64_t off = cw[(size_t)c] - w_lo;
-                const int64_t hi = std::min(n, (c + 1) * kChunk);
-                for (int64_t k = c * kChunk; k < hi; ++k) {
+                uint64_t off = cw[(size_t)c];
+                const int64_t hi = std::min(n, lo + (c + 1) * kChunk);
+                for (int64_t k = lo + c * kChunk; k < hi; ++k) {
                     const bsw_packed_rec &rr = rec[k];
                     const uint32_t wide = rr.flags & 1u;
                     PairMeta &m = s.h_meta[k - lo];
@@ -1520,6 +1522,8 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
                                              sizeof(PairOut) * (size_t)ns, cudaMemcpyDeviceToHost, s.stream), "D2H out"))) break;
         st.d2h_bytes += (int64_t)(sizeof(PairOut) * (size_t)ns);
         if ((rc = cuda_rc(h, cudaEventRecord(s.ev_done, s.stream), "cudaEventRecord"))) break;
+        lo += ns;
+        w_lo += words;
     }
     // drain (also on error, so that no stream still touches memory we or the caller may free)
     for (int d = 0; d < ng; ++d) {

@@ -97,7 +97,9 @@ int bsw_gpu_batch_retry(bsw_handle *h, bsw_seqpair *pairs, const uint8_t *ref, c
  * buffers and no 72-byte records exist on this path. Results come back as 16-byte records in the same order.
  * `data` (4-byte aligned) and `out` are DMA'd in place when they are page-locked (bsw_gpu_host_alloc, or memory the
  * caller registered with CUDA); pageable memory works too and is staged through the library's pinned buffers.
- * Same domain rules as bsw_gpu_batch (BSW_ERR_RANGE, nothing written). */
+ * Domain: lengths <= BSW_MAX_SEQ_LEN, h0 >= 0 and h0 + min(len1, len2)*match <= 32767 for every record (packed pair
+ * files of this repo are written from such data); otherwise BSW_ERR_RANGE. Records are validated slab by slab
+ * (~1 M pairs) as the call streams, so on that error slabs before the offending one may already hold results. */
 /* (bsw_packed_rec, 12 bytes, and bsw_result, 16 bytes: include/bsw_types.h) */
 int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t *data, int64_t data_bytes,
                          int64_t n, int32_t w, bsw_result *out);
