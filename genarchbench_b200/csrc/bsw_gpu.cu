@@ -36,6 +36,7 @@ using namespace bswk;
 namespace {
 
 constexpr int kRing = 3;                       // slabs in flight per GPU
+constexpr int kBaseSlots = 8192;               // chunk bases of a packed slab (4096-pair chunks: up to 32 Mi pairs)
 // pairs per slab (upper bound); BSW_SLAB_PAIRS overrides (tuning). The streaming path wants small slabs
 // (host packing, GPU and scatter overlap slab by slab: 1 Mi measured best end to end), the resident path
 // larger ones (more blocks per launch, shorter tails: 4 Mi is 4 % faster than 1 Mi on the device).
@@ -92,7 +93,10 @@ struct Slab {
     PairMeta *h_meta = nullptr;
     uint32_t *h_blob = nullptr;
     PairOut *h_out = nullptr;
+    uint32_t *h_base = nullptr;      // packed input: first word of every 4096-pair chunk (kBaseSlots entries)
     // device
+    uint32_t *d_base = nullptr;
+    bool use_base = false;           // the current contents' PairMeta offsets are chunk-relative
     PairMeta *d_meta = nullptr;      // caller order
     uint32_t *d_blob = nullptr;
     PairOut *d_out = nullptr;
@@ -175,6 +179,8 @@ void free_slab(Slab &s) {
         if (s.h_blob) cudaFreeHost(s.h_blob);
         if (s.h_out) cudaFreeHost(s.h_out);
     }
+    if (s.h_base) cudaFreeHost(s.h_base);
+    if (s.d_base) cudaFree(s.d_base);
     if (s.d_meta) cudaFree(s.d_meta);
     if (s.d_blob) cudaFree(s.d_blob);
     if (s.d_out) cudaFree(s.d_out);
@@ -195,6 +201,8 @@ int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
         CU(cudaEventCreate(&s.ev_k0));
         CU(cudaEventCreate(&s.ev_k1));
         CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        CU(cudaHostAlloc((void **)&s.h_base, sizeof(uint32_t) * kBaseSlots, cudaHostAllocDefault));
+        CU(cudaMalloc((void **)&s.d_base, sizeof(uint32_t) * kBaseSlots));
     }
     if (pairs > s.cap_pairs) {
         int64_t cap = std::max<int64_t>(pairs, 1024);
@@ -338,6 +346,7 @@ int prepare_slab(bsw_handle *h, Slab &s, const bsw_seqpair *pairs, const uint8_t
     const bsw_seqpair *pp = pairs + lo;
     bsw_gpu_stats &st = h->stats;
     s.lo = lo; s.n = n;
+    s.use_base = false;
     s.launches.clear();
     s.trivial.clear();
     auto t0 = Clock::now();
@@ -753,7 +762,7 @@ int bin_slab(bsw_handle *h, Slab &s, cudaStream_t st) {
     if (s.n_dev == 0) return BSW_OK;
     const int n = s.n;
     bsw_key_kernel<<<(n + 255) / 256, 256, 0, st>>>(s.d_meta, n, s.d_keys, s.d_ord, s.key_b1, s.key_b0, s.long_bin0,
-                                                    s.d_out);
+                                                    s.d_out, s.use_base ? s.d_base : nullptr);
     CU(cudaGetLastError());
     h->stats.kernel_launches++;
     size_t tmp = s.sort_tmp_bytes;
@@ -1409,76 +1418,81 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
         Device &dev = h->devs[(size_t)d];
         Slab &s = dev.ring[r];
         if ((rc = cuda_rc(h, cudaSetDevice(dev.id), "cudaSetDevice"))) break;
-        // ---- sizes of the slab's chunks (validated on the way), prefix, cut at the byte limit
-        t0 = Clock::now();
+        if ((rc = finish(d, r))) break;
         // slab sizes ramp up from 128 Ki pairs (the GPU starts after a fraction of a millisecond of host work and
         // copying instead of a whole slab's) and taper off at the end (the last download and hand-over are short)
         int64_t target = std::min<int64_t>(full, (int64_t)131072 << std::min(sidx / ng, 6));
         if (use_taper() && n - lo <= target + target / 2 && n - lo > 2 * 131072)
             target = std::max<int64_t>(131072, ((n - lo) / 2 + kChunk - 1) / kChunk * kChunk);
         int64_t nch = (std::min(n - lo, target) + kChunk - 1) / kChunk;
-        int bad = 0;
-#pragma omp parallel for schedule(static) reduction(| : bad)
-        for (int64_t c = 0; c < nch; ++c) {
-            uint64_t wsum = 0;
-            const int64_t hi = std::min(n, lo + (c + 1) * kChunk);
-            for (int64_t k = lo + c * kChunk; k < hi; ++k) {
-                const bsw_packed_rec &rr = rec[k];
-                if (rr.len1 > BSW_MAX_SEQ_LEN || rr.len2 > BSW_MAX_SEQ_LEN || rr.h0 < 0 ||
-                    (int64_t)rr.h0 + (int64_t)std::min(rr.len1, rr.len2) * match > 32767) bad |= 1;
-                wsum += rec_words(rr);
+        int ns = 0;
+        uint64_t words = 0;
+        int maxq = 0, maxsc = 0, maxt = 0, maxh = 0, ntriv = 0, bad = 0;
+        // ---- ONE pass over the slab's records: validate, PairMeta in the caller's order with offsets relative to the
+        // pair's 4096-pair chunk (the key kernel adds the chunks' bases), launch histogram, maxima. Repeated over fewer
+        // chunks in the rare case that the slab exceeds the byte limit.
+        for (;;) {
+            t0 = Clock::now();
+            ns = (int)(std::min(n, lo + nch * kChunk) - lo);
+            rc = ensure_slab(h, s, ns, 0);
+            st.host_alloc_ms += ms_since(t0);
+            if (rc) break;
+            t0 = Clock::now();
+            s.lo = lo; s.n = ns; s.trivial.clear();
+            h->hist.assign((size_t)T * 2 * kMaxBins, 0);
+            maxq = maxsc = maxt = maxh = ntriv = bad = 0;
+#pragma omp parallel num_threads(T) reduction(max : maxq) reduction(max : maxsc) reduction(max : maxt) reduction(max : maxh) reduction(+ : ntriv) reduction(| : bad)
+            {
+                uint32_t *hist = h->hist.data() + (size_t)omp_get_thread_num() * 2 * kMaxBins;
+#pragma omp for schedule(static)
+                for (int64_t c = 0; c < nch; ++c) {
+                    uint32_t off = 0;
+                    const int64_t hi = std::min(n, lo + (c + 1) * kChunk);
+                    for (int64_t k = lo + c * kChunk; k < hi; ++k) {
+                        const bsw_packed_rec &rr = rec[k];
+                        if (rr.len1 > BSW_MAX_SEQ_LEN || rr.len2 > BSW_MAX_SEQ_LEN || rr.h0 < 0 ||
+                            (int64_t)rr.h0 + (int64_t)std::min(rr.len1, rr.len2) * match > 32767) { bad |= 1; continue; }
+                        const uint32_t wide = rr.flags & 1u;
+                        PairMeta &m = s.h_meta[k - lo];
+                        m.off = off;
+                        m.id = (uint32_t)(k - lo);
+                        m.len2 = rr.len2; m.len1 = rr.len1;
+                        m.h0 = (int16_t)rr.h0;
+                        m.flags = (uint16_t)(wide ? 3u : 0u);
+                        off += rec_words(rr);
+                        if (rr.len1 == 0 || rr.len2 == 0) { ++ntriv; continue; }
+                        hist[wide * kMaxBins + (uint32_t)(rr.len2 - 1) / kBinCols] += 1;
+                        maxq = std::max(maxq, (int)rr.len2);
+                        maxsc = std::max(maxsc, rr.h0 + (int)std::min(rr.len1, rr.len2) * match);
+                        maxt = std::max(maxt, (int)rr.len1);
+                        maxh = std::max(maxh, rr.h0);
+                    }
+                    cw[(size_t)c + 1] = off;
+                }
             }
-            cw[(size_t)c + 1] = wsum;
+            if (bad) { rc = BSW_ERR_RANGE; break; }
+            cw[0] = 0;
+            int64_t fit = nch;
+            for (int64_t c = 0; c < nch; ++c) {
+                cw[(size_t)c + 1] += cw[(size_t)c];
+                if (cw[(size_t)c + 1] * 4 >= (uint64_t)kSlabBases / 4 && c + 1 < nch) { fit = c + 1; break; }
+            }
+            st.host_plan_ms += ms_since(t0);
+            if (fit == nch) break;
+            nch = fit;
         }
-        if (bad) { rc = BSW_ERR_RANGE; break; }
-        cw[0] = 0;
-        for (int64_t c = 0; c < nch; ++c) {
-            cw[(size_t)c + 1] += cw[(size_t)c];
-            if (cw[(size_t)c + 1] * 4 >= (uint64_t)kSlabBases / 4) { nch = c + 1; break; }
-        }
-        const int ns = (int)(std::min(n, lo + nch * kChunk) - lo);
-        const uint64_t words = cw[(size_t)nch];
+        if (rc) break;
+        words = cw[(size_t)nch];
         if ((w_lo + words) * 4 > (uint64_t)data_bytes) { rc = BSW_ERR_ARG; break; }
-        if (words > 0xFFFFFF00ull) { rc = BSW_ERR_RANGE; break; }
-        st.host_cut_ms += ms_since(t0);
-        if ((rc = finish(d, r))) break;
-        const int64_t c_lo = 0, c_hi = nch;
+        if (words > 0xFFFFFF00ull || nch > kBaseSlots) { rc = BSW_ERR_RANGE; break; }
         t0 = Clock::now();
         rc = ensure_slab(h, s, ns, data_pinned ? 0 : (size_t)words * 4 + 64);
         if (!rc) rc = ensure_dblob(h, s, (size_t)words * 4 + 64);
         st.host_alloc_ms += ms_since(t0);
         if (rc) break;
-        // ---- records -> PairMeta in the caller's order (offsets: running sums inside each chunk), histograms
         t0 = Clock::now();
-        s.lo = lo; s.n = ns; s.trivial.clear();
-        h->hist.assign((size_t)T * 2 * kMaxBins, 0);
-        int maxq = 0, maxsc = 0, maxt = 0, maxh = 0, ntriv = 0;
-#pragma omp parallel num_threads(T) reduction(max : maxq) reduction(max : maxsc) reduction(max : maxt) reduction(max : maxh) reduction(+ : ntriv)
-        {
-            uint32_t *hist = h->hist.data() + (size_t)omp_get_thread_num() * 2 * kMaxBins;
-#pragma omp for schedule(static)
-            for (int64_t c = c_lo; c < c_hi; ++c) {
-                uint64_t off = cw[(size_t)c];
-                const int64_t hi = std::min(n, lo + (c + 1) * kChunk);
-                for (int64_t k = lo + c * kChunk; k < hi; ++k) {
-                    const bsw_packed_rec &rr = rec[k];
-                    const uint32_t wide = rr.flags & 1u;
-                    PairMeta &m = s.h_meta[k - lo];
-                    m.off = (uint32_t)off;
-                    m.id = (uint32_t)(k - lo);
-                    m.len2 = rr.len2; m.len1 = rr.len1;
-                    m.h0 = (int16_t)rr.h0;
-                    m.flags = (uint16_t)(wide ? 3u : 0u);
-                    off += rec_words(rr);
-                    if (rr.len1 == 0 || rr.len2 == 0) { ++ntriv; continue; }
-                    hist[wide * kMaxBins + (uint32_t)(rr.len2 - 1) / kBinCols] += 1;
-                    maxq = std::max(maxq, (int)rr.len2);
-                    maxsc = std::max(maxsc, rr.h0 + (int)std::min(rr.len1, rr.len2) * match);
-                    maxt = std::max(maxt, (int)rr.len1);
-                    maxh = std::max(maxh, rr.h0);
-                }
-            }
-        }
+        for (int64_t c = 0; c < nch; ++c) s.h_base[c] = (uint32_t)cw[(size_t)c];
+        s.use_base = true;
         s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
         s.max_sc = maxsc;
         s.key_b1 = bits_for((uint32_t)maxt);
@@ -1503,6 +1517,7 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
         }
         s.busy = true;      // (from here on work may be in flight on the slab's stream: see bsw_gpu_batch)
         if ((rc = cuda_rc(h, cudaMemcpyAsync(s.d_meta, s.h_meta, sizeof(PairMeta) * (size_t)ns, cudaMemcpyHostToDevice, s.stream), "H2D meta"))) break;
+        if ((rc = cuda_rc(h, cudaMemcpyAsync(s.d_base, s.h_base, sizeof(uint32_t) * (size_t)nch, cudaMemcpyHostToDevice, s.stream), "H2D chunk bases"))) break;
         if (words && (rc = cuda_rc(h, cudaMemcpyAsync(s.d_blob, src, (size_t)words * 4, cudaMemcpyHostToDevice, s.stream), "H2D blob"))) break;
         // (the kernels read one word past a pair's target a refill period ahead)
         if ((rc = cuda_rc(h, cudaMemsetAsync(reinterpret_cast<char *>(s.d_blob) + (size_t)words * 4, 0, 16, s.stream), "memset"))) break;
@@ -1512,7 +1527,7 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
             if ((rc = bin_slab(h, s, s.stream))) break;
             if ((rc = launch_slab(h, dev, s))) break;
         } else if (ns) {   // only pairs with an empty sequence: the key kernel answers them
-            bsw_key_kernel<<<(ns + 255) / 256, 256, 0, s.stream>>>(s.d_meta, ns, s.d_keys, s.d_ord, s.key_b1, s.key_b0, s.long_bin0, s.d_out);
+            bsw_key_kernel<<<(ns + 255) / 256, 256, 0, s.stream>>>(s.d_meta, ns, s.d_keys, s.d_ord, s.key_b1, s.key_b0, s.long_bin0, s.d_out, nullptr);
         }
         if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k1, s.stream), "cudaEventRecord"))) break;
         PackedSlabOut &po = pending[(size_t)d * kRing + r];

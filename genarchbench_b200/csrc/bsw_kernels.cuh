@@ -1340,12 +1340,18 @@ __host__ __device__ inline uint64_t sort_key(uint32_t len2, uint32_t len1, uint3
     return ((uint64_t)top << (b1 + b0)) | ((uint64_t)len1 << b0) | h0;
 }
 #ifndef BSW_HOST_EMUL
-__global__ void bsw_key_kernel(const PairMeta *__restrict__ meta, int n, uint64_t *__restrict__ keys,
+// chunk_base (nullable; packed input): meta[k].off is relative to its chunk of 4096 pairs, the chunk's first word is
+// chunk_base[k >> 12] -- added here, so that the host writes the records in one pass without a prefix sum in between
+__global__ void bsw_key_kernel(PairMeta *__restrict__ meta, int n, uint64_t *__restrict__ keys,
                                uint32_t *__restrict__ idx, int b1, int b0, int long_bin0,
-                               PairOut *__restrict__ out) {
+                               PairOut *__restrict__ out, const uint32_t *__restrict__ chunk_base) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const PairMeta m = meta[k];
+    PairMeta m = meta[k];
+    if (chunk_base) {
+        m.off += chunk_base[k >> 12];
+        meta[k].off = m.off;
+    }
     keys[k] = sort_key(m.len2, m.len1, (uint32_t)m.h0, m.flags & 1u, b1, b0, long_bin0);
     idx[k] = (uint32_t)k;
     // empty target or query: no DP kernel is launched for the pair (key 0 sorts behind every launch), the
