@@ -93,9 +93,12 @@ struct Slab {
     PairMeta *h_meta = nullptr;
     uint32_t *h_blob = nullptr;
     PairOut *h_out = nullptr;
-    uint32_t *h_base = nullptr;      // packed input: first word of every 4096-pair chunk (kBaseSlots entries)
+    SlabStatsDev *h_stats = nullptr; // packed input: the statistics block bsw_rec_meta_kernel fills
     // device
-    uint32_t *d_base = nullptr;
+    uint32_t *d_base = nullptr;      // packed input: first word of every 4096-pair chunk (kBaseSlots entries)
+    uint32_t *d_chunk_total = nullptr;
+    SlabStatsDev *d_stats = nullptr;
+    cudaEvent_t ev_stats = nullptr;
     bool use_base = false;           // the current contents' PairMeta offsets are chunk-relative
     PairMeta *d_meta = nullptr;      // caller order
     uint32_t *d_blob = nullptr;
@@ -179,8 +182,11 @@ void free_slab(Slab &s) {
         if (s.h_blob) cudaFreeHost(s.h_blob);
         if (s.h_out) cudaFreeHost(s.h_out);
     }
-    if (s.h_base) cudaFreeHost(s.h_base);
+    if (s.h_stats) cudaFreeHost(s.h_stats);
     if (s.d_base) cudaFree(s.d_base);
+    if (s.d_chunk_total) cudaFree(s.d_chunk_total);
+    if (s.d_stats) cudaFree(s.d_stats);
+    if (s.ev_stats) cudaEventDestroy(s.ev_stats);
     if (s.d_meta) cudaFree(s.d_meta);
     if (s.d_blob) cudaFree(s.d_blob);
     if (s.d_out) cudaFree(s.d_out);
@@ -197,12 +203,19 @@ void free_slab(Slab &s) {
 
 int ensure_slab(bsw_handle *h, Slab &s, int64_t pairs, size_t blob_bytes) {
     if (!s.stream) {
-        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        // (highest priority: a slab's small copies, its record / key kernels and its sort get SM and copy-engine
+        // slots ahead of the DP launches of the slabs before it, which run on the default-priority aux streams)
+        int prio_lo = 0, prio_hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CU(cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_hi));
         CU(cudaEventCreate(&s.ev_k0));
         CU(cudaEventCreate(&s.ev_k1));
         CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-        CU(cudaHostAlloc((void **)&s.h_base, sizeof(uint32_t) * kBaseSlots, cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&s.ev_stats, cudaEventDisableTiming));
+        CU(cudaHostAlloc((void **)&s.h_stats, sizeof(SlabStatsDev), cudaHostAllocDefault));
         CU(cudaMalloc((void **)&s.d_base, sizeof(uint32_t) * kBaseSlots));
+        CU(cudaMalloc((void **)&s.d_chunk_total, sizeof(uint32_t) * kBaseSlots));
+        CU(cudaMalloc((void **)&s.d_stats, sizeof(SlabStatsDev)));
     }
     if (pairs > s.cap_pairs) {
         int64_t cap = std::max<int64_t>(pairs, 1024);
@@ -1376,7 +1389,7 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
     const int64_t full = std::max<int64_t>(slab_pairs(false) / kChunk * kChunk, kChunk);
     std::vector<uint64_t> cw((size_t)(full / kChunk) + 1, 0);
     auto t0 = Clock::now();
-    const bool data_pinned = is_pinned(data), out_pinned = is_pinned(out);
+    const bool data_pinned = is_pinned(data), out_pinned = is_pinned(out), rec_pinned = is_pinned(rec);
     std::vector<double> kms((size_t)ng, 0.0);
     std::vector<PackedSlabOut> pending((size_t)ng * kRing);
     int rc = BSW_OK;
@@ -1411,96 +1424,103 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
         return BSW_OK;
     };
 
-    int64_t lo = 0;          // first pair of the next slab
-    uint64_t w_lo = 0;       // its first word in `data`
-    for (int sidx = 0; lo < n && rc == BSW_OK; ++sidx) {
+    // Two steps per slab, pipelined one slab apart: PREP (records -> device, bsw_rec_meta_kernel, statistics back) is
+    // issued for slab s + 1 before the host waits for the statistics of slab s, plans its launches and enqueues them.
+    struct PSlab { int d = 0, r = 0, ns = 0; int64_t lo = 0, nch = 0; bool valid = false; };
+    int prep_idx = 0;          // next slab to prepare
+    int64_t prep_lo = 0;       // its first pair
+    auto prep = [&](PSlab &ps) -> int {
+        ps.valid = false;
+        if (prep_lo >= n) return BSW_OK;
+        const int sidx = prep_idx;
         const int d = sidx % ng, r = (sidx / ng) % kRing;
         Device &dev = h->devs[(size_t)d];
         Slab &s = dev.ring[r];
-        if ((rc = cuda_rc(h, cudaSetDevice(dev.id), "cudaSetDevice"))) break;
-        if ((rc = finish(d, r))) break;
-        // slab sizes ramp up from 128 Ki pairs (the GPU starts after a fraction of a millisecond of host work and
-        // copying instead of a whole slab's) and taper off at the end (the last download and hand-over are short)
+        int e = cuda_rc(h, cudaSetDevice(dev.id), "cudaSetDevice");
+        if (e) return e;
+        if ((e = finish(d, r))) return e;
+        // slab sizes ramp up from 128 Ki pairs (the GPU starts after a fraction of a millisecond of copying instead of
+        // a whole slab's) and taper off at the end (the last download and hand-over are short)
         int64_t target = std::min<int64_t>(full, (int64_t)131072 << std::min(sidx / ng, 6));
-        if (use_taper() && n - lo <= target + target / 2 && n - lo > 2 * 131072)
-            target = std::max<int64_t>(131072, ((n - lo) / 2 + kChunk - 1) / kChunk * kChunk);
-        int64_t nch = (std::min(n - lo, target) + kChunk - 1) / kChunk;
-        int ns = 0;
-        uint64_t words = 0;
-        int maxq = 0, maxsc = 0, maxt = 0, maxh = 0, ntriv = 0, bad = 0;
-        // ---- ONE pass over the slab's records: validate, PairMeta in the caller's order with offsets relative to the
-        // pair's 4096-pair chunk (the key kernel adds the chunks' bases), launch histogram, maxima. Repeated over fewer
-        // chunks in the rare case that the slab exceeds the byte limit.
-        for (;;) {
-            t0 = Clock::now();
-            ns = (int)(std::min(n, lo + nch * kChunk) - lo);
-            rc = ensure_slab(h, s, ns, 0);
-            st.host_alloc_ms += ms_since(t0);
-            if (rc) break;
-            t0 = Clock::now();
-            s.lo = lo; s.n = ns; s.trivial.clear();
-            h->hist.assign((size_t)T * 2 * kMaxBins, 0);
-            maxq = maxsc = maxt = maxh = ntriv = bad = 0;
-#pragma omp parallel num_threads(T) reduction(max : maxq) reduction(max : maxsc) reduction(max : maxt) reduction(max : maxh) reduction(+ : ntriv) reduction(| : bad)
-            {
-                uint32_t *hist = h->hist.data() + (size_t)omp_get_thread_num() * 2 * kMaxBins;
-#pragma omp for schedule(static)
-                for (int64_t c = 0; c < nch; ++c) {
-                    uint32_t off = 0;
-                    const int64_t hi = std::min(n, lo + (c + 1) * kChunk);
-                    for (int64_t k = lo + c * kChunk; k < hi; ++k) {
-                        const bsw_packed_rec &rr = rec[k];
-                        if (rr.len1 > BSW_MAX_SEQ_LEN || rr.len2 > BSW_MAX_SEQ_LEN || rr.h0 < 0 ||
-                            (int64_t)rr.h0 + (int64_t)std::min(rr.len1, rr.len2) * match > 32767) { bad |= 1; continue; }
-                        const uint32_t wide = rr.flags & 1u;
-                        PairMeta &m = s.h_meta[k - lo];
-                        m.off = off;
-                        m.id = (uint32_t)(k - lo);
-                        m.len2 = rr.len2; m.len1 = rr.len1;
-                        m.h0 = (int16_t)rr.h0;
-                        m.flags = (uint16_t)(wide ? 3u : 0u);
-                        off += rec_words(rr);
-                        if (rr.len1 == 0 || rr.len2 == 0) { ++ntriv; continue; }
-                        hist[wide * kMaxBins + (uint32_t)(rr.len2 - 1) / kBinCols] += 1;
-                        maxq = std::max(maxq, (int)rr.len2);
-                        maxsc = std::max(maxsc, rr.h0 + (int)std::min(rr.len1, rr.len2) * match);
-                        maxt = std::max(maxt, (int)rr.len1);
-                        maxh = std::max(maxh, rr.h0);
-                    }
-                    cw[(size_t)c + 1] = off;
-                }
+        if (use_taper() && n - prep_lo <= target + target / 2 && n - prep_lo > 2 * 131072)
+            target = std::max<int64_t>(131072, ((n - prep_lo) / 2 + kChunk - 1) / kChunk * kChunk);
+        const int64_t nch = (std::min(n - prep_lo, target) + kChunk - 1) / kChunk;
+        const int ns = (int)(std::min(n, prep_lo + nch * kChunk) - prep_lo);
+        if (nch > kBaseSlots) return BSW_ERR_RANGE;
+        auto t1 = Clock::now();
+        e = ensure_slab(h, s, ns, 0);
+        st.host_alloc_ms += ms_since(t1);
+        if (e) return e;
+        // ---- records -> PairMeta ON THE DEVICE (bsw_rec_meta_kernel: sizes, chunk-relative offsets, validation, launch
+        // histogram, maxima; bsw_chunk_scan_kernel: chunk bases); the host reads the 16 KB statistics block only
+        t1 = Clock::now();
+        s.lo = prep_lo; s.n = ns; s.trivial.clear();
+        s.busy = true;      // (from here on work may be in flight on the slab's stream: see bsw_gpu_batch)
+        const bsw_packed_rec *rsrc = rec + prep_lo;
+        if (!rec_pinned) {   // 12 bytes per pair through the (otherwise unused) pinned meta buffer
+            char *dst = reinterpret_cast<char *>(s.h_meta);
+            const char *src = reinterpret_cast<const char *>(rsrc);
+            const size_t bytes = sizeof(bsw_packed_rec) * (size_t)ns;
+#pragma omp parallel for schedule(static)
+            for (int t = 0; t < T; ++t) {
+                const size_t a = bytes * (size_t)t / T & ~(size_t)63, b = t + 1 == T ? bytes : (bytes * (size_t)(t + 1) / T & ~(size_t)63);
+                memcpy(dst + a, src + a, b - a);
             }
-            if (bad) { rc = BSW_ERR_RANGE; break; }
-            cw[0] = 0;
-            int64_t fit = nch;
-            for (int64_t c = 0; c < nch; ++c) {
-                cw[(size_t)c + 1] += cw[(size_t)c];
-                if (cw[(size_t)c + 1] * 4 >= (uint64_t)kSlabBases / 4 && c + 1 < nch) { fit = c + 1; break; }
-            }
-            st.host_plan_ms += ms_since(t0);
-            if (fit == nch) break;
-            nch = fit;
+            rsrc = reinterpret_cast<const bsw_packed_rec *>(s.h_meta);
         }
-        if (rc) break;
-        words = cw[(size_t)nch];
-        if ((w_lo + words) * 4 > (uint64_t)data_bytes) { rc = BSW_ERR_ARG; break; }
-        if (words > 0xFFFFFF00ull || nch > kBaseSlots) { rc = BSW_ERR_RANGE; break; }
+        PackedRecDev *d_rec = reinterpret_cast<PackedRecDev *>(s.d_keys);   // 16 bytes per pair there; free until the key kernel
+        if ((e = cuda_rc(h, cudaMemcpyAsync(d_rec, rsrc, sizeof(bsw_packed_rec) * (size_t)ns, cudaMemcpyHostToDevice, s.stream), "H2D records"))) return e;
+        if ((e = cuda_rc(h, cudaMemsetAsync(s.d_stats, 0, sizeof(SlabStatsDev), s.stream), "memset"))) return e;
+        bsw_rec_meta_kernel<<<(int)nch, 256, 0, s.stream>>>(d_rec, ns, match, s.d_meta, s.d_chunk_total, s.d_stats);
+        bsw_chunk_scan_kernel<<<1, 256, 0, s.stream>>>(s.d_chunk_total, (int)nch, s.d_base, s.d_stats);
+        if ((e = cuda_rc(h, cudaGetLastError(), "record kernels"))) return e;
+        st.kernel_launches += 2;
+        if ((e = cuda_rc(h, cudaMemcpyAsync(s.h_stats, s.d_stats, sizeof(SlabStatsDev), cudaMemcpyDeviceToHost, s.stream), "D2H stats"))) return e;
+        if ((e = cuda_rc(h, cudaEventRecord(s.ev_stats, s.stream), "cudaEventRecord"))) return e;
+        st.host_plan_ms += ms_since(t1);
+        ps.d = d; ps.r = r; ps.ns = ns; ps.lo = prep_lo; ps.nch = nch; ps.valid = true;
+        prep_lo += ns;
+        ++prep_idx;
+        return BSW_OK;
+    };
+
+    uint64_t w_lo = 0;       // first word in `data` of the slab being launched
+    auto launch = [&](const PSlab &ps) -> int {
+        const int d = ps.d, r = ps.r, ns = ps.ns;
+        const int64_t lo = ps.lo;
+        Device &dev = h->devs[(size_t)d];
+        Slab &s = dev.ring[r];
+        int rc = cuda_rc(h, cudaSetDevice(dev.id), "cudaSetDevice");
+        if (rc) return rc;
+        {
+            auto tw = Clock::now();
+            rc = cuda_rc(h, cudaEventSynchronize(s.ev_stats), "cudaEventSynchronize");
+            st.host_wait_ms += ms_since(tw);
+            if (rc) return rc;
+        }
         t0 = Clock::now();
-        rc = ensure_slab(h, s, ns, data_pinned ? 0 : (size_t)words * 4 + 64);
+        const SlabStatsDev &sd = *s.h_stats;
+        if (sd.bad) return BSW_ERR_RANGE;
+        const uint64_t words = sd.total_words;
+        if ((w_lo + words) * 4 > (uint64_t)data_bytes) return BSW_ERR_ARG;
+        if (words > 0xFFFFFF00ull) return BSW_ERR_RANGE;
+        h->hist.assign((size_t)2 * kMaxBins, 0);
+        static_assert(kRecBins == kMaxBins, "device and host launch bins");
+        memcpy(h->hist.data(), &sd.hist[0][0], sizeof(uint32_t) * 2 * kMaxBins);
+        s.use_base = true;
+        s.fastm = (int64_t)sd.maxsc * (match + 1) <= 32767;
+        s.max_sc = sd.maxsc;
+        s.key_b1 = bits_for((uint32_t)sd.maxt);
+        s.key_b0 = bits_for((uint32_t)sd.maxh);
+        s.n_dev = ns - (int)sd.ntriv;
+        s.blob_bytes = (size_t)words * 4;
+        plan_slab(h, s, 1, sd.maxq);
+        st.host_plan_ms += ms_since(t0);
+        t0 = Clock::now();
+        if (!data_pinned) rc = ensure_slab(h, s, ns, (size_t)words * 4 + 64);
         if (!rc) rc = ensure_dblob(h, s, (size_t)words * 4 + 64);
         st.host_alloc_ms += ms_since(t0);
-        if (rc) break;
-        t0 = Clock::now();
-        for (int64_t c = 0; c < nch; ++c) s.h_base[c] = (uint32_t)cw[(size_t)c];
-        s.use_base = true;
-        s.fastm = (int64_t)maxsc * (match + 1) <= 32767;
-        s.max_sc = maxsc;
-        s.key_b1 = bits_for((uint32_t)maxt);
-        s.key_b0 = bits_for((uint32_t)maxh);
-        s.n_dev = ns - ntriv;
-        s.blob_bytes = (size_t)words * 4;
-        plan_slab(h, s, T, maxq);
-        st.host_plan_ms += ms_since(t0);
+        if (rc) return rc;
         // ---- the packed sequences: in place if page-locked, else through the slab's pinned blob
         const uint8_t *src = data + (size_t)w_lo * 4;
         if (!data_pinned && words) {
@@ -1515,30 +1535,37 @@ int bsw_gpu_batch_packed(bsw_handle *h, const bsw_packed_rec *rec, const uint8_t
             src = reinterpret_cast<const uint8_t *>(s.h_blob);
             st.host_pack_ms += ms_since(t0);
         }
-        s.busy = true;      // (from here on work may be in flight on the slab's stream: see bsw_gpu_batch)
-        if ((rc = cuda_rc(h, cudaMemcpyAsync(s.d_meta, s.h_meta, sizeof(PairMeta) * (size_t)ns, cudaMemcpyHostToDevice, s.stream), "H2D meta"))) break;
-        if ((rc = cuda_rc(h, cudaMemcpyAsync(s.d_base, s.h_base, sizeof(uint32_t) * (size_t)nch, cudaMemcpyHostToDevice, s.stream), "H2D chunk bases"))) break;
-        if (words && (rc = cuda_rc(h, cudaMemcpyAsync(s.d_blob, src, (size_t)words * 4, cudaMemcpyHostToDevice, s.stream), "H2D blob"))) break;
+        if (words && (rc = cuda_rc(h, cudaMemcpyAsync(s.d_blob, src, (size_t)words * 4, cudaMemcpyHostToDevice, s.stream), "H2D blob"))) return rc;
         // (the kernels read one word past a pair's target a refill period ahead)
-        if ((rc = cuda_rc(h, cudaMemsetAsync(reinterpret_cast<char *>(s.d_blob) + (size_t)words * 4, 0, 16, s.stream), "memset"))) break;
-        st.h2d_bytes += (int64_t)(sizeof(PairMeta) * (size_t)ns + (size_t)words * 4);
-        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k0, s.stream), "cudaEventRecord"))) break;
+        if ((rc = cuda_rc(h, cudaMemsetAsync(reinterpret_cast<char *>(s.d_blob) + (size_t)words * 4, 0, 16, s.stream), "memset"))) return rc;
+        st.h2d_bytes += (int64_t)(sizeof(bsw_packed_rec) * (size_t)ns + (size_t)words * 4);
+        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k0, s.stream), "cudaEventRecord"))) return rc;
         if (s.n_dev) {
-            if ((rc = bin_slab(h, s, s.stream))) break;
-            if ((rc = launch_slab(h, dev, s))) break;
+            if ((rc = bin_slab(h, s, s.stream))) return rc;
+            if ((rc = launch_slab(h, dev, s))) return rc;
         } else if (ns) {   // only pairs with an empty sequence: the key kernel answers them
             bsw_key_kernel<<<(ns + 255) / 256, 256, 0, s.stream>>>(s.d_meta, ns, s.d_keys, s.d_ord, s.key_b1, s.key_b0, s.long_bin0, s.d_out, nullptr);
         }
-        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k1, s.stream), "cudaEventRecord"))) break;
+        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_k1, s.stream), "cudaEventRecord"))) return rc;
         PackedSlabOut &po = pending[(size_t)d * kRing + r];
         po.n = ns;
         po.dst = out_pinned ? nullptr : out + lo;
         if ((rc = cuda_rc(h, cudaMemcpyAsync(out_pinned ? reinterpret_cast<void *>(out + lo) : reinterpret_cast<void *>(s.h_out), s.d_out,
-                                             sizeof(PairOut) * (size_t)ns, cudaMemcpyDeviceToHost, s.stream), "D2H out"))) break;
+                                             sizeof(PairOut) * (size_t)ns, cudaMemcpyDeviceToHost, s.stream), "D2H out"))) return rc;
         st.d2h_bytes += (int64_t)(sizeof(PairOut) * (size_t)ns);
-        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_done, s.stream), "cudaEventRecord"))) break;
-        lo += ns;
+        if ((rc = cuda_rc(h, cudaEventRecord(s.ev_done, s.stream), "cudaEventRecord"))) return rc;
         w_lo += words;
+        return BSW_OK;
+    };
+
+    {
+        PSlab cur, nxt;
+        rc = prep(cur);
+        while (rc == BSW_OK && cur.valid) {
+            if ((rc = prep(nxt))) break;      // the next slab's records are on their way while this one is planned
+            if ((rc = launch(cur))) break;
+            cur = nxt;
+        }
     }
     // drain (also on error, so that no stream still touches memory we or the caller may free)
     for (int d = 0; d < ng; ++d) {

@@ -1366,6 +1366,132 @@ __global__ void bsw_key_kernel(PairMeta *__restrict__ meta, int n, uint64_t *__r
 #endif
 
 // ---------------------------------------------------------------------------------------------
+// Packed input (bsw_gpu_batch_packed): the slab's 12-byte records -> PairMeta, ON THE DEVICE, so that the host's work
+// per slab does not grow with the pairs (it only waits for the small statistics block below and plans the launches).
+//   bsw_rec_meta_kernel : one block per chunk of 4096 pairs. Thread t owns 16 consecutive records: sizes them,
+//                         a block-wide exclusive sum gives its first word inside the chunk, it writes the 16
+//                         PairMeta (offsets chunk-relative: bsw_key_kernel adds the chunk's base), validates, and
+//                         feeds the (wide, len2 bin) histogram (privatised in shared memory) and the slab maxima.
+//   bsw_chunk_scan_kernel: exclusive sum of the chunk totals -> chunk bases, total words.
+// ---------------------------------------------------------------------------------------------
+struct PackedRecDev { uint16_t len1, len2; int32_t h0; uint32_t flags; };   // == bsw_packed_rec
+constexpr int kRecChunk = 4096;          // pairs per chunk (the host's cut granularity as well)
+constexpr int kRecBins = 2049;           // == BSW_MAX_SEQ_LEN / 16 + 2 (launch bins of 16 query lengths)
+struct SlabStatsDev {
+    uint32_t hist[2][kRecBins];          // [wide][(len2 - 1) / 16]
+    int32_t maxq, maxsc, maxt, maxh;     // longest query, largest h0 + min(len1, len2) * match, longest target, largest h0
+    uint32_t ntriv, bad;                 // pairs with an empty sequence; records outside the domain
+    uint64_t total_words;
+};
+
+#ifndef BSW_HOST_EMUL
+__global__ void __launch_bounds__(256)
+bsw_rec_meta_kernel(const PackedRecDev *__restrict__ rec, int n, int match, PairMeta *__restrict__ meta,
+                    uint32_t *__restrict__ chunk_total, SlabStatsDev *__restrict__ stats) {
+    __shared__ uint32_t s_hist[2][kRecBins];
+    __shared__ uint32_t s_warp[8];
+    __shared__ int s_max[4];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * kRecBins; i += 256) (&s_hist[0][0])[i] = 0u;
+    if (tid < 4) s_max[tid] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kRecChunk + tid * 16;
+    uint32_t words[16];
+    uint32_t sum = 0, ntriv = 0, bad = 0;
+    int maxq = 0, maxsc = 0, maxt = 0, maxh = 0;
+    PackedRecDev r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int k = base + i;
+        words[i] = 0;
+        if (k < n) {
+            r[i] = rec[k];
+            const bool wide = r[i].flags & 1u;
+            words[i] = (seq_bytes(r[i].len2, wide) + seq_bytes(r[i].len1, wide)) >> 2;
+            const int sc = r[i].h0 + (int)min(r[i].len1, r[i].len2) * match;
+            if (r[i].len1 > 32767 || r[i].len2 > 32767 || r[i].h0 < 0 || sc > 32767) bad = 1;
+            else if (r[i].len1 == 0 || r[i].len2 == 0) ++ntriv;
+            else {
+                atomicAdd(&s_hist[wide ? 1 : 0][(r[i].len2 - 1) >> 4], 1u);
+                maxq = max(maxq, (int)r[i].len2); maxsc = max(maxsc, sc);
+                maxt = max(maxt, (int)r[i].len1); maxh = max(maxh, r[i].h0);
+            }
+        }
+        sum += words[i];
+    }
+    // block-wide exclusive sum of the threads' totals (warp scan + scan of the 8 warp totals)
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((tid & 31) >= d) incl += y;
+    }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (w < (tid >> 5)) woff += s_warp[w];
+        total += s_warp[w];
+    }
+    uint32_t off = woff + incl - sum;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int k = base + i;
+        if (k < n) {
+            PairMeta m;
+            m.off = off; m.id = (uint32_t)k; m.len2 = r[i].len2; m.len1 = r[i].len1;
+            m.h0 = (int16_t)r[i].h0; m.flags = (uint16_t)((r[i].flags & 1u) ? 3u : 0u);
+            meta[k] = m;
+            off += words[i];
+        }
+    }
+    // statistics: warp-reduced, then one atomic per warp / block
+    maxq = __reduce_max_sync(0xFFFFFFFFu, maxq); maxsc = __reduce_max_sync(0xFFFFFFFFu, maxsc);
+    maxt = __reduce_max_sync(0xFFFFFFFFu, maxt); maxh = __reduce_max_sync(0xFFFFFFFFu, maxh);
+    ntriv = __reduce_add_sync(0xFFFFFFFFu, ntriv); bad = __reduce_or_sync(0xFFFFFFFFu, bad);
+    if ((tid & 31) == 0) {
+        atomicMax(&s_max[0], maxq); atomicMax(&s_max[1], maxsc); atomicMax(&s_max[2], maxt); atomicMax(&s_max[3], maxh);
+        if (ntriv) atomicAdd(&stats->ntriv, ntriv);
+        if (bad) atomicOr(&stats->bad, 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        chunk_total[blockIdx.x] = total;
+        atomicMax(&stats->maxq, s_max[0]); atomicMax(&stats->maxsc, s_max[1]);
+        atomicMax(&stats->maxt, s_max[2]); atomicMax(&stats->maxh, s_max[3]);
+    }
+    for (int i = tid; i < 2 * kRecBins; i += 256) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&stats->hist[0][0] + i, c);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bsw_chunk_scan_kernel(const uint32_t *__restrict__ chunk_total, int nch, uint32_t *__restrict__ chunk_base,
+                      SlabStatsDev *__restrict__ stats) {
+    __shared__ uint64_t s_part[256];
+    const int tid = threadIdx.x;
+    const int per = (nch + 255) / 256;
+    uint64_t sum = 0;
+    for (int i = 0; i < per; ++i) { const int c = tid * per + i; if (c < nch) sum += chunk_total[c]; }
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t run = 0;
+        for (int t = 0; t < 256; ++t) { const uint64_t x = s_part[t]; s_part[t] = run; run += x; }
+        stats->total_words = run;
+    }
+    __syncthreads();
+    uint64_t run = s_part[tid];
+    for (int i = 0; i < per; ++i) {
+        const int c = tid * per + i;
+        if (c < nch) { chunk_base[c] = (uint32_t)run; run += chunk_total[c]; }
+    }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // The scalar class: pairs whose score bound h0 + len2 * match leaves int16. bwa-mem2 sorts them out a priori
 // (bwamem.cpp:2218-2228, the third class of sortPairsLenExt :1846-1925) and runs them through the SCALAR kernel
 // (scalarBandedSWAWrapper, bwamem.cpp:2384-2390 -> bandedSWA.cpp:132-276), so its rules apply, not the vector
