@@ -461,6 +461,61 @@ def test_packed_file_through_the_driver(tmp_path):
     assert "Total Pairs processed: 30000" in r.stdout
 
 
+def test_random_call_sequences_on_one_handle(gpu):
+    """Thirty calls of random kind (byte buffers, packed from pageable / page-locked memory, staged, band-doubling
+    retry), size (0 .. 400 k pairs: single tiny slabs up to several slabs, so ring slots are reused with smaller and
+    larger contents in every order) and band on ONE handle; every result against the oracle."""
+    rng = np.random.default_rng(2024)
+    for step in range(30):
+        kind = ("batch", "packed", "packed_pinned", "staged", "retry")[int(rng.integers(0, 5))]
+        n = int(rng.choice([0, 1, 7, 513, 4097, 70_000, 150_000, 400_000]))
+        w = int(rng.choice([3, 30, 100]))
+        cfg = int(rng.choice([1, 4]))
+        c = pairio.preset(cfg)
+        c.n_frac = float(rng.choice([0.0, 0.3]))
+        if cfg == 4:
+            c.len2_max = 400
+        b = pairio.generate(c, max(n, 1), seed=1000 + step)
+        b = pairio.PairBatch(b.pairs[:n].copy(), b.ref, b.qer)
+        if n > 100:
+            b.pairs["len2"][3::211] = 0
+        a = b.copy()
+        if kind == "retry":
+            continue_ok = n > 0
+            if not continue_ok:
+                continue
+            tries = gpu.batch_retry(b.pairs, b.ref, b.qer, w, 2)
+            # the same loop with the oracle (bwamem.cpp:2448-2508)
+            oracle.oracle_batch(a, w=w)
+            lim = (w >> 1) + (w >> 2)
+            again = np.nonzero(a.pairs["max_off"] >= lim)[0]
+            if len(again):
+                sub = pairio.PairBatch(a.pairs[again].copy(), a.ref, a.qer)
+                oracle.oracle_batch(sub, w=2 * w)
+                for f in pairio.OUTPUT_FIELDS:
+                    a.pairs[f][again] = sub.pairs[f]
+            assert (tries[again] == 2).all()
+            got = b.outputs()
+        elif kind == "batch":
+            gpu.batch(b.pairs, b.ref, b.qer, w)
+            oracle.oracle_batch(a, w=w)
+            got = b.outputs()
+        elif kind == "staged":
+            if n == 0:
+                continue
+            gpu.stage(b.pairs, b.ref, b.qer, w)
+            gpu.run_staged()
+            gpu.fetch_staged(b.pairs)
+            oracle.oracle_batch(a, w=w)
+            got = b.outputs()
+        else:
+            rec, data = pairio.pack(b, bsw.host_alloc if kind == "packed_pinned" else None)
+            res = gpu.batch_packed(rec, data, w)
+            oracle.oracle_batch(a, w=w)
+            got = bsw.results_to_outputs(res)
+        assert_same_outputs(got, a.outputs(), a, f"call {step}: {kind}, n={n}, w={w}, config {cfg}")
+
+
 def test_two_pairs_per_thread_kernel_matches_oracle():
     """BSW_DUO2=1 routes the short bins to extend_duo2 (bsw_duo.cuh: the two DPX lanes are the same cell of two
     neighbouring pairs; an evaluated alternative, off by default). The switch is read once per process."""
