@@ -1,0 +1,417 @@
+// kswv_gpu.cu -- host side of the kswv path (include/kswv_gpu.h): chunks of pairs flow through a ring of three
+// slots per GPU (tasks + sequences H2D, one persistent-warp kernel, results D2H), the host orders each chunk's
+// tasks by decreasing DP size and scatters finished results to aln[regid]. Kernels: kswv_kernels.cuh.
+#include <cuda_runtime.h>
+#include <omp.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "bsw_gpu.h"
+#include "kswv_gpu.h"
+#include "kswv_kernels.cuh"
+
+using namespace kswvk;
+
+namespace {
+
+constexpr int kRing = 3;
+constexpr int64_t kChunkPairs = 32768;          // pairs per chunk (about 40 MB of sequence at 150 bp reads)
+constexpr int64_t kChunkBytes = 96ll << 20;     // and at most this many sequence bytes
+constexpr int kBlocksPerSm = 4;                 // x kKswvWarps warps
+
+struct KSlot {
+    Task *h_tasks = nullptr, *d_tasks = nullptr;
+    Result *h_out = nullptr, *d_out = nullptr;
+    uint8_t *h_seq = nullptr;                   // gather staging (only when a chunk is not one dense range)
+    uint8_t *d_ref = nullptr, *d_qer = nullptr;
+    int *d_counter = nullptr;
+    size_t cap_pairs = 0, cap_ref = 0, cap_qer = 0, cap_seq = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    bool busy = false;
+    int64_t first = 0, count = 0;               // the chunk in flight: pairs [first, first + count)
+};
+
+struct KDev {
+    int id = 0, sms = 0, warps = 0;
+    cudaStream_t st = nullptr;
+    KSlot slot[kRing];
+    uint16_t *d_rowmx = nullptr;
+    uint2 *d_bnd = nullptr;
+    size_t cap_rows = 0, cap_bnd = 0;
+    int next = 0;
+};
+
+}  // namespace
+
+struct kswv_handle {
+    kswv_params P;
+    KParams K;
+    std::vector<KDev> devs;
+    kswv_gpu_stats stats;
+    char err[256];
+};
+
+namespace {
+
+void set_err(kswv_handle *h, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof h->err, fmt, ap);
+    va_end(ap);
+}
+
+#define KCU(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            set_err(h, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);        \
+            return e_ == cudaErrorMemoryAllocation ? BSW_ERR_NOMEM : BSW_ERR_CUDA;                  \
+        }                                                                                           \
+    } while (0)
+
+template <typename T>
+int grow_dev(kswv_handle *h, T *&p, size_t &cap, size_t need) {
+    if (need <= cap) return BSW_OK;
+    if (p) KCU(cudaFree(p));
+    p = nullptr; cap = 0;
+    const size_t want = need + need / 4 + 256;
+    KCU(cudaMalloc((void **)&p, want * sizeof(T)));
+    cap = want;
+    return BSW_OK;
+}
+
+template <typename T>
+int grow_host(kswv_handle *h, T *&p, size_t have, size_t want) {
+    (void)have;
+    if (p) KCU(cudaFreeHost(p));
+    p = nullptr;
+    KCU(cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault));
+    return BSW_OK;
+}
+
+int ensure_dev(kswv_handle *h, KDev &d) {
+    if (d.st) return BSW_OK;
+    KCU(cudaSetDevice(d.id));
+    KCU(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
+    for (KSlot &s : d.slot) {
+        KCU(cudaEventCreate(&s.ev_start));
+        KCU(cudaEventCreate(&s.ev_stop));
+        KCU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        KCU(cudaMalloc((void **)&s.d_counter, sizeof(int)));
+    }
+    d.warps = d.sms * kBlocksPerSm * kKswvWarps;
+    return BSW_OK;
+}
+
+int ensure_slot(kswv_handle *h, KSlot &s, size_t npairs, size_t ref_bytes, size_t qer_bytes, size_t gather_bytes) {
+    if (npairs > s.cap_pairs) {
+        const size_t want = npairs + npairs / 4 + 256;
+        if (s.d_tasks) KCU(cudaFree(s.d_tasks));
+        if (s.d_out) KCU(cudaFree(s.d_out));
+        s.d_tasks = nullptr; s.d_out = nullptr; s.cap_pairs = 0;
+        int rc = grow_host(h, s.h_tasks, 0, want);
+        if (rc) return rc;
+        rc = grow_host(h, s.h_out, 0, want);
+        if (rc) return rc;
+        KCU(cudaMalloc((void **)&s.d_tasks, want * sizeof(Task)));
+        KCU(cudaMalloc((void **)&s.d_out, want * sizeof(Result)));
+        s.cap_pairs = want;
+    }
+    int rc = grow_dev(h, s.d_ref, s.cap_ref, ref_bytes + 64);
+    if (rc) return rc;
+    rc = grow_dev(h, s.d_qer, s.cap_qer, qer_bytes + 64);
+    if (rc) return rc;
+    if (gather_bytes > s.cap_seq) {
+        const size_t want = gather_bytes + gather_bytes / 4 + 4096;
+        rc = grow_host(h, s.h_seq, 0, want);
+        if (rc) return rc;
+        s.cap_seq = want;
+    }
+    return BSW_OK;
+}
+
+void free_dev(KDev &d) {
+    cudaSetDevice(d.id);
+    for (KSlot &s : d.slot) {
+        if (s.h_tasks) cudaFreeHost(s.h_tasks);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.h_seq) cudaFreeHost(s.h_seq);
+        if (s.d_tasks) cudaFree(s.d_tasks);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_ref) cudaFree(s.d_ref);
+        if (s.d_qer) cudaFree(s.d_qer);
+        if (s.d_counter) cudaFree(s.d_counter);
+        if (s.ev_start) cudaEventDestroy(s.ev_start);
+        if (s.ev_stop) cudaEventDestroy(s.ev_stop);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    if (d.d_rowmx) cudaFree(d.d_rowmx);
+    if (d.d_bnd) cudaFree(d.d_bnd);
+    if (d.st) cudaStreamDestroy(d.st);
+}
+
+inline int padded_cols(int qlen, bool byte) {
+    const int q = byte ? 16 : 8;
+    const int n = (qlen + q - 1) / q * q;
+    return n == 0 ? q : n;
+}
+
+// waits for the slot's chunk, scatters its results to aln[regid], adds its kernel time
+int drain_slot(kswv_handle *h, KDev &d, KSlot &s, const bsw_seqpair *pairs, kswv_result *aln) {
+    if (!s.busy) return BSW_OK;
+    KCU(cudaSetDevice(d.id));
+    KCU(cudaEventSynchronize(s.ev_done));
+    float ms = 0;
+    KCU(cudaEventElapsedTime(&ms, s.ev_start, s.ev_stop));
+    h->stats.kernel_ms += ms;
+    const bsw_seqpair *p = pairs + s.first;
+    const Result *r = s.h_out;
+    static_assert(sizeof(Result) == sizeof(kswv_result), "Result is kswr_t");
+#pragma omp parallel for schedule(static) if (s.count > 4096)
+    for (int64_t i = 0; i < s.count; ++i) memcpy(&aln[p[i].regid], &r[i], sizeof(Result));
+    s.busy = false;
+    return BSW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kswv_gpu_init(const kswv_params *params, int n_gpus, kswv_handle **out) {
+    if (!params || !out) return BSW_ERR_ARG;
+    *out = nullptr;
+    const kswv_params &p = *params;
+    if (p.match <= 0 || p.match > 127 || p.mismatch <= 0 || p.mismatch > 127 || p.o_del < 0 || p.o_ins < 0 ||
+        p.e_del <= 0 || p.e_ins <= 0 || p.o_del + p.e_del > 127 || p.o_ins + p.e_ins > 127 ||
+        p.match + p.mismatch > 254)
+        return BSW_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return BSW_ERR_NO_DEVICE;
+    const int want = n_gpus > 0 ? n_gpus : ndev;
+    if (want > ndev) return BSW_ERR_NO_DEVICE;
+    kswv_handle *h = new (std::nothrow) kswv_handle();
+    if (!h) return BSW_ERR_NOMEM;
+    h->P = p;
+    h->K = make_kparams(p.o_del, p.e_del, p.o_ins, p.e_ins, p.match, p.mismatch);
+    h->err[0] = 0;
+    memset(&h->stats, 0, sizeof h->stats);
+    h->stats.n_gpus = want;
+    h->devs.resize((size_t)want);
+    for (int d = 0; d < want; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) != cudaSuccess || prop.major < 10) {
+            delete h;
+            return BSW_ERR_NO_DEVICE;           // kernels are sm_100a only
+        }
+        h->devs[(size_t)d].id = d;
+        h->devs[(size_t)d].sms = prop.multiProcessorCount;
+    }
+    *out = h;
+    return BSW_OK;
+}
+
+void kswv_gpu_free(kswv_handle *h) {
+    if (!h) return;
+    for (KDev &d : h->devs) free_dev(d);
+    delete h;
+}
+
+int kswv_gpu_get_stats(const kswv_handle *h, kswv_gpu_stats *out) {
+    if (!h || !out) return BSW_ERR_ARG;
+    *out = h->stats;
+    return BSW_OK;
+}
+
+const char *kswv_gpu_last_error(const kswv_handle *h) { return h ? h->err : "null handle"; }
+
+static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                           int64_t n, kswv_result *aln);
+
+int kswv_gpu_batch(kswv_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                   int64_t n, kswv_result *aln) {
+    const int rc = kswv_batch_impl(h, pairs, ref, qer, n, aln);
+    if (rc != BSW_OK && h)      // nothing may stay in flight towards the caller's arrays after a failed call
+        for (KDev &d : h->devs) {
+            if (!d.st) continue;
+            cudaSetDevice(d.id);
+            cudaStreamSynchronize(d.st);
+            for (KSlot &s : d.slot) s.busy = false;
+        }
+    return rc;
+}
+
+static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
+                           int64_t n, kswv_result *aln) {
+    if (!h || n < 0 || (n > 0 && (!pairs || !ref || !qer || !aln))) return BSW_ERR_ARG;
+    const auto t0 = std::chrono::steady_clock::now();
+    kswv_gpu_stats &S = h->stats;
+    S.chunks = 0; S.pairs = n; S.pairs8 = 0; S.cells = 0; S.h2d_bytes = 0; S.d2h_bytes = 0; S.kernel_launches = 0;
+    S.gathered = 0; S.kernel_ms = 0; S.wall_ms = 0;
+    h->err[0] = 0;
+    if (n == 0) return BSW_OK;
+
+    // ---- validation and totals (one host pass over the 72-byte records)
+    int64_t bad = -1, n8 = 0, cells = 0;
+    int bad_kind = 0;
+    int maxT = 0, maxCols = 0;
+#pragma omp parallel for schedule(static) reduction(+ : n8) reduction(+ : cells) reduction(max : maxT) reduction(max : maxCols)
+    for (int64_t i = 0; i < n; ++i) {
+        const bsw_seqpair &sp = pairs[i];
+        const bool byte = (sp.h0 & kXByte) != 0;
+        int kind = 0;
+        if (sp.len1 < 0 || sp.len2 < 0 || sp.len1 > 32767 || sp.len2 > 32767 || sp.idr < 0 || sp.idq < 0) kind = 1;
+        else if (!byte && (int64_t)std::min(sp.len1, sp.len2) * h->P.match > 32767) kind = 1;
+        else if (sp.regid < 0 || sp.regid >= n) kind = 2;
+        if (kind) {
+#pragma omp critical
+            if (bad < 0 || i < bad) { bad = i; bad_kind = kind; }
+            continue;
+        }
+        n8 += byte;
+        const int nc = padded_cols(sp.len2, byte);
+        cells += (int64_t)sp.len1 * nc;
+        maxT = std::max(maxT, sp.len1);
+        maxCols = std::max(maxCols, nc);
+    }
+    if (bad >= 0) {
+        set_err(h, bad_kind == 2 ? "pair %lld: regid %d outside [0, n_pairs)" : "pair %lld outside the kswv domain (len1=%d len2=%d)",
+                (long long)bad, bad_kind == 2 ? pairs[bad].regid : pairs[bad].len1, pairs[bad].len2);
+        return bad_kind == 2 ? BSW_ERR_ARG : BSW_ERR_RANGE;
+    }
+    S.pairs8 = n8; S.cells = cells;
+
+    // ---- per-device scratch: one row-maximum column (and one boundary column for queries above 256 columns) per warp
+    for (KDev &d : h->devs) {
+        int rc = ensure_dev(h, d);
+        if (rc) return rc;
+        KCU(cudaSetDevice(d.id));
+        const size_t rows = (size_t)maxT + 8;
+        rc = grow_dev(h, d.d_rowmx, d.cap_rows, rows * (size_t)d.warps);
+        if (rc) return rc;
+        if (maxCols > kPassCols) {
+            rc = grow_dev(h, d.d_bnd, d.cap_bnd, rows * (size_t)d.warps);
+            if (rc) return rc;
+        }
+    }
+    const int scratch_rows = maxT + 8;
+
+    // ---- chunks
+    int rc = BSW_OK;
+    size_t dev_rr = 0;
+    std::vector<uint32_t> order, bucket_start;
+    for (int64_t first = 0; first < n && rc == BSW_OK;) {
+        // cut: at most kChunkPairs pairs / kChunkBytes sequence bytes; small batches are split across the GPUs
+        int64_t target = kChunkPairs;
+        const int64_t per_gpu = (n + (int64_t)h->devs.size() - 1) / (int64_t)h->devs.size();
+        if (per_gpu < target) target = std::max<int64_t>(per_gpu, 1);
+        int64_t cnt = 0, bytes = 0;
+        int64_t rlo = INT64_MAX, rhi = 0, qlo = INT64_MAX, qhi = 0, rsum = 0, qsum = 0;
+        bool ordered = true;
+        while (first + cnt < n && cnt < target) {
+            const bsw_seqpair &sp = pairs[first + cnt];
+            if (cnt > 0 && bytes + sp.len1 + sp.len2 > kChunkBytes) break;
+            if (sp.idr < rhi || sp.idq < qhi) ordered = false;
+            rlo = std::min<int64_t>(rlo, sp.idr); rhi = std::max<int64_t>(rhi, sp.idr + sp.len1);
+            qlo = std::min<int64_t>(qlo, sp.idq); qhi = std::max<int64_t>(qhi, sp.idq + sp.len2);
+            rsum += sp.len1; qsum += sp.len2;
+            bytes += sp.len1 + sp.len2;
+            ++cnt;
+        }
+        // one dense range per buffer (the production layout: mem_matesw_batch_pre appends, bwamem_pair.cpp:1006-1013)?
+        const bool dense = ordered && (rhi - rlo) <= rsum + rsum / 8 + 4096 && (qhi - qlo) <= qsum + qsum / 8 + 4096 &&
+                           (rhi - rlo) < (1ll << 32) && (qhi - qlo) < (1ll << 32);
+        KDev &d = h->devs[dev_rr % h->devs.size()];
+        ++dev_rr;
+        KCU(cudaSetDevice(d.id));
+        KSlot &s = d.slot[d.next];
+        d.next = (d.next + 1) % kRing;
+        rc = drain_slot(h, d, s, pairs, aln);
+        if (rc) break;
+        const size_t ref_bytes = dense ? (size_t)(rhi - rlo) : (size_t)rsum;
+        const size_t qer_bytes = dense ? (size_t)(qhi - qlo) : (size_t)qsum;
+        rc = ensure_slot(h, s, (size_t)cnt, ref_bytes, qer_bytes, dense ? 0 : (size_t)(rsum + qsum) + 64);
+        if (rc) break;
+
+        // tasks in decreasing DP size (counting sort on rows x padded columns, 1024 buckets)
+        const bsw_seqpair *cp = pairs + first;
+        order.resize((size_t)cnt);
+        {
+            constexpr int kBuckets = 1024;
+            int64_t maxcost = 1;
+            for (int64_t i = 0; i < cnt; ++i)
+                maxcost = std::max<int64_t>(maxcost, (int64_t)cp[i].len1 * padded_cols(cp[i].len2, (cp[i].h0 & kXByte) != 0));
+            bucket_start.assign(kBuckets + 1, 0);
+            auto bucket_of = [&](int64_t i) {
+                const int64_t c = (int64_t)cp[i].len1 * padded_cols(cp[i].len2, (cp[i].h0 & kXByte) != 0);
+                return (int)(kBuckets - 1 - c * (kBuckets - 1) / maxcost);           // large first
+            };
+            for (int64_t i = 0; i < cnt; ++i) ++bucket_start[(size_t)bucket_of(i) + 1];
+            for (int b = 0; b < kBuckets; ++b) bucket_start[(size_t)b + 1] += bucket_start[(size_t)b];
+            for (int64_t i = 0; i < cnt; ++i) order[bucket_start[(size_t)bucket_of(i)]++] = (uint32_t)i;
+        }
+        if (dense) {
+#pragma omp parallel for schedule(static) if (cnt > 4096)
+            for (int64_t j = 0; j < cnt; ++j) {
+                const uint32_t i = order[(size_t)j];
+                const bsw_seqpair &sp = cp[i];
+                s.h_tasks[j] = Task{(uint32_t)(sp.idr - rlo), (uint32_t)(sp.idq - qlo), sp.len1, sp.len2, sp.h0, (int32_t)i};
+            }
+        } else {
+            // gather: offsets by a prefix sum in the caller's order, then the copies in parallel
+            std::vector<uint32_t> roff((size_t)cnt), qoff((size_t)cnt);
+            uint32_t ro = 0, qo = 0;
+            for (int64_t i = 0; i < cnt; ++i) { roff[(size_t)i] = ro; qoff[(size_t)i] = qo; ro += (uint32_t)cp[i].len1; qo += (uint32_t)cp[i].len2; }
+            uint8_t *gr = s.h_seq, *gq = s.h_seq + rsum;
+#pragma omp parallel for schedule(static) if (cnt > 1024)
+            for (int64_t i = 0; i < cnt; ++i) {
+                memcpy(gr + roff[(size_t)i], ref + cp[i].idr, (size_t)cp[i].len1);
+                memcpy(gq + qoff[(size_t)i], qer + cp[i].idq, (size_t)cp[i].len2);
+            }
+            for (int64_t j = 0; j < cnt; ++j) {
+                const uint32_t i = order[(size_t)j];
+                s.h_tasks[j] = Task{roff[i], qoff[i], cp[i].len1, cp[i].len2, cp[i].h0, (int32_t)i};
+            }
+            ++S.gathered;
+        }
+        // ---- enqueue
+        KCU(cudaMemcpyAsync(s.d_tasks, s.h_tasks, sizeof(Task) * (size_t)cnt, cudaMemcpyHostToDevice, d.st));
+        if (dense) {
+            if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, ref + rlo, ref_bytes, cudaMemcpyHostToDevice, d.st));
+            if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, qer + qlo, qer_bytes, cudaMemcpyHostToDevice, d.st));
+        } else {
+            if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, s.h_seq, ref_bytes, cudaMemcpyHostToDevice, d.st));
+            if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, s.h_seq + rsum, qer_bytes, cudaMemcpyHostToDevice, d.st));
+        }
+        KCU(cudaMemsetAsync(s.d_counter, 0, sizeof(int), d.st));
+        KCU(cudaEventRecord(s.ev_start, d.st));
+        const int blocks = (int)std::min<int64_t>((cnt + kKswvWarps - 1) / kKswvWarps, (int64_t)d.sms * kBlocksPerSm);
+        kswv_kernel<<<blocks, kKswvWarps * 32, 0, d.st>>>(h->K, s.d_tasks, (int)cnt, s.d_ref, s.d_qer, s.d_out, d.d_rowmx,
+                                                           maxCols > kPassCols ? d.d_bnd : nullptr, scratch_rows, s.d_counter);
+        KCU(cudaGetLastError());
+        KCU(cudaEventRecord(s.ev_stop, d.st));
+        KCU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(Result) * (size_t)cnt, cudaMemcpyDeviceToHost, d.st));
+        KCU(cudaEventRecord(s.ev_done, d.st));
+        s.busy = true; s.first = first; s.count = cnt;
+        S.h2d_bytes += (int64_t)(sizeof(Task) * (size_t)cnt + ref_bytes + qer_bytes);
+        S.d2h_bytes += (int64_t)(sizeof(Result) * (size_t)cnt);
+        ++S.kernel_launches; ++S.chunks;
+        first += cnt;
+    }
+    // ---- drain, oldest first on every device
+    for (KDev &d : h->devs)
+        for (int j = 0; j < kRing; ++j) {
+            KSlot &s = d.slot[(d.next + j) % kRing];
+            const int rc2 = drain_slot(h, d, s, pairs, aln);
+            if (rc == BSW_OK) rc = rc2;
+        }
+    S.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+}  // extern "C"

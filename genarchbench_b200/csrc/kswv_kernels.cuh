@@ -1,0 +1,329 @@
+// kswv on the GPU: bwa-mem2's batched mate-rescue Smith-Waterman (class kswv,
+// /root/reference/benchmarks/fmi/bwa-mem2/x86_64/src/kswv.cpp), one WARP per pair.
+//
+// What is computed is what one lane of the reference's 64/32-lane vector kernels computes (kswv512_u8
+// kswv.cpp:371-716, kswv512_16 :933-1215; see oracle/kswv_oracle.c for the statement-by-statement
+// restatement): a full (unbanded) local-alignment DP over len1 rows x the query padded to a multiple of 16
+// (8-bit class) or 8 (16-bit class) zero-score columns, the row maxima with their first column, gmax/te/qe,
+// the early stop on KSW_XSTOP / 8-bit saturation, the second-best row maximum from the reference's
+// rising-row filter, and the reverse pass for tb/qb (phase 1 of mem_sam_pe_batch, bwamem_pair.cpp:660-699).
+//
+// Mapping. The query's padded columns are split into 32 strips of C consecutive columns, one per lane
+// (C = ceil(columns / 32), 1..8; queries above 256 columns take several 256-column passes with the boundary
+// column kept in global memory). Lane k works on row s - k at step s: H and F of its strip live in
+// registers, and what a row needs from the left -- H and E of the strip's last column and the running row
+// maximum -- arrives by one shuffle pair per step. A cell is 10 integer instructions: one PRMT looks up the
+// signed score, VIADDMNMX adds it to the diagonal and clamps (the 8-bit class's saturation is that clamp, at
+// 255 - shift), VIMNMX3 with relu forms H, two IADD + two VIADDMNMX update E and F, and LEA + VIADDMNMX keep
+// the row maximum as a key (H << 16 | 0xFFFF - column) whose maximum is the FIRST column of the largest H.
+// Columns added on the left to fill the strips score negative against everything and therefore stay at zero.
+// The last active lane sees the finished row: it updates gmax/te/qe, stores the row maximum (2 bytes) for the
+// second-best pass and raises the stop flag, which ends the warp's loop at the next step.
+#pragma once
+#include <stdint.h>
+
+#ifdef BSW_HOST_EMUL
+#include "dpx_host_emul.h"
+#include "warp_fibers.h"
+static inline int __viaddmin_s32(int a, int b, int c) { return std::min((int)((uint32_t)a + (uint32_t)b), c); }
+static inline int __viaddmax_s32_relu(int a, int b, int c) { return std::max(std::max((int)((uint32_t)a + (uint32_t)b), c), 0); }
+static inline int __vimax3_s32_relu(int a, int b, int c) { return std::max(std::max(std::max(a, b), c), 0); }
+#else
+#include <cuda_runtime.h>
+#endif
+
+namespace kswvk {
+
+constexpr int kXByte = 0x10000, kXStop = 0x20000, kXSubo = 0x40000, kXStart = 0x80000;   // ksw.h:31-34
+constexpr int kPassCols = 256;      // columns one pass of a warp covers (32 lanes x 8)
+constexpr int kNoStop = 0x7FFFFFFF;
+
+struct KParams {
+    int32_t a, b, amb;                        // match, mismatch (negative), ambiguous (-1, kswv.cpp:131)
+    int32_t oe_del, e_del, oe_ins, e_ins;
+    int32_t qmax, shift;                      // g_qmax (kswv.cpp:132-133), the 8-bit bias (kswv.cpp:396-404)
+    uint32_t lut_mis, lut_ab, lut_amb, lut_hi;
+};
+
+struct Task { uint32_t roff, qoff; int32_t tlen, qlen, xtra, out; };
+struct Result { int32_t score, te, qe, score2, te2, tb, qb; };   // == kswr_t, ksw.h:45-50
+
+// ------------------------------------------------------------------ warp primitives
+#ifdef BSW_HOST_EMUL
+inline int w_lane() { return wf::lane(); }
+inline uint32_t w_up1(uint32_t v) { return wf::shfl_up1(v); }
+inline uint32_t w_from(uint32_t v, int src) { return wf::shfl(v, src); }
+inline bool w_any(bool p) { return wf::any(p); }
+inline uint32_t w_ballot(bool p) { return wf::ballot(p); }
+inline uint32_t w_max(uint32_t v) { return wf::reduce_max(v); }
+inline void w_sync() { wf::syncwarp(); }
+inline uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) { return emul::prmt(a, b, sel); }
+#else
+__device__ __forceinline__ int w_lane() { return (int)(threadIdx.x & 31u); }
+__device__ __forceinline__ uint32_t w_up1(uint32_t v) { return __shfl_up_sync(0xFFFFFFFFu, v, 1); }
+__device__ __forceinline__ uint32_t w_from(uint32_t v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+__device__ __forceinline__ bool w_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
+__device__ __forceinline__ uint32_t w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+__device__ __forceinline__ uint32_t w_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+__device__ __forceinline__ void w_sync() { __syncwarp(); }
+// PTX prmt.b32, default mode: a selector nibble with bit 3 set replicates the selected byte's sign bit
+__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+#endif
+
+// host side of KParams: the two LUT words. Byte q of lut_lo(r) is the score of reference base r against query
+// code q = 0..3; lut_hi holds query codes 4 (ambiguous), 5 (zero-score padding column), 6 (left filler: negative).
+inline KParams make_kparams(int o_del, int e_del, int o_ins, int e_ins, int match, int mismatch) {
+    KParams K;
+    K.a = match; K.b = -mismatch; K.amb = -1;
+    K.oe_del = o_del + e_del; K.e_del = e_del; K.oe_ins = o_ins + e_ins; K.e_ins = e_ins;
+    K.qmax = match > K.amb ? match : K.amb;
+    if (K.b > K.qmax) K.qmax = K.b;
+    int mn = K.a < K.b ? K.a : K.b;
+    if (K.amb < mn) mn = K.amb;
+    K.shift = (uint8_t)(256 - (uint8_t)mn);
+    const uint32_t A = (uint8_t)(int8_t)K.a, B = (uint8_t)(int8_t)K.b, N = (uint8_t)(int8_t)K.amb;
+    K.lut_mis = B * 0x01010101u;
+    K.lut_ab = A ^ B;
+    K.lut_amb = N * 0x01010101u;
+    K.lut_hi = N | (0u << 8) | (N << 16) | (N << 24);
+    return K;
+}
+
+struct Best { int32_t gmax, te, qe, rows; bool dead; };
+
+// One pass structure: the DP of t[0..tlen) x q[0..qlen) (padded) on one warp.
+//  rt    : the first rt reference bases are read in reverse order (phase 1), 0 in phase 0
+//  qrev  : the query is read in reverse order (phase 1)
+//  thr   : gmax >= thr ends the lane (kNoStop: never)
+//  rowmx : if non-null, row i's maximum is stored at rowmx[i] for rows 0 .. rows-1
+//  bnd   : boundary column between passes (queries above 256 columns), tlen entries
+template <int C>
+__device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict__ t, int tlen, int rt,
+                        const uint8_t *__restrict__ q, int qlen, bool qrev, bool byte, int thr,
+                        uint16_t *rowmx, uint2 *bnd) {
+    const int k = w_lane();
+    const int quantum = byte ? 16 : 8;
+    int ncol = (qlen + quantum - 1) / quantum * quantum;
+    if (ncol == 0) ncol = quantum;          // an empty query is all padding: every H stays 0
+    const int npass = (ncol + kPassCols - 1) / kPassCols;
+    // scalars by value: K sits in the caller's local memory and would be re-read every step
+    const int clamp = byte ? 255 - K.shift : 32767;
+    const int noe_ins = -K.oe_ins, noe_del = -K.oe_del, e_ins = K.e_ins, e_del = K.e_del;
+    const uint32_t lut_mis = K.lut_mis, lut_ab = K.lut_ab, lut_amb = K.lut_amb, lut_hi = K.lut_hi;
+
+    int gmax = 0, te = -1, qcol = 0, rows = 0;
+    bool dead = false;
+    int pad = 0;
+    for (int p = 0; p < npass; ++p) {
+        const int c_lo = p * kPassCols;
+        const int pcols = (ncol - c_lo < kPassCols) ? ncol - c_lo : kPassCols;
+        const int nl = (pcols + C - 1) / C;
+        pad = nl * C - pcols;               // only non-zero in a single-pass DP (C divides 256)
+        const int last = nl - 1;
+        const bool lastpass = p == npass - 1;
+        int H[C], F[C];
+        uint32_t sel[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int gc = c_lo + k * C + c - pad;
+            uint32_t code;
+            if (gc < 0 || k >= nl) code = 6u;
+            else if (gc >= qlen) code = 5u;
+            else {
+                const uint32_t b = q[qrev ? qlen - 1 - gc : gc];
+                code = b > 3u ? 4u : b;
+            }
+            sel[c] = code * 0x1111u + 0x8880u;
+            H[c] = 0; F[c] = 0;
+        }
+        const int kc0 = 0xFFFF - (c_lo + k * C);
+        int hdiag = 0;
+        uint32_t out_he = 0, out_key = 0;
+        const int steps = tlen + nl - 1;
+        for (int s = 0; s < steps; ++s) {
+            if (lastpass && w_any(dead)) break;
+            uint32_t in_he = w_up1(out_he), in_key = w_up1(out_key);
+            const int i = s - k;
+            const bool active = k < nl && i >= 0 && i < tlen;
+            if (k == 0) {
+                in_he = 0; in_key = 0;
+                if (p > 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
+            }
+            if (active) {
+                uint32_t r = t[i < rt ? rt - 1 - i : i];
+                const uint32_t lut_lo = r > 3u ? lut_amb : (lut_mis ^ (lut_ab << (8u * r)));
+                const int hl = (int)(in_he & 0xFFFFu);
+                int e = (int)(in_he >> 16);
+                int key = (int)in_key;
+                int diag = hdiag;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int sc = (int)prmt_sx(lut_lo, lut_hi, sel[c]);
+                    const int x = __viaddmin_s32(diag, sc, clamp);
+                    diag = H[c];
+                    const int f = F[c];
+                    const int h = __vimax3_s32_relu(x, e, f);
+                    key = __viaddmax_s32((h << 16) + kc0, -c, key);
+                    e = __viaddmax_s32_relu(h, noe_ins, e - e_ins);
+                    F[c] = __viaddmax_s32_relu(h, noe_del, f - e_del);
+                    H[c] = h;
+                }
+                hdiag = hl;
+                out_he = (uint32_t)H[C - 1] | ((uint32_t)e << 16);
+                out_key = (uint32_t)key;
+                if (k == last) {
+                    if (lastpass) {
+                        const int rmax = key >> 16;
+                        if (rmax > gmax) { gmax = rmax; te = i; qcol = 0xFFFF - (key & 0xFFFF); }
+                        if (rowmx) rowmx[i] = (uint16_t)rmax;
+                        rows = i + 1;
+                        if (gmax >= thr) dead = true;
+                    } else {
+                        bnd[i] = make_uint2(out_he, out_key);
+                    }
+                }
+            }
+        }
+        if (!lastpass) w_sync();            // the next pass's lane 0 reads what this pass's last lane wrote
+        if (lastpass) {
+            gmax = (int)w_from((uint32_t)gmax, last);
+            te = (int)w_from((uint32_t)te, last);
+            qcol = (int)w_from((uint32_t)qcol, last);
+            rows = (int)w_from((uint32_t)rows, last);
+            dead = w_from(dead ? 1u : 0u, last) != 0u;
+        }
+    }
+    Best B;
+    B.gmax = gmax; B.te = te; B.rows = rows; B.dead = dead;
+    B.qe = te < 0 ? 0 : qcol - pad;
+    if (byte) B.qe &= 255;                  // the 8-bit kernel counts columns in a byte (l512, kswv.cpp:505)
+    return B;
+}
+
+template <int C>
+struct DpCall {
+    static __device__ Best run(const KParams &K, const uint8_t *t, int tlen, int rt, const uint8_t *q, int qlen,
+                               bool qrev, bool byte, int thr, uint16_t *rowmx, uint2 *bnd) {
+        return kswv_dp<C>(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+    }
+};
+
+__device__ inline Best kswv_dp_any(const KParams &K, const uint8_t *t, int tlen, int rt, const uint8_t *q, int qlen,
+                                   bool qrev, bool byte, int thr, uint16_t *rowmx, uint2 *bnd) {
+    const int quantum = byte ? 16 : 8;
+    int ncol = (qlen + quantum - 1) / quantum * quantum;
+    if (ncol == 0) ncol = quantum;
+    const int c = ncol >= kPassCols ? 8 : (ncol + 31) / 32;
+    switch (c) {
+        case 1: return DpCall<1>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+        case 2: return DpCall<2>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+        case 3: return DpCall<3>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+        case 4: return DpCall<4>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+        case 5: return DpCall<5>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+        case 6: return DpCall<6>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+        case 7: return DpCall<7>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+        default: return DpCall<8>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+    }
+}
+
+// Second best (kswv.cpp:589-703, :1139-1212) from the stored row maxima. Row i's maximum is kept when row i+1
+// did not rise above it and row i-1 was not kept (Block I's mask, kswv.cpp:510-523), it reached minsc, and the
+// lane was still live when the reference stored it. kept(i) = nr(i+1) & !kept(i-1) is a one-bit recurrence:
+// 32 rows per step, the bits of one ballot word resolved in a short serial loop that every lane runs.
+__device__ inline void kswv_second(const KParams &K, const uint16_t *rowmx, int tlen, const Best &B, bool byte,
+                                   bool has_minsc, int minsc, int32_t *score2, int32_t *te2) {
+    const int k = w_lane();
+    const int R = B.dead ? B.rows - 1 : tlen;           // rows whose stored maximum can be kept
+    const int val = (B.gmax + K.qmax - 1) / K.qmax;
+    const int low = (int16_t)(B.te - val), high = (int16_t)(B.te + val);
+    const uint32_t off = byte ? 0u : 1u;
+    uint32_t best = 0;
+    if (has_minsc) {
+        uint32_t carry = 0;
+        for (int base = 0; base < R; base += 32) {
+            const int i = base + k;
+            const int cur = i < R ? (int)rowmx[i] : 0;
+            const int nxt = (i + 1 < B.rows && i < R) ? (int)rowmx[i + 1] : 0;   // past the last row: not rising
+            const uint32_t N = w_ballot(i < R && !(nxt > cur));
+            uint32_t X = 0, prev = carry;
+            for (int b = 0; b < 32; ++b) {
+                const uint32_t bit = (N >> b) & 1u & (prev ^ 1u);
+                X |= bit << b;
+                prev = bit;
+            }
+            carry = prev;
+            const bool kept = ((X >> k) & 1u) != 0u && cur >= minsc && (i < low || i > high);
+            const uint32_t w = (uint32_t)cur + off;
+            if (kept && w > 0u) {
+                const uint32_t key = (w << 16) | (uint32_t)(0xFFFF - i);
+                best = key > best ? key : best;
+            }
+        }
+    }
+    best = w_max(best);
+    if (best == 0u) { *score2 = -1; *te2 = -1; }
+    else { *score2 = (int)(best >> 16) - (int)off; *te2 = 0xFFFF - (int)(best & 0xFFFFu); }
+}
+
+// One pair on one warp: phase 0, second best, phase 1. Every lane returns the same Result.
+__device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_t *ref, const uint8_t *qer,
+                                   uint16_t *rowmx, uint2 *bnd) {
+    const int xtra = T.xtra;
+    const bool byte = (xtra & kXByte) != 0;
+    const int lim = byte ? 255 : 32767;
+    int v = (xtra & kXSubo) ? (xtra & 0xffff) : 0x10000;                 // kswv.cpp:422-437, :976-993
+    const bool has_minsc = v <= lim;
+    const int minsc = v;
+    v = (xtra & kXStop) ? (xtra & 0xffff) : 0x10000;
+    int thr = v <= lim ? v : kNoStop;
+    const int sat = byte ? 255 - K.shift : kNoStop;                      // adds_epu8(gmax, shift) == 255, kswv.cpp:539-540
+    if (sat < thr) thr = sat;
+    const uint8_t *t = ref + T.roff, *q = qer + T.qoff;
+
+    Result r;
+    Best B = kswv_dp_any(K, t, T.tlen, 0, q, T.qlen, false, byte, thr, rowmx, bnd);
+    w_sync();                                                            // rowmx: one lane wrote, all lanes read
+    r.score = byte ? (B.gmax + K.shift < 255 ? B.gmax : 255) : B.gmax;   // kswv.cpp:568
+    r.te = B.te; r.qe = B.qe;
+    r.tb = r.qb = -1;
+    if (byte && r.score == 255) { r.score2 = -1; r.te2 = -1; }
+    else kswv_second(K, rowmx, T.tlen, B, byte, has_minsc, minsc, &r.score2, &r.te2);
+
+    if ((xtra & kXStart) && !((xtra & kXSubo) && r.score < (xtra & 0xffff))) {   // bwamem_pair.cpp:667, :685
+        int thr1 = r.score;                                             // h0 = KSW_XSTOP | score
+        if (sat < thr1) thr1 = sat;
+        const Best V = kswv_dp_any(K, t, T.tlen, r.te + 1, q, r.qe + 1, true, byte, thr1, nullptr, bnd);
+        if (r.score == V.gmax) { r.tb = r.te - V.te; r.qb = r.qe - V.qe; }
+    }
+    return r;
+}
+
+#ifndef BSW_HOST_EMUL
+constexpr int kKswvWarps = 4;       // warps per block
+
+// Persistent warps: each takes the next task (the host orders them by decreasing rows x columns) until none is left.
+__global__ void __launch_bounds__(kKswvWarps * 32)
+kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint8_t *__restrict__ ref,
+            const uint8_t *__restrict__ qer, Result *__restrict__ out, uint16_t *rowmx_all, uint2 *bnd_all,
+            int scratch_rows, int *counter) {
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    uint16_t *rowmx = rowmx_all + (size_t)warp * scratch_rows;
+    uint2 *bnd = bnd_all ? bnd_all + (size_t)warp * scratch_rows : nullptr;
+    for (;;) {
+        int id = 0;
+        if (w_lane() == 0) id = atomicAdd(counter, 1);
+        id = (int)w_from((uint32_t)id, 0);
+        if (id >= ntasks) break;
+        const Task T = tasks[id];
+        const Result r = kswv_pair(K, T, ref, qer, rowmx, bnd);
+        if (w_lane() == 0) out[T.out] = r;
+        w_sync();
+    }
+}
+#endif
+
+}  // namespace kswvk

@@ -69,3 +69,29 @@ def test_a_priori_classes_follow_bwa_mem2():
         p[k]["len1"], p[k]["len2"], p[k]["h0"] = l1, l2, h0
     counts, cls = bsw.classify(p, 1)
     assert cls.tolist() == [c[3] for c in cases] and counts == [1, 4, 1]
+
+
+def test_kswv_header_symbols_are_exported():
+    from genarchbench_b200 import kswv
+    text = open(os.path.join(ROOT, "include", "kswv_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(kswv_gpu_\w+)\s*\(", text)))
+    assert set(names) == set(kswv.EXPORTS), (names, kswv.EXPORTS)
+    L = kswv.lib()
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/kswv_gpu.h but not exported"
+    h = C.c_void_p()
+    assert L.kswv_gpu_init(None, 1, C.byref(h)) == 1                                   # BSW_ERR_ARG
+    bad = kswv.Params(6, 0, 6, 1, 1, 4)
+    assert L.kswv_gpu_init(C.byref(bad), 1, C.byref(h)) == 1
+    assert L.kswv_gpu_batch(None, None, None, None, 0, None) == 1
+
+
+def test_kswv_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from genarchbench_b200 import kswv
+    with pytest.raises(bsw.BswError) as e:
+        kswv.Kswv()
+    assert e.value.code == 2                                                            # BSW_ERR_NO_DEVICE

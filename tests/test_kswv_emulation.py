@@ -1,0 +1,69 @@
+"""The kswv device code (genarchbench_b200/csrc/kswv_kernels.cuh: strips of columns per lane, the row pipeline
+through shuffles, the second-best pass, the reverse phase) compiled for the CPU -- DPX / PRMT through
+tests/host_emul/dpx_host_emul.h, the warp as 32 fibers (warp_fibers.h) -- against the golden vectors and the oracle.
+Catches algorithmic errors where no GPU exists; the real kernel is checked by tests/test_kswv_gpu.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import KSWV_GOLDEN_NAMES, ROOT, assert_same_aln, load_kswv_golden
+from oracle import kswv
+from oracle.kswv import KSW_XBYTE, KSW_XSTART, KSW_XSTOP, KSW_XSUBO
+
+
+@pytest.fixture(scope="module")
+def emul():
+    d = os.path.join(ROOT, "tests", "host_emul")
+    so = os.path.join(d, "libkswv_emul.so")
+    srcs = [os.path.join(d, "kswv_emul_lib.cpp"), os.path.join(d, "warp_fibers.h"),
+            os.path.join(ROOT, "genarchbench_b200", "csrc", "kswv_kernels.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-Wall", "-Wno-unknown-pragmas",
+                        "-I", d, "-I", os.path.join(ROOT, "genarchbench_b200", "csrc"),
+                        "-I", os.path.join(ROOT, "include"), "-o", so, srcs[0]], check=True)
+    L = C.CDLL(so)
+    L.kswv_emul_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
+
+    def run(pairs, ref, qer, params=None):
+        aln = np.full((len(pairs), 7), -7, np.int32)
+        rc = L.kswv_emul_batch(kswv._params(params), pairs.ctypes.data, np.ascontiguousarray(ref).ctypes.data,
+                               np.ascontiguousarray(qer).ctypes.data, len(pairs), aln.ctypes.data)
+        assert rc == 0, f"lanes of a warp disagree ({rc})"
+        return aln
+    return run
+
+
+@pytest.mark.parametrize("name", KSWV_GOLDEN_NAMES)
+def test_device_code_matches_golden(emul, name):
+    pairs, ref, qer, params, want = load_kswv_golden(name)
+    assert_same_aln(emul(pairs, ref, qer, params), want, pairs, f"emulated kernel vs golden[{name}]")
+
+
+CASES = [
+    ("every strip width", None, dict(n=800, read_len=(1, 300), window=(0.3, 4.0), min_seed_len=5)),
+    ("several passes (above 256 columns), 16-bit", None, dict(n=60, read_len=(257, 700))),
+    ("several passes, 8-bit class", None, dict(n=60, read_len=(257, 600), p_sub=0.3,
+                                              xtra=lambda l: KSW_XSUBO | KSW_XSTART | KSW_XBYTE | 19)),
+    ("stop + start", None, dict(n=200, xtra=lambda l: KSW_XSTOP | KSW_XSTART | (KSW_XBYTE if l < 120 else 0) | 45)),
+    ("asymmetric gaps, a=2", dict(match=2, mismatch=5, o_del=4, e_del=2, o_ins=7, e_ins=1),
+     dict(n=200, match=2, read_len=(60, 180), p_indel=0.03)),
+]
+
+
+@pytest.mark.parametrize("what,params,kw", CASES, ids=[c[0] for c in CASES])
+def test_device_code_matches_oracle(emul, what, params, kw):
+    pairs, ref, qer = kswv.make_workload(seed=21, **kw)
+    want, _ = kswv.oracle_batch(pairs, ref, qer, params)
+    assert_same_aln(emul(pairs, ref, qer, params), want, pairs, what)
+
+
+def test_empty_sequences(emul):
+    pairs, ref, qer = kswv.make_workload(40, seed=3, read_len=(5, 40), min_seed_len=3)
+    pairs["len1"][::4] = 0
+    pairs["len2"][1::4] = 0
+    want, _ = kswv.oracle_batch(pairs, ref, qer)
+    assert_same_aln(emul(pairs, ref, qer), want, pairs, "empty reference / query")

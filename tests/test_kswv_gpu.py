@@ -1,0 +1,115 @@
+"""kswv on the B200 through the C ABI (kswv_gpu_batch) against the golden vectors (compiled reference) and the
+oracle (pinned to it): bit-exact on all seven kswr_t fields."""
+import numpy as np
+import pytest
+
+from conftest import KSWV_GOLDEN_NAMES, assert_same_aln, load_kswv_golden
+from oracle import kswv as okswv
+from oracle.kswv import KSW_XBYTE, KSW_XSTART, KSW_XSTOP, KSW_XSUBO
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from genarchbench_b200 import kswv
+    g = kswv.Kswv()
+    yield g
+    g.close()
+
+
+def handle_for(params):
+    from genarchbench_b200 import kswv
+    p = dict(okswv.DEFAULT_PARAMS)
+    p.update(params or {})
+    return kswv.Kswv(p["o_del"], p["e_del"], p["o_ins"], p["e_ins"], p["match"], p["mismatch"])
+
+
+@pytest.mark.parametrize("name", KSWV_GOLDEN_NAMES)
+def test_matches_golden(name):
+    pairs, ref, qer, params, want = load_kswv_golden(name)
+    g = handle_for(params)
+    try:
+        assert_same_aln(g.align(pairs, ref, qer), want, pairs, f"GPU vs golden[{name}]")
+    finally:
+        g.close()
+
+
+CASES = [
+    ("mate rescue, 151 bp reads", dict(n=6000, read_len=(100, 151))),
+    ("both classes mixed", dict(n=3000, read_len=(200, 300))),
+    ("every strip width", dict(n=6000, read_len=(1, 300), window=(0.3, 4.0), min_seed_len=5)),
+    ("several passes (above 256 columns)", dict(n=400, read_len=(257, 900))),
+    ("several passes, 8-bit class", dict(n=400, read_len=(257, 600), p_sub=0.3,
+                                         xtra=lambda l: KSW_XSUBO | KSW_XSTART | KSW_XBYTE | 19)),
+    ("saturating 8-bit", dict(n=2000, read_len=(240, 330), p_sub=0.005,
+                              xtra=lambda l: KSW_XSUBO | KSW_XSTART | KSW_XBYTE | 19)),
+    ("stop + start", dict(n=2000, xtra=lambda l: KSW_XSTOP | KSW_XSTART | (KSW_XBYTE if l < 120 else 0) | 45)),
+    ("no flags", dict(n=1000, xtra=0)),
+    ("ambiguous bases", dict(n=2000, p_n=0.2)),
+    ("long windows", dict(n=300, read_len=(100, 151), window=(20.0, 60.0))),
+]
+
+
+@pytest.mark.parametrize("what,kw", CASES, ids=[c[0] for c in CASES])
+def test_matches_oracle(dev, what, kw):
+    pairs, ref, qer = okswv.make_workload(seed=31, **kw)
+    want, cells = okswv.oracle_batch(pairs, ref, qer)
+    got = dev.align(pairs, ref, qer)
+    assert_same_aln(got, want, pairs, what)
+    st = dev.stats()
+    assert st["cells"] == cells and st["pairs"] == len(pairs) and st["kernel_launches"] >= 1
+
+
+def test_nondefault_scoring():
+    params = dict(match=2, mismatch=5, o_del=4, e_del=2, o_ins=7, e_ins=1)
+    pairs, ref, qer = okswv.make_workload(3000, seed=32, match=2, read_len=(60, 180), p_indel=0.03)
+    want, _ = okswv.oracle_batch(pairs, ref, qer, params)
+    g = handle_for(params)
+    try:
+        assert_same_aln(g.align(pairs, ref, qer), want, pairs, "a=2, asymmetric gaps")
+    finally:
+        g.close()
+
+
+def test_many_chunks_shuffled_order_and_regid(dev):
+    """More pairs than one chunk, in shuffled order (so the sequences are gathered, not sent as a range), with
+    regid a permutation: every result lands in aln[regid]."""
+    pairs, ref, qer = okswv.make_workload(80000, seed=33, read_len=(20, 60), window=(1.0, 3.0), min_seed_len=5)
+    rng = np.random.default_rng(1)
+    want, _ = okswv.oracle_batch(pairs, ref, qer)
+    perm = rng.permutation(len(pairs))
+    shuffled = pairs[perm].copy()
+    got = dev.align(shuffled, ref, qer)
+    assert_same_aln(got, want, pairs, "shuffled order")
+    st = dev.stats()
+    assert st["chunks"] >= 3 and st["gathered"] == st["chunks"]
+    got = dev.align(pairs, ref, qer)            # dense, in order: sent as ranges
+    assert_same_aln(got, want, pairs, "dense order")
+    assert dev.stats()["gathered"] == 0
+
+
+def test_empty_sequences_and_empty_batch(dev):
+    pairs, ref, qer = okswv.make_workload(400, seed=34, read_len=(5, 40), min_seed_len=3)
+    pairs["len1"][::4] = 0
+    pairs["len2"][1::4] = 0
+    want, _ = okswv.oracle_batch(pairs, ref, qer)
+    assert_same_aln(dev.align(pairs, ref, qer), want, pairs, "empty reference / query")
+    assert dev.align(pairs[:0].copy(), ref, qer).shape == (0, 7)
+
+
+def test_domain_errors(dev):
+    from genarchbench_b200 import bsw
+    pairs, ref, qer = okswv.make_workload(10, seed=35)
+    bad = pairs.copy()
+    bad["len1"][3] = 40000
+    with pytest.raises(bsw.BswError) as e:
+        dev.align(bad, ref, qer)
+    assert e.value.code == 5                                                   # BSW_ERR_RANGE
+    bad = pairs.copy()
+    bad["regid"][2] = 10
+    with pytest.raises(bsw.BswError) as e:
+        dev.align(bad, ref, qer)
+    assert e.value.code == 1                                                   # BSW_ERR_ARG
+    want, _ = okswv.oracle_batch(pairs, ref, qer)
+    assert_same_aln(dev.align(pairs, ref, qer), want, pairs, "after rejected calls")
