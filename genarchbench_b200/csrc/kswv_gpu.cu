@@ -41,7 +41,7 @@ struct KDev {
     int id = 0, sms = 0, warps = 0;
     cudaStream_t st = nullptr;
     KSlot slot[kRing];
-    uint16_t *d_rowmx = nullptr;
+    uint32_t *d_rowmx = nullptr;
     uint2 *d_bnd = nullptr;
     size_t cap_rows = 0, cap_bnd = 0;
     int next = 0;

@@ -28,6 +28,7 @@
 static inline int __viaddmin_s32(int a, int b, int c) { return std::min((int)((uint32_t)a + (uint32_t)b), c); }
 static inline int __viaddmax_s32_relu(int a, int b, int c) { return std::max(std::max((int)((uint32_t)a + (uint32_t)b), c), 0); }
 static inline int __vimax3_s32_relu(int a, int b, int c) { return std::max(std::max(std::max(a, b), c), 0); }
+static inline int __vimax3_s32(int a, int b, int c) { return std::max(std::max(a, b), c); }
 #else
 #include <cuda_runtime.h>
 #endif
@@ -99,12 +100,14 @@ struct Best { int32_t gmax, te, qe, rows; bool dead; };
 //  rt    : the first rt reference bases are read in reverse order (phase 1), 0 in phase 0
 //  qrev  : the query is read in reverse order (phase 1)
 //  thr   : gmax >= thr ends the lane (kNoStop: never)
-//  rowmx : if non-null, row i's maximum is stored at rowmx[i] for rows 0 .. rows-1
+//  rowkey: row i's key (row maximum << 16 | 0xFFFF - its first column, fillers included) for rows 0 .. rows-1
 //  bnd   : boundary column between passes (queries above 256 columns), tlen entries
+// gmax / te / qe are taken from the stored keys afterwards (kswv_best): the lane that sees a finished row only
+// stores its key and tests the stop threshold, because whatever it does costs the whole warp an issue slot.
 template <int C>
 __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict__ t, int tlen, int rt,
                         const uint8_t *__restrict__ q, int qlen, bool qrev, bool byte, int thr,
-                        uint16_t *rowmx, uint2 *bnd) {
+                        uint32_t *rowkey, uint2 *bnd) {
     const int k = w_lane();
     const int quantum = byte ? 16 : 8;
     int ncol = (qlen + quantum - 1) / quantum * quantum;
@@ -115,7 +118,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
     const int noe_ins = -K.oe_ins, noe_del = -K.oe_del, e_ins = K.e_ins, e_del = K.e_del;
     const uint32_t lut_mis = K.lut_mis, lut_ab = K.lut_ab, lut_amb = K.lut_amb, lut_hi = K.lut_hi;
 
-    int gmax = 0, te = -1, qcol = 0, rows = 0;
+    int rows = 0;
     bool dead = false;
     int pad = 0;
     for (int p = 0; p < npass; ++p) {
@@ -140,7 +143,15 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
             sel[c] = code * 0x1111u + 0x8880u;
             H[c] = 0; F[c] = 0;
         }
-        const int kc0 = 0xFFFF - (c_lo + k * C);
+        int kc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            kc[c] = 0xFFFF - (c_lo + k * C + c);
+#ifndef BSW_HOST_EMUL
+            asm volatile("" : "+r"(kc[c]));     // keep one register per column: base + immediate would bring VIADDMNMX back
+#endif
+        }
+        const int my_rows = k < nl ? tlen : 0;
         int hdiag = 0;
         uint32_t out_he = 0, out_key = 0;
         const int steps = tlen + nl - 1;
@@ -148,7 +159,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
             if (lastpass && w_any(dead)) break;
             uint32_t in_he = w_up1(out_he), in_key = w_up1(out_key);
             const int i = s - k;
-            const bool active = k < nl && i >= 0 && i < tlen;
+            const bool active = (unsigned)i < (unsigned)my_rows;
             if (k == 0) {
                 in_he = 0; in_key = 0;
                 if (p > 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
@@ -160,6 +171,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
                 int e = (int)(in_he >> 16);
                 int key = (int)in_key;
                 int diag = hdiag;
+                int kprev = 0;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const int sc = (int)prmt_sx(lut_lo, lut_hi, sel[c]);
@@ -167,7 +179,10 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
                     diag = H[c];
                     const int f = F[c];
                     const int h = __vimax3_s32_relu(x, e, f);
-                    key = __viaddmax_s32((h << 16) + kc0, -c, key);
+                    const int kcur = (h << 16) + kc[c];             // IMAD: the FMA pipe has room, the ALU pipe does not
+                    if (c & 1) key = __vimax3_s32(key, kprev, kcur);  // one VIMNMX3 per two columns
+                    else if (c == C - 1) key = max(key, kcur);
+                    kprev = kcur;
                     e = __viaddmax_s32_relu(h, noe_ins, e - e_ins);
                     F[c] = __viaddmax_s32_relu(h, noe_del, f - e_del);
                     H[c] = h;
@@ -177,11 +192,9 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
                 out_key = (uint32_t)key;
                 if (k == last) {
                     if (lastpass) {
-                        const int rmax = key >> 16;
-                        if (rmax > gmax) { gmax = rmax; te = i; qcol = 0xFFFF - (key & 0xFFFF); }
-                        if (rowmx) rowmx[i] = (uint16_t)rmax;
+                        rowkey[i] = (uint32_t)key;
                         rows = i + 1;
-                        if (gmax >= thr) dead = true;
+                        dead = (key >> 16) >= thr;      // gmax >= thr first holds on the first row that reaches thr
                     } else {
                         bnd[i] = make_uint2(out_he, out_key);
                     }
@@ -190,43 +203,56 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
         }
         if (!lastpass) w_sync();            // the next pass's lane 0 reads what this pass's last lane wrote
         if (lastpass) {
-            gmax = (int)w_from((uint32_t)gmax, last);
-            te = (int)w_from((uint32_t)te, last);
-            qcol = (int)w_from((uint32_t)qcol, last);
             rows = (int)w_from((uint32_t)rows, last);
             dead = w_from(dead ? 1u : 0u, last) != 0u;
         }
     }
+    w_sync();                               // rowkey: one lane wrote, all lanes read
+    // Block II (kswv.cpp:526-548): gmax is the largest row maximum up to the stop row, te its FIRST row, qe that
+    // row's first column
+    uint32_t best = 0;
+    for (int base = 0; base < rows; base += 32) {
+        const int i = base + k;
+        if (i < rows) {
+            const uint32_t cand = (rowkey[i] & 0xFFFF0000u) | (uint32_t)(0xFFFF - i);
+            best = cand > best ? cand : best;
+        }
+    }
+    best = w_max(best);
     Best B;
-    B.gmax = gmax; B.te = te; B.rows = rows; B.dead = dead;
-    B.qe = te < 0 ? 0 : qcol - pad;
-    if (byte) B.qe &= 255;                  // the 8-bit kernel counts columns in a byte (l512, kswv.cpp:505)
+    B.gmax = (int)(best >> 16); B.rows = rows; B.dead = dead;
+    B.te = -1; B.qe = 0;
+    if (B.gmax > 0) {
+        B.te = 0xFFFF - (int)(best & 0xFFFFu);
+        B.qe = 0xFFFF - (int)(rowkey[B.te] & 0xFFFFu) - pad;
+        if (byte) B.qe &= 255;              // the 8-bit kernel counts columns in a byte (l512, kswv.cpp:505)
+    }
     return B;
 }
 
 template <int C>
 struct DpCall {
     static __device__ Best run(const KParams &K, const uint8_t *t, int tlen, int rt, const uint8_t *q, int qlen,
-                               bool qrev, bool byte, int thr, uint16_t *rowmx, uint2 *bnd) {
-        return kswv_dp<C>(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+                               bool qrev, bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
+        return kswv_dp<C>(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
     }
 };
 
 __device__ inline Best kswv_dp_any(const KParams &K, const uint8_t *t, int tlen, int rt, const uint8_t *q, int qlen,
-                                   bool qrev, bool byte, int thr, uint16_t *rowmx, uint2 *bnd) {
+                                   bool qrev, bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
     const int quantum = byte ? 16 : 8;
     int ncol = (qlen + quantum - 1) / quantum * quantum;
     if (ncol == 0) ncol = quantum;
     const int c = ncol >= kPassCols ? 8 : (ncol + 31) / 32;
     switch (c) {
-        case 1: return DpCall<1>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
-        case 2: return DpCall<2>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
-        case 3: return DpCall<3>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
-        case 4: return DpCall<4>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
-        case 5: return DpCall<5>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
-        case 6: return DpCall<6>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
-        case 7: return DpCall<7>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
-        default: return DpCall<8>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowmx, bnd);
+        case 1: return DpCall<1>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+        case 2: return DpCall<2>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+        case 3: return DpCall<3>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+        case 4: return DpCall<4>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+        case 5: return DpCall<5>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+        case 6: return DpCall<6>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+        case 7: return DpCall<7>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+        default: return DpCall<8>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
     }
 }
 
@@ -234,7 +260,7 @@ __device__ inline Best kswv_dp_any(const KParams &K, const uint8_t *t, int tlen,
 // did not rise above it and row i-1 was not kept (Block I's mask, kswv.cpp:510-523), it reached minsc, and the
 // lane was still live when the reference stored it. kept(i) = nr(i+1) & !kept(i-1) is a one-bit recurrence:
 // 32 rows per step, the bits of one ballot word resolved in a short serial loop that every lane runs.
-__device__ inline void kswv_second(const KParams &K, const uint16_t *rowmx, int tlen, const Best &B, bool byte,
+__device__ inline void kswv_second(const KParams &K, const uint32_t *rowkey, int tlen, const Best &B, bool byte,
                                    bool has_minsc, int minsc, int32_t *score2, int32_t *te2) {
     const int k = w_lane();
     const int R = B.dead ? B.rows - 1 : tlen;           // rows whose stored maximum can be kept
@@ -246,8 +272,8 @@ __device__ inline void kswv_second(const KParams &K, const uint16_t *rowmx, int 
         uint32_t carry = 0;
         for (int base = 0; base < R; base += 32) {
             const int i = base + k;
-            const int cur = i < R ? (int)rowmx[i] : 0;
-            const int nxt = (i + 1 < B.rows && i < R) ? (int)rowmx[i + 1] : 0;   // past the last row: not rising
+            const int cur = i < R ? (int)(rowkey[i] >> 16) : 0;
+            const int nxt = (i + 1 < B.rows && i < R) ? (int)(rowkey[i + 1] >> 16) : 0;   // past the last row: not rising
             const uint32_t N = w_ballot(i < R && !(nxt > cur));
             uint32_t X = 0, prev = carry;
             for (int b = 0; b < 32; ++b) {
@@ -271,7 +297,7 @@ __device__ inline void kswv_second(const KParams &K, const uint16_t *rowmx, int 
 
 // One pair on one warp: phase 0, second best, phase 1. Every lane returns the same Result.
 __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_t *ref, const uint8_t *qer,
-                                   uint16_t *rowmx, uint2 *bnd) {
+                                   uint32_t *rowkey, uint2 *bnd) {
     const int xtra = T.xtra;
     const bool byte = (xtra & kXByte) != 0;
     const int lim = byte ? 255 : 32767;
@@ -285,18 +311,18 @@ __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_
     const uint8_t *t = ref + T.roff, *q = qer + T.qoff;
 
     Result r;
-    Best B = kswv_dp_any(K, t, T.tlen, 0, q, T.qlen, false, byte, thr, rowmx, bnd);
-    w_sync();                                                            // rowmx: one lane wrote, all lanes read
+    Best B = kswv_dp_any(K, t, T.tlen, 0, q, T.qlen, false, byte, thr, rowkey, bnd);
     r.score = byte ? (B.gmax + K.shift < 255 ? B.gmax : 255) : B.gmax;   // kswv.cpp:568
     r.te = B.te; r.qe = B.qe;
     r.tb = r.qb = -1;
     if (byte && r.score == 255) { r.score2 = -1; r.te2 = -1; }
-    else kswv_second(K, rowmx, T.tlen, B, byte, has_minsc, minsc, &r.score2, &r.te2);
+    else kswv_second(K, rowkey, T.tlen, B, byte, has_minsc, minsc, &r.score2, &r.te2);
 
     if ((xtra & kXStart) && !((xtra & kXSubo) && r.score < (xtra & 0xffff))) {   // bwamem_pair.cpp:667, :685
         int thr1 = r.score;                                             // h0 = KSW_XSTOP | score
         if (sat < thr1) thr1 = sat;
-        const Best V = kswv_dp_any(K, t, T.tlen, r.te + 1, q, r.qe + 1, true, byte, thr1, nullptr, bnd);
+        w_sync();                                                        // phase 0's keys are no longer needed
+        const Best V = kswv_dp_any(K, t, T.tlen, r.te + 1, q, r.qe + 1, true, byte, thr1, rowkey, bnd);
         if (r.score == V.gmax) { r.tb = r.te - V.te; r.qb = r.qe - V.qe; }
     }
     return r;
@@ -308,10 +334,10 @@ constexpr int kKswvWarps = 4;       // warps per block
 // Persistent warps: each takes the next task (the host orders them by decreasing rows x columns) until none is left.
 __global__ void __launch_bounds__(kKswvWarps * 32)
 kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint8_t *__restrict__ ref,
-            const uint8_t *__restrict__ qer, Result *__restrict__ out, uint16_t *rowmx_all, uint2 *bnd_all,
+            const uint8_t *__restrict__ qer, Result *__restrict__ out, uint32_t *rowkey_all, uint2 *bnd_all,
             int scratch_rows, int *counter) {
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    uint16_t *rowmx = rowmx_all + (size_t)warp * scratch_rows;
+    uint32_t *rowkey = rowkey_all + (size_t)warp * scratch_rows;
     uint2 *bnd = bnd_all ? bnd_all + (size_t)warp * scratch_rows : nullptr;
     for (;;) {
         int id = 0;
@@ -319,7 +345,7 @@ kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const u
         id = (int)w_from((uint32_t)id, 0);
         if (id >= ntasks) break;
         const Task T = tasks[id];
-        const Result r = kswv_pair(K, T, ref, qer, rowmx, bnd);
+        const Result r = kswv_pair(K, T, ref, qer, rowkey, bnd);
         if (w_lane() == 0) out[T.out] = r;
         w_sync();
     }

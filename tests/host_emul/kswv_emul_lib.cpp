@@ -18,14 +18,14 @@ extern "C" int kswv_emul_batch(const int32_t *params, const bsw_seqpair *pairs, 
 #pragma omp parallel
     {
         wf::Warp warp;
-        std::vector<uint16_t> rowmx;
+        std::vector<uint32_t> rowmx;
         std::vector<uint2> bnd;
 #pragma omp for schedule(dynamic, 8)
         for (int64_t i = 0; i < n; ++i) {
             const bsw_seqpair &sp = pairs[i];
             Task T{(uint32_t)sp.idr, (uint32_t)sp.idq, sp.len1, sp.len2, sp.h0, (int32_t)i};
             // exactly what the kernel gets per warp, poisoned so that a read of a row nobody stored shows up
-            rowmx.assign((size_t)sp.len1 + 1, (uint16_t)0xDEAD);
+            rowmx.assign((size_t)sp.len1 + 1, 0xDEADBEEFu);
             bnd.assign((size_t)sp.len1 + 1, uint2{0xDEADBEEFu, 0xDEADBEEFu});
             Result res[32];
             wf::run_warp(warp, [&]() {
