@@ -43,7 +43,8 @@ struct KDev {
     KSlot slot[kRing];
     uint32_t *d_rowmx = nullptr;
     uint2 *d_bnd = nullptr;
-    size_t cap_rows = 0, cap_bnd = 0;
+    uint8_t *d_seq = nullptr;                   // per warp: the reversed copies phase 1 reads
+    size_t cap_rows = 0, cap_bnd = 0, cap_seq = 0;
     int next = 0;
 };
 
@@ -153,6 +154,7 @@ void free_dev(KDev &d) {
     }
     if (d.d_rowmx) cudaFree(d.d_rowmx);
     if (d.d_bnd) cudaFree(d.d_bnd);
+    if (d.d_seq) cudaFree(d.d_seq);
     if (d.st) cudaStreamDestroy(d.st);
 }
 
@@ -259,8 +261,8 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
     // ---- validation and totals (one host pass over the 72-byte records)
     int64_t bad = -1, n8 = 0, cells = 0;
     int bad_kind = 0;
-    int maxT = 0, maxCols = 0;
-#pragma omp parallel for schedule(static) reduction(+ : n8) reduction(+ : cells) reduction(max : maxT) reduction(max : maxCols)
+    int maxT = 0, maxCols = 0, maxQ = 0;
+#pragma omp parallel for schedule(static) reduction(+ : n8) reduction(+ : cells) reduction(max : maxT) reduction(max : maxCols) reduction(max : maxQ)
     for (int64_t i = 0; i < n; ++i) {
         const bsw_seqpair &sp = pairs[i];
         const bool byte = (sp.h0 & kXByte) != 0;
@@ -278,6 +280,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         cells += (int64_t)sp.len1 * nc;
         maxT = std::max(maxT, sp.len1);
         maxCols = std::max(maxCols, nc);
+        maxQ = std::max(maxQ, sp.len2);
     }
     if (bad >= 0) {
         set_err(h, bad_kind == 2 ? "pair %lld: regid %d outside [0, n_pairs)" : "pair %lld outside the kswv domain (len1=%d len2=%d)",
@@ -298,8 +301,10 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             rc = grow_dev(h, d.d_bnd, d.cap_bnd, rows * (size_t)d.warps);
             if (rc) return rc;
         }
+        rc = grow_dev(h, d.d_seq, d.cap_seq, (size_t)(maxT + maxQ + 64) * (size_t)d.warps);
+        if (rc) return rc;
     }
-    const int scratch_rows = maxT + 8;
+    const int scratch_rows = maxT + 8, scratch_seq = maxT + maxQ + 64;
 
     // ---- chunks
     int rc = BSW_OK;
@@ -392,7 +397,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         KCU(cudaEventRecord(s.ev_start, d.st));
         const int blocks = (int)std::min<int64_t>((cnt + kKswvWarps - 1) / kKswvWarps, (int64_t)d.sms * kBlocksPerSm);
         kswv_kernel<<<blocks, kKswvWarps * 32, 0, d.st>>>(h->K, s.d_tasks, (int)cnt, s.d_ref, s.d_qer, s.d_out, d.d_rowmx,
-                                                           maxCols > kPassCols ? d.d_bnd : nullptr, scratch_rows, s.d_counter);
+                                                           maxCols > kPassCols ? d.d_bnd : nullptr, d.d_seq, scratch_rows, scratch_seq, s.d_counter);
         KCU(cudaGetLastError());
         KCU(cudaEventRecord(s.ev_stop, d.st));
         KCU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(Result) * (size_t)cnt, cudaMemcpyDeviceToHost, d.st));

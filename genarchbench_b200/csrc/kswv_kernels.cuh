@@ -43,6 +43,7 @@ struct KParams {
     int32_t a, b, amb;                        // match, mismatch (negative), ambiguous (-1, kswv.cpp:131)
     int32_t oe_del, e_del, oe_ins, e_ins;
     int32_t qmax, shift;                      // g_qmax (kswv.cpp:132-133), the 8-bit bias (kswv.cpp:396-404)
+    int32_t one;                              // 1, opaque to the compiler (see kswv_dp)
     uint32_t lut_mis, lut_ab, lut_amb, lut_hi;
 };
 
@@ -91,31 +92,33 @@ inline KParams make_kparams(int o_del, int e_del, int o_ins, int e_ins, int matc
     K.lut_ab = A ^ B;
     K.lut_amb = N * 0x01010101u;
     K.lut_hi = N | (0u << 8) | (N << 16) | (N << 24);
+    K.one = 1;
     return K;
 }
 
 struct Best { int32_t gmax, te, qe, rows; bool dead; };
 
-// One pass structure: the DP of t[0..tlen) x q[0..qlen) (padded) on one warp.
-//  rt    : the first rt reference bases are read in reverse order (phase 1), 0 in phase 0
-//  qrev  : the query is read in reverse order (phase 1)
+// The DP of t[0..tlen) x q[0..qlen) (padded) on one warp.
 //  thr   : gmax >= thr ends the lane (kNoStop: never)
 //  rowkey: row i's key (row maximum << 16 | 0xFFFF - its first column, fillers included) for rows 0 .. rows-1
-//  bnd   : boundary column between passes (queries above 256 columns), tlen entries
-// gmax / te / qe are taken from the stored keys afterwards (kswv_best): the lane that sees a finished row only
-// stores its key and tests the stop threshold, because whatever it does costs the whole warp an issue slot.
-template <int C>
-__device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict__ t, int tlen, int rt,
-                        const uint8_t *__restrict__ q, int qlen, bool qrev, bool byte, int thr,
-                        uint32_t *rowkey, uint2 *bnd) {
+//  bnd   : boundary column between passes (MP: queries above 256 columns), tlen entries
+// gmax / te / qe are taken from the stored keys after the loop: the lane that sees a finished row only stores its
+// key and tests the stop threshold, because whatever a single lane does costs the whole warp an issue slot.
+// SAT: the diagonal term can reach the 8-bit class's ceiling (255 - shift) and is clamped there by a VIADDMNMX.
+// When min(tlen, qlen) * match stays below the ceiling (every pair bwa-mem2 puts in the 8-bit class: l_ms * a < 250)
+// and in the 16-bit class, the sum is an IMAD by a run-time 1 instead -- the FMA pipe has room, the ALU pipe binds.
+template <int C, bool SAT, bool MP>
+__device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict__ t, int tlen,
+                                     const uint8_t *__restrict__ q, int qlen, bool byte, int thr,
+                                     uint32_t *rowkey, uint2 *bnd) {
     const int k = w_lane();
     const int quantum = byte ? 16 : 8;
     int ncol = (qlen + quantum - 1) / quantum * quantum;
     if (ncol == 0) ncol = quantum;          // an empty query is all padding: every H stays 0
-    const int npass = (ncol + kPassCols - 1) / kPassCols;
+    const int npass = MP ? (ncol + kPassCols - 1) / kPassCols : 1;
     // scalars by value: K sits in the caller's local memory and would be re-read every step
     const int clamp = byte ? 255 - K.shift : 32767;
-    const int noe_ins = -K.oe_ins, noe_del = -K.oe_del, e_ins = K.e_ins, e_del = K.e_del;
+    const int noe_ins = -K.oe_ins, noe_del = -K.oe_del, e_ins = K.e_ins, e_del = K.e_del, one = K.one;
     const uint32_t lut_mis = K.lut_mis, lut_ab = K.lut_ab, lut_amb = K.lut_amb, lut_hi = K.lut_hi;
 
     int rows = 0;
@@ -127,8 +130,8 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
         const int nl = (pcols + C - 1) / C;
         pad = nl * C - pcols;               // only non-zero in a single-pass DP (C divides 256)
         const int last = nl - 1;
-        const bool lastpass = p == npass - 1;
-        int H[C], F[C];
+        const bool lastpass = !MP || p == npass - 1;
+        int H[C], F[C], kc[C];
         uint32_t sel[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -137,35 +140,32 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
             if (gc < 0 || k >= nl) code = 6u;
             else if (gc >= qlen) code = 5u;
             else {
-                const uint32_t b = q[qrev ? qlen - 1 - gc : gc];
+                const uint32_t b = q[gc];
                 code = b > 3u ? 4u : b;
             }
             sel[c] = code * 0x1111u + 0x8880u;
             H[c] = 0; F[c] = 0;
-        }
-        int kc[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
             kc[c] = 0xFFFF - (c_lo + k * C + c);
 #ifndef BSW_HOST_EMUL
             asm volatile("" : "+r"(kc[c]));     // keep one register per column: base + immediate would bring VIADDMNMX back
 #endif
         }
         const int my_rows = k < nl ? tlen : 0;
+        const bool keeper = k == last && lastpass;      // the lane that sees finished rows
+        const bool feeder = MP && k == last && !lastpass;
+        const uint32_t not0 = k == 0 ? 0u : 0xFFFFFFFFu;
         int hdiag = 0;
         uint32_t out_he = 0, out_key = 0;
         const int steps = tlen + nl - 1;
-        for (int s = 0; s < steps; ++s) {
-            if (lastpass && w_any(dead)) break;
-            uint32_t in_he = w_up1(out_he), in_key = w_up1(out_key);
+        int s = 0;
+        for (; s < steps; ++s) {
+            if (w_any(dead)) break;
+            uint32_t in_he = w_up1(out_he) & not0, in_key = w_up1(out_key) & not0;
             const int i = s - k;
             const bool active = (unsigned)i < (unsigned)my_rows;
-            if (k == 0) {
-                in_he = 0; in_key = 0;
-                if (p > 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
-            }
+            if (MP && p > 0 && k == 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
             if (active) {
-                uint32_t r = t[i < rt ? rt - 1 - i : i];
+                const uint32_t r = t[i];
                 const uint32_t lut_lo = r > 3u ? lut_amb : (lut_mis ^ (lut_ab << (8u * r)));
                 const int hl = (int)(in_he & 0xFFFFu);
                 int e = (int)(in_he >> 16);
@@ -175,11 +175,11 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const int sc = (int)prmt_sx(lut_lo, lut_hi, sel[c]);
-                    const int x = __viaddmin_s32(diag, sc, clamp);
+                    const int x = SAT ? __viaddmin_s32(diag, sc, clamp) : diag * one + sc;
                     diag = H[c];
                     const int f = F[c];
                     const int h = __vimax3_s32_relu(x, e, f);
-                    const int kcur = (h << 16) + kc[c];             // IMAD: the FMA pipe has room, the ALU pipe does not
+                    const int kcur = (h << 16) + kc[c];             // IMAD
                     if (c & 1) key = __vimax3_s32(key, kprev, kcur);  // one VIMNMX3 per two columns
                     else if (c == C - 1) key = max(key, kcur);
                     kprev = kcur;
@@ -190,21 +190,18 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
                 hdiag = hl;
                 out_he = (uint32_t)H[C - 1] | ((uint32_t)e << 16);
                 out_key = (uint32_t)key;
-                if (k == last) {
-                    if (lastpass) {
-                        rowkey[i] = (uint32_t)key;
-                        rows = i + 1;
-                        dead = (key >> 16) >= thr;      // gmax >= thr first holds on the first row that reaches thr
-                    } else {
-                        bnd[i] = make_uint2(out_he, out_key);
-                    }
-                }
+                if (keeper) rowkey[i] = (uint32_t)key;
+                dead = keeper && (key >> 16) >= thr;    // gmax >= thr first holds on the first row that reaches thr
+                if (MP && feeder) bnd[i] = make_uint2(out_he, out_key);
             }
         }
-        if (!lastpass) w_sync();            // the next pass's lane 0 reads what this pass's last lane wrote
+        if (MP && !lastpass) w_sync();      // the next pass's lane 0 reads what this pass's last lane wrote
         if (lastpass) {
-            rows = (int)w_from((uint32_t)rows, last);
-            dead = w_from(dead ? 1u : 0u, last) != 0u;
+            // the loop ran `s` steps; the keeper's last finished row is s - 1 - last
+            rows = s - last;
+            if (rows > tlen) rows = tlen;
+            if (rows < 0) rows = 0;
+            dead = w_any(dead);
         }
     }
     w_sync();                               // rowkey: one lane wrote, all lanes read
@@ -232,27 +229,29 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
 
 template <int C>
 struct DpCall {
-    static __device__ Best run(const KParams &K, const uint8_t *t, int tlen, int rt, const uint8_t *q, int qlen,
-                               bool qrev, bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
-        return kswv_dp<C>(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+    static __device__ Best run(const KParams &K, const uint8_t *t, int tlen, const uint8_t *q, int qlen,
+                               bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
+        const int bound = (tlen < qlen ? tlen : qlen) * K.a;          // no H can exceed it
+        if (byte && bound >= 255 - K.shift) return kswv_dp<C, true, false>(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        return kswv_dp<C, false, false>(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
     }
 };
 
-__device__ inline Best kswv_dp_any(const KParams &K, const uint8_t *t, int tlen, int rt, const uint8_t *q, int qlen,
-                                   bool qrev, bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
+__device__ inline Best kswv_dp_any(const KParams &K, const uint8_t *t, int tlen, const uint8_t *q, int qlen,
+                                   bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
     const int quantum = byte ? 16 : 8;
     int ncol = (qlen + quantum - 1) / quantum * quantum;
     if (ncol == 0) ncol = quantum;
-    const int c = ncol >= kPassCols ? 8 : (ncol + 31) / 32;
-    switch (c) {
-        case 1: return DpCall<1>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
-        case 2: return DpCall<2>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
-        case 3: return DpCall<3>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
-        case 4: return DpCall<4>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
-        case 5: return DpCall<5>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
-        case 6: return DpCall<6>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
-        case 7: return DpCall<7>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
-        default: return DpCall<8>::run(K, t, tlen, rt, q, qlen, qrev, byte, thr, rowkey, bnd);
+    if (ncol > kPassCols) return kswv_dp<8, true, true>(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+    switch ((ncol + 31) / 32) {
+        case 1: return DpCall<1>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        case 2: return DpCall<2>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        case 3: return DpCall<3>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        case 4: return DpCall<4>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        case 5: return DpCall<5>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        case 6: return DpCall<6>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        case 7: return DpCall<7>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        default: return DpCall<8>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
     }
 }
 
@@ -297,7 +296,7 @@ __device__ inline void kswv_second(const KParams &K, const uint32_t *rowkey, int
 
 // One pair on one warp: phase 0, second best, phase 1. Every lane returns the same Result.
 __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_t *ref, const uint8_t *qer,
-                                   uint32_t *rowkey, uint2 *bnd) {
+                                   uint32_t *rowkey, uint2 *bnd, uint8_t *seqbuf) {
     const int xtra = T.xtra;
     const bool byte = (xtra & kXByte) != 0;
     const int lim = byte ? 255 : 32767;
@@ -311,7 +310,7 @@ __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_
     const uint8_t *t = ref + T.roff, *q = qer + T.qoff;
 
     Result r;
-    Best B = kswv_dp_any(K, t, T.tlen, 0, q, T.qlen, false, byte, thr, rowkey, bnd);
+    Best B = kswv_dp_any(K, t, T.tlen, q, T.qlen, byte, thr, rowkey, bnd);
     r.score = byte ? (B.gmax + K.shift < 255 ? B.gmax : 255) : B.gmax;   // kswv.cpp:568
     r.te = B.te; r.qe = B.qe;
     r.tb = r.qb = -1;
@@ -321,8 +320,14 @@ __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_
     if ((xtra & kXStart) && !((xtra & kXSubo) && r.score < (xtra & 0xffff))) {   // bwamem_pair.cpp:667, :685
         int thr1 = r.score;                                             // h0 = KSW_XSTOP | score
         if (sat < thr1) thr1 = sat;
-        w_sync();                                                        // phase 0's keys are no longer needed
-        const Best V = kswv_dp_any(K, t, T.tlen, r.te + 1, q, r.qe + 1, true, byte, thr1, rowkey, bnd);
+        // the reversed prefixes (revseq, bwamem_pair.cpp:673, :691) are written out once so that the row loop
+        // reads its sequences the same way in both phases; the rows below te keep their order (len1 is unchanged)
+        const int rt = r.te + 1, q1 = r.qe + 1, k = w_lane();
+        uint8_t *tr = seqbuf, *qr = seqbuf + ((T.tlen + 15) & ~15);
+        for (int i = k; i < T.tlen; i += 32) tr[i] = t[i < rt ? rt - 1 - i : i];
+        for (int j = k; j < q1; j += 32) qr[j] = q[q1 - 1 - j];
+        w_sync();                                                        // also: phase 0's keys are no longer needed
+        const Best V = kswv_dp_any(K, tr, T.tlen, qr, q1, byte, thr1, rowkey, bnd);
         if (r.score == V.gmax) { r.tb = r.te - V.te; r.qb = r.qe - V.qe; }
     }
     return r;
@@ -335,17 +340,18 @@ constexpr int kKswvWarps = 4;       // warps per block
 __global__ void __launch_bounds__(kKswvWarps * 32)
 kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint8_t *__restrict__ ref,
             const uint8_t *__restrict__ qer, Result *__restrict__ out, uint32_t *rowkey_all, uint2 *bnd_all,
-            int scratch_rows, int *counter) {
+            uint8_t *seq_all, int scratch_rows, int scratch_seq, int *counter) {
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     uint32_t *rowkey = rowkey_all + (size_t)warp * scratch_rows;
     uint2 *bnd = bnd_all ? bnd_all + (size_t)warp * scratch_rows : nullptr;
+    uint8_t *seqbuf = seq_all + (size_t)warp * scratch_seq;
     for (;;) {
         int id = 0;
         if (w_lane() == 0) id = atomicAdd(counter, 1);
         id = (int)w_from((uint32_t)id, 0);
         if (id >= ntasks) break;
         const Task T = tasks[id];
-        const Result r = kswv_pair(K, T, ref, qer, rowkey, bnd);
+        const Result r = kswv_pair(K, T, ref, qer, rowkey, bnd, seqbuf);
         if (w_lane() == 0) out[T.out] = r;
         w_sync();
     }
