@@ -43,8 +43,9 @@ struct KDev {
     KSlot slot[kRing];
     uint32_t *d_rowmx = nullptr;
     uint2 *d_bnd = nullptr;
-    uint8_t *d_seq = nullptr;                   // per warp: the reversed copies phase 1 reads
-    size_t cap_rows = 0, cap_bnd = 0, cap_seq = 0;
+    uint32_t *d_lutw = nullptr;                 // per warp: one LUT word per reference row
+    uint8_t *d_qbuf = nullptr;                  // per warp: the reversed query prefix phase 1 reads
+    size_t cap_rows = 0, cap_bnd = 0, cap_lutw = 0, cap_qbuf = 0;
     int next = 0;
 };
 
@@ -154,7 +155,8 @@ void free_dev(KDev &d) {
     }
     if (d.d_rowmx) cudaFree(d.d_rowmx);
     if (d.d_bnd) cudaFree(d.d_bnd);
-    if (d.d_seq) cudaFree(d.d_seq);
+    if (d.d_lutw) cudaFree(d.d_lutw);
+    if (d.d_qbuf) cudaFree(d.d_qbuf);
     if (d.st) cudaStreamDestroy(d.st);
 }
 
@@ -301,10 +303,12 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             rc = grow_dev(h, d.d_bnd, d.cap_bnd, rows * (size_t)d.warps);
             if (rc) return rc;
         }
-        rc = grow_dev(h, d.d_seq, d.cap_seq, (size_t)(maxT + maxQ + 64) * (size_t)d.warps);
+        rc = grow_dev(h, d.d_lutw, d.cap_lutw, rows * (size_t)d.warps);
+        if (rc) return rc;
+        rc = grow_dev(h, d.d_qbuf, d.cap_qbuf, (size_t)(maxQ + 64) * (size_t)d.warps);
         if (rc) return rc;
     }
-    const int scratch_rows = maxT + 8, scratch_seq = maxT + maxQ + 64;
+    const int scratch_rows = maxT + 8, scratch_q = maxQ + 64;
 
     // ---- chunks
     int rc = BSW_OK;
@@ -397,7 +401,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         KCU(cudaEventRecord(s.ev_start, d.st));
         const int blocks = (int)std::min<int64_t>((cnt + kKswvWarps - 1) / kKswvWarps, (int64_t)d.sms * kBlocksPerSm);
         kswv_kernel<<<blocks, kKswvWarps * 32, 0, d.st>>>(h->K, s.d_tasks, (int)cnt, s.d_ref, s.d_qer, s.d_out, d.d_rowmx,
-                                                           maxCols > kPassCols ? d.d_bnd : nullptr, d.d_seq, scratch_rows, scratch_seq, s.d_counter);
+                                                           maxCols > kPassCols ? d.d_bnd : nullptr, d.d_lutw, d.d_qbuf, scratch_rows, scratch_q, s.d_counter);
         KCU(cudaGetLastError());
         KCU(cudaEventRecord(s.ev_stop, d.st));
         KCU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(Result) * (size_t)cnt, cudaMemcpyDeviceToHost, d.st));

@@ -98,7 +98,8 @@ inline KParams make_kparams(int o_del, int e_del, int o_ins, int e_ins, int matc
 
 struct Best { int32_t gmax, te, qe, rows; bool dead; };
 
-// The DP of t[0..tlen) x q[0..qlen) (padded) on one warp.
+// The DP of tlen reference rows x q[0..qlen) (padded) on one warp.
+//  lutw  : per reference row, the four scores of its base against query codes 0..3 (one byte each; row_luts())
 //  thr   : gmax >= thr ends the lane (kNoStop: never)
 //  rowkey: row i's key (row maximum << 16 | 0xFFFF - its first column, fillers included) for rows 0 .. rows-1
 //  bnd   : boundary column between passes (MP: queries above 256 columns), tlen entries
@@ -108,7 +109,7 @@ struct Best { int32_t gmax, te, qe, rows; bool dead; };
 // When min(tlen, qlen) * match stays below the ceiling (every pair bwa-mem2 puts in the 8-bit class: l_ms * a < 250)
 // and in the 16-bit class, the sum is an IMAD by a run-time 1 instead -- the FMA pipe has room, the ALU pipe binds.
 template <int C, bool SAT, bool MP>
-__device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict__ t, int tlen,
+__device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restrict__ lutw, int tlen,
                                      const uint8_t *__restrict__ q, int qlen, bool byte, int thr,
                                      uint32_t *rowkey, uint2 *bnd) {
     const int k = w_lane();
@@ -119,7 +120,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
     // scalars by value: K sits in the caller's local memory and would be re-read every step
     const int clamp = byte ? 255 - K.shift : 32767;
     const int noe_ins = -K.oe_ins, noe_del = -K.oe_del, e_ins = K.e_ins, e_del = K.e_del, one = K.one;
-    const uint32_t lut_mis = K.lut_mis, lut_ab = K.lut_ab, lut_amb = K.lut_amb, lut_hi = K.lut_hi;
+    const uint32_t lut_hi = K.lut_hi;
 
     int rows = 0;
     bool dead = false;
@@ -157,16 +158,20 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
         int hdiag = 0;
         uint32_t out_he = 0, out_key = 0;
         const int steps = tlen + nl - 1;
-        int s = 0;
-        for (; s < steps; ++s) {
+        int s4 = 0;
+        // four steps per stop test: a lane that has reached thr keeps going for at most three rows, which the
+        // scan after the loop drops again
+        for (; s4 < steps; s4 += 4) {
             if (w_any(dead)) break;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+            const int s = s4 + u;
             uint32_t in_he = w_up1(out_he) & not0, in_key = w_up1(out_key) & not0;
             const int i = s - k;
             const bool active = (unsigned)i < (unsigned)my_rows;
             if (MP && p > 0 && k == 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
             if (active) {
-                const uint32_t r = t[i];
-                const uint32_t lut_lo = r > 3u ? lut_amb : (lut_mis ^ (lut_ab << (8u * r)));
+                const uint32_t lut_lo = lutw[i];
                 const int hl = (int)(in_he & 0xFFFFu);
                 int e = (int)(in_he >> 16);
                 int key = (int)in_key;
@@ -191,20 +196,32 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
                 out_he = (uint32_t)H[C - 1] | ((uint32_t)e << 16);
                 out_key = (uint32_t)key;
                 if (keeper) rowkey[i] = (uint32_t)key;
-                dead = keeper && (key >> 16) >= thr;    // gmax >= thr first holds on the first row that reaches thr
+                dead |= keeper && (key >> 16) >= thr;   // gmax >= thr first holds on the first row that reaches thr
                 if (MP && feeder) bnd[i] = make_uint2(out_he, out_key);
+            }
             }
         }
         if (MP && !lastpass) w_sync();      // the next pass's lane 0 reads what this pass's last lane wrote
         if (lastpass) {
-            // the loop ran `s` steps; the keeper's last finished row is s - 1 - last
-            rows = s - last;
+            // the loop ran s4 steps; the keeper's last finished row is s4 - 1 - last
+            rows = s4 - last;
             if (rows > tlen) rows = tlen;
             if (rows < 0) rows = 0;
-            dead = w_any(dead);
         }
     }
     w_sync();                               // rowkey: one lane wrote, all lanes read
+    // the stop row: the first row whose maximum reaches thr (Block II's exit, kswv.cpp:535-548); rows past it
+    // were computed by the lanes that were ahead of the keeper and do not exist for the reference
+    {
+        uint32_t first = 0;
+        for (int base = 0; base < rows; base += 32) {
+            const int i = base + k;
+            if (i < rows && (int)(rowkey[i] >> 16) >= thr) { first = (uint32_t)(0xFFFF - i); break; }
+        }
+        first = w_max(first);
+        dead = first != 0u;
+        if (dead) rows = 0xFFFF - (int)first + 1;
+    }
     // Block II (kswv.cpp:526-548): gmax is the largest row maximum up to the stop row, te its FIRST row, qe that
     // row's first column
     uint32_t best = 0;
@@ -229,7 +246,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint8_t *__restrict
 
 template <int C>
 struct DpCall {
-    static __device__ Best run(const KParams &K, const uint8_t *t, int tlen, const uint8_t *q, int qlen,
+    static __device__ Best run(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
                                bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
         const int bound = (tlen < qlen ? tlen : qlen) * K.a;          // no H can exceed it
         if (byte && bound >= 255 - K.shift) return kswv_dp<C, true, false>(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
@@ -237,7 +254,7 @@ struct DpCall {
     }
 };
 
-__device__ inline Best kswv_dp_any(const KParams &K, const uint8_t *t, int tlen, const uint8_t *q, int qlen,
+__device__ inline Best kswv_dp_any(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
                                    bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
     const int quantum = byte ? 16 : 8;
     int ncol = (qlen + quantum - 1) / quantum * quantum;
@@ -296,7 +313,7 @@ __device__ inline void kswv_second(const KParams &K, const uint32_t *rowkey, int
 
 // One pair on one warp: phase 0, second best, phase 1. Every lane returns the same Result.
 __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_t *ref, const uint8_t *qer,
-                                   uint32_t *rowkey, uint2 *bnd, uint8_t *seqbuf) {
+                                   uint32_t *rowkey, uint2 *bnd, uint32_t *lutw, uint8_t *qbuf) {
     const int xtra = T.xtra;
     const bool byte = (xtra & kXByte) != 0;
     const int lim = byte ? 255 : 32767;
@@ -309,8 +326,16 @@ __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_
     if (sat < thr) thr = sat;
     const uint8_t *t = ref + T.roff, *q = qer + T.qoff;
 
+    // per reference row the four scores of its base (LUT word): built once per phase by all lanes, so that a step
+    // of the row loop loads one word instead of a base and five instructions of LUT arithmetic
+    const int k = w_lane();
+    for (int i = k; i < T.tlen; i += 32) {
+        const uint32_t b = t[i];
+        lutw[i] = b > 3u ? K.lut_amb : (K.lut_mis ^ (K.lut_ab << (8u * b)));
+    }
+    w_sync();
     Result r;
-    Best B = kswv_dp_any(K, t, T.tlen, q, T.qlen, byte, thr, rowkey, bnd);
+    Best B = kswv_dp_any(K, lutw, T.tlen, q, T.qlen, byte, thr, rowkey, bnd);
     r.score = byte ? (B.gmax + K.shift < 255 ? B.gmax : 255) : B.gmax;   // kswv.cpp:568
     r.te = B.te; r.qe = B.qe;
     r.tb = r.qb = -1;
@@ -322,12 +347,15 @@ __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_
         if (sat < thr1) thr1 = sat;
         // the reversed prefixes (revseq, bwamem_pair.cpp:673, :691) are written out once so that the row loop
         // reads its sequences the same way in both phases; the rows below te keep their order (len1 is unchanged)
-        const int rt = r.te + 1, q1 = r.qe + 1, k = w_lane();
-        uint8_t *tr = seqbuf, *qr = seqbuf + ((T.tlen + 15) & ~15);
-        for (int i = k; i < T.tlen; i += 32) tr[i] = t[i < rt ? rt - 1 - i : i];
-        for (int j = k; j < q1; j += 32) qr[j] = q[q1 - 1 - j];
+        const int rt = r.te + 1, q1 = r.qe + 1;
+        w_sync();                                                        // every lane is done with phase 0's words
+        for (int i = k; i < T.tlen; i += 32) {
+            const uint32_t b = t[i < rt ? rt - 1 - i : i];
+            lutw[i] = b > 3u ? K.lut_amb : (K.lut_mis ^ (K.lut_ab << (8u * b)));
+        }
+        for (int j = k; j < q1; j += 32) qbuf[j] = q[q1 - 1 - j];
         w_sync();                                                        // also: phase 0's keys are no longer needed
-        const Best V = kswv_dp_any(K, tr, T.tlen, qr, q1, byte, thr1, rowkey, bnd);
+        const Best V = kswv_dp_any(K, lutw, T.tlen, qbuf, q1, byte, thr1, rowkey, bnd);
         if (r.score == V.gmax) { r.tb = r.te - V.te; r.qb = r.qe - V.qe; }
     }
     return r;
@@ -340,18 +368,19 @@ constexpr int kKswvWarps = 4;       // warps per block
 __global__ void __launch_bounds__(kKswvWarps * 32)
 kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint8_t *__restrict__ ref,
             const uint8_t *__restrict__ qer, Result *__restrict__ out, uint32_t *rowkey_all, uint2 *bnd_all,
-            uint8_t *seq_all, int scratch_rows, int scratch_seq, int *counter) {
+            uint32_t *lutw_all, uint8_t *qbuf_all, int scratch_rows, int scratch_q, int *counter) {
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     uint32_t *rowkey = rowkey_all + (size_t)warp * scratch_rows;
     uint2 *bnd = bnd_all ? bnd_all + (size_t)warp * scratch_rows : nullptr;
-    uint8_t *seqbuf = seq_all + (size_t)warp * scratch_seq;
+    uint32_t *lutw = lutw_all + (size_t)warp * scratch_rows;
+    uint8_t *qbuf = qbuf_all + (size_t)warp * scratch_q;
     for (;;) {
         int id = 0;
         if (w_lane() == 0) id = atomicAdd(counter, 1);
         id = (int)w_from((uint32_t)id, 0);
         if (id >= ntasks) break;
         const Task T = tasks[id];
-        const Result r = kswv_pair(K, T, ref, qer, rowkey, bnd, seqbuf);
+        const Result r = kswv_pair(K, T, ref, qer, rowkey, bnd, lutw, qbuf);
         if (w_lane() == 0) out[T.out] = r;
         w_sync();
     }

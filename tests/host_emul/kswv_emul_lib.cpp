@@ -20,7 +20,8 @@ extern "C" int kswv_emul_batch(const int32_t *params, const bsw_seqpair *pairs, 
         wf::Warp warp;
         std::vector<uint32_t> rowmx;
         std::vector<uint2> bnd;
-        std::vector<uint8_t> seqbuf;
+        std::vector<uint8_t> qbuf;
+        std::vector<uint32_t> lutw;
 #pragma omp for schedule(dynamic, 8)
         for (int64_t i = 0; i < n; ++i) {
             const bsw_seqpair &sp = pairs[i];
@@ -28,10 +29,11 @@ extern "C" int kswv_emul_batch(const int32_t *params, const bsw_seqpair *pairs, 
             // exactly what the kernel gets per warp, poisoned so that a read of a row nobody stored shows up
             rowmx.assign((size_t)sp.len1 + 1, 0xDEADBEEFu);
             bnd.assign((size_t)sp.len1 + 1, uint2{0xDEADBEEFu, 0xDEADBEEFu});
-            seqbuf.assign((size_t)sp.len1 + sp.len2 + 64, (uint8_t)0xEE);
+            qbuf.assign((size_t)sp.len2 + 64, (uint8_t)0xEE);
+            lutw.assign((size_t)sp.len1 + 8, 0xDEADBEEFu);
             Result res[32];
             wf::run_warp(warp, [&]() {
-                const Result r = kswv_pair(K, T, ref, qer, rowmx.data(), bnd.data(), seqbuf.data());
+                const Result r = kswv_pair(K, T, ref, qer, rowmx.data(), bnd.data(), lutw.data(), qbuf.data());
                 res[w_lane()] = r;
             });
             for (int l = 1; l < 32; ++l)
