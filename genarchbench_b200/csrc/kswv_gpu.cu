@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -38,7 +39,8 @@ struct KSlot {
 };
 
 struct KDev {
-    int id = 0, sms = 0, warps = 0;
+    int id = 0, sms = 0, warps = 0, groups = 0;
+    int occ[3] = {0, 0, 0};                      // resident blocks per SM of the 8-, 16- and 32-lane kernels
     cudaStream_t st = nullptr;
     KSlot slot[kRing];
     uint32_t *d_rowmx = nullptr;
@@ -56,6 +58,7 @@ struct kswv_handle {
     KParams K;
     std::vector<KDev> devs;
     kswv_gpu_stats stats;
+    int force_width = 0;                        // KSWV_MIN_LANES: developer switch, at least this many lanes per pair
     char err[256];
 };
 
@@ -105,9 +108,14 @@ int ensure_dev(kswv_handle *h, KDev &d) {
         KCU(cudaEventCreate(&s.ev_start));
         KCU(cudaEventCreate(&s.ev_stop));
         KCU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-        KCU(cudaMalloc((void **)&s.d_counter, sizeof(int)));
+        KCU(cudaMalloc((void **)&s.d_counter, 2 * sizeof(int)));
     }
+    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[0], kswv_kernel<8>, kKswvWarps * 32, 0));
+    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[1], kswv_kernel<16>, kKswvWarps * 32, 0));
+    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[2], kswv_kernel<32>, kKswvWarps * 32, 0));
+    for (int &o : d.occ) o = std::max(1, std::min(o, kBlocksPerSm));
     d.warps = d.sms * kBlocksPerSm * kKswvWarps;
+    d.groups = d.warps * 4;                     // 8 lanes per pair at the narrowest
     return BSW_OK;
 }
 
@@ -160,12 +168,6 @@ void free_dev(KDev &d) {
     if (d.st) cudaStreamDestroy(d.st);
 }
 
-inline int padded_cols(int qlen, bool byte) {
-    const int q = byte ? 16 : 8;
-    const int n = (qlen + q - 1) / q * q;
-    return n == 0 ? q : n;
-}
-
 // waits for the slot's chunk, scatters its results to aln[regid], adds its kernel time
 int drain_slot(kswv_handle *h, KDev &d, KSlot &s, const bsw_seqpair *pairs, kswv_result *aln) {
     if (!s.busy) return BSW_OK;
@@ -204,6 +206,10 @@ int kswv_gpu_init(const kswv_params *params, int n_gpus, kswv_handle **out) {
     h->P = p;
     h->K = make_kparams(p.o_del, p.e_del, p.o_ins, p.e_ins, p.match, p.mismatch);
     h->err[0] = 0;
+    if (const char *e = getenv("KSWV_MIN_LANES")) {
+        const int w = atoi(e);
+        if (w == 8 || w == 16 || w == 32) h->force_width = w;
+    }
     memset(&h->stats, 0, sizeof h->stats);
     h->stats.n_gpus = want;
     h->devs.resize((size_t)want);
@@ -256,7 +262,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
     const auto t0 = std::chrono::steady_clock::now();
     kswv_gpu_stats &S = h->stats;
     S.chunks = 0; S.pairs = n; S.pairs8 = 0; S.cells = 0; S.h2d_bytes = 0; S.d2h_bytes = 0; S.kernel_launches = 0;
-    S.gathered = 0; S.kernel_ms = 0; S.wall_ms = 0;
+    S.gathered = 0; S.kernel_ms = 0; S.wall_ms = 0; S.lanes_per_pair = 0;
     h->err[0] = 0;
     if (n == 0) return BSW_OK;
 
@@ -297,15 +303,15 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         if (rc) return rc;
         KCU(cudaSetDevice(d.id));
         const size_t rows = (size_t)maxT + 8;
-        rc = grow_dev(h, d.d_rowmx, d.cap_rows, rows * (size_t)d.warps);
+        rc = grow_dev(h, d.d_rowmx, d.cap_rows, rows * (size_t)d.groups);
         if (rc) return rc;
         if (maxCols > kPassCols) {
-            rc = grow_dev(h, d.d_bnd, d.cap_bnd, rows * (size_t)d.warps);
+            rc = grow_dev(h, d.d_bnd, d.cap_bnd, rows * (size_t)d.warps);     // several passes: 32 lanes per pair only
             if (rc) return rc;
         }
-        rc = grow_dev(h, d.d_lutw, d.cap_lutw, rows * (size_t)d.warps);
+        rc = grow_dev(h, d.d_lutw, d.cap_lutw, rows * (size_t)d.groups);
         if (rc) return rc;
-        rc = grow_dev(h, d.d_qbuf, d.cap_qbuf, (size_t)(maxQ + 64) * (size_t)d.warps);
+        rc = grow_dev(h, d.d_qbuf, d.cap_qbuf, (size_t)(maxQ + 64) * (size_t)d.groups);
         if (rc) return rc;
     }
     const int scratch_rows = maxT + 8, scratch_q = maxQ + 64;
@@ -347,22 +353,32 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         rc = ensure_slot(h, s, (size_t)cnt, ref_bytes, qer_bytes, dense ? 0 : (size_t)(rsum + qsum) + 64);
         if (rc) break;
 
-        // tasks in decreasing DP size (counting sort on rows x padded columns, 1024 buckets)
+        // Task order. Plain pairs first: no clamped arithmetic and at most 256 padded columns, the ones a group of
+        // fewer than 32 lanes can take. Inside each class by decreasing strip-width bucket (padded columns / 32) and
+        // decreasing reference length (8-row bins): the pairs that share a warp get the same code and nearly the same
+        // trip counts, and the largest DPs start first. One counting sort.
         const bsw_seqpair *cp = pairs + first;
         order.resize((size_t)cnt);
+        int64_t n_plain = 0;
+        int plain_cols = 0;
         {
-            constexpr int kBuckets = 1024;
-            int64_t maxcost = 1;
-            for (int64_t i = 0; i < cnt; ++i)
-                maxcost = std::max<int64_t>(maxcost, (int64_t)cp[i].len1 * padded_cols(cp[i].len2, (cp[i].h0 & kXByte) != 0));
-            bucket_start.assign(kBuckets + 1, 0);
-            auto bucket_of = [&](int64_t i) {
-                const int64_t c = (int64_t)cp[i].len1 * padded_cols(cp[i].len2, (cp[i].h0 & kXByte) != 0);
-                return (int)(kBuckets - 1 - c * (kBuckets - 1) / maxcost);           // large first
+            constexpr int kLenBins = 4096, kColBins = 9, kBuckets = 2 * kColBins * kLenBins;
+            bucket_start.assign((size_t)kBuckets + 1, 0);
+            auto bucket_of = [&](int64_t i, bool *plain, int *cols) {
+                const bool byte = (cp[i].h0 & kXByte) != 0;
+                const int nc = padded_cols(cp[i].len2, byte);
+                const bool special = nc > kPassCols || needs_sat(h->K.a, h->K.shift, cp[i].len1, cp[i].len2, byte);
+                const int cb = std::min((nc + 31) / 32, kColBins - 1);
+                if (plain) { *plain = !special; *cols = nc; }
+                return ((special ? 1 : 0) * kColBins + (kColBins - 1 - cb)) * kLenBins + (kLenBins - 1 - (cp[i].len1 >> 3));
             };
-            for (int64_t i = 0; i < cnt; ++i) ++bucket_start[(size_t)bucket_of(i) + 1];
+            for (int64_t i = 0; i < cnt; ++i) {
+                bool plain; int cols;
+                ++bucket_start[(size_t)bucket_of(i, &plain, &cols) + 1];
+                if (plain) { ++n_plain; plain_cols = std::max(plain_cols, cols); }
+            }
             for (int b = 0; b < kBuckets; ++b) bucket_start[(size_t)b + 1] += bucket_start[(size_t)b];
-            for (int64_t i = 0; i < cnt; ++i) order[bucket_start[(size_t)bucket_of(i)]++] = (uint32_t)i;
+            for (int64_t i = 0; i < cnt; ++i) order[bucket_start[(size_t)bucket_of(i, nullptr, nullptr)]++] = (uint32_t)i;
         }
         if (dense) {
 #pragma omp parallel for schedule(static) if (cnt > 4096)
@@ -397,19 +413,34 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, s.h_seq, ref_bytes, cudaMemcpyHostToDevice, d.st));
             if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, s.h_seq + rsum, qer_bytes, cudaMemcpyHostToDevice, d.st));
         }
-        KCU(cudaMemsetAsync(s.d_counter, 0, sizeof(int), d.st));
+        KCU(cudaMemsetAsync(s.d_counter, 0, 2 * sizeof(int), d.st));
         KCU(cudaEventRecord(s.ev_start, d.st));
-        const int blocks = (int)std::min<int64_t>((cnt + kKswvWarps - 1) / kKswvWarps, (int64_t)d.sms * kBlocksPerSm);
-        kswv_kernel<<<blocks, kKswvWarps * 32, 0, d.st>>>(h->K, s.d_tasks, (int)cnt, s.d_ref, s.d_qer, s.d_out, d.d_rowmx,
-                                                           maxCols > kPassCols ? d.d_bnd : nullptr, d.d_lutw, d.d_qbuf, scratch_rows, scratch_q, s.d_counter);
-        KCU(cudaGetLastError());
+        // lanes per pair for the plain pairs: 8 up to 160 padded columns (strips of up to 20), 16 up to 256, else 32
+        int width = plain_cols <= group_cols(8) ? 8 : (plain_cols <= group_cols(16) ? 16 : 32);
+        if (h->force_width) width = std::max(width, h->force_width);
+        auto launch = [&](int W, const Task *tasks, int64_t nt, int *counter) -> cudaError_t {
+            if (nt <= 0) return cudaSuccess;
+            const int per_block = kKswvWarps * (32 / W);
+            const int blocks = (int)std::min<int64_t>((nt + per_block - 1) / per_block,
+                                                      (int64_t)d.sms * d.occ[W == 8 ? 0 : (W == 16 ? 1 : 2)]);
+            uint2 *bnd = (W == 32 && maxCols > kPassCols) ? d.d_bnd : nullptr;
+#define KSWV_LAUNCH(WW) kswv_kernel<WW><<<blocks, kKswvWarps * 32, 0, d.st>>>(h->K, tasks, (int)nt, s.d_ref, s.d_qer, s.d_out, \
+                            d.d_rowmx, bnd, d.d_lutw, d.d_qbuf, scratch_rows, scratch_q, counter)
+            if (W == 8) KSWV_LAUNCH(8); else if (W == 16) KSWV_LAUNCH(16); else KSWV_LAUNCH(32);
+#undef KSWV_LAUNCH
+            ++S.kernel_launches;
+            return cudaGetLastError();
+        };
+        KCU(launch(width, s.d_tasks, n_plain, s.d_counter));
+        KCU(launch(32, s.d_tasks + n_plain, cnt - n_plain, s.d_counter + 1));
+        S.lanes_per_pair = width;
         KCU(cudaEventRecord(s.ev_stop, d.st));
         KCU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(Result) * (size_t)cnt, cudaMemcpyDeviceToHost, d.st));
         KCU(cudaEventRecord(s.ev_done, d.st));
         s.busy = true; s.first = first; s.count = cnt;
         S.h2d_bytes += (int64_t)(sizeof(Task) * (size_t)cnt + ref_bytes + qer_bytes);
         S.d2h_bytes += (int64_t)(sizeof(Result) * (size_t)cnt);
-        ++S.kernel_launches; ++S.chunks;
+        ++S.chunks;
         first += cnt;
     }
     // ---- drain, oldest first on every device

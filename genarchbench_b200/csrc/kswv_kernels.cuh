@@ -50,31 +50,50 @@ struct KParams {
 struct Task { uint32_t roff, qoff; int32_t tlen, qlen, xtra, out; };
 struct Result { int32_t score, te, qe, score2, te2, tb, qb; };   // == kswr_t, ksw.h:45-50
 
-// ------------------------------------------------------------------ warp primitives
+// ------------------------------------------------------------------ lane-group primitives
+// A pair is worked on by a group of W = 8, 16 or 32 adjacent lanes (32 / W pairs per warp). Every collective of
+// the per-pair code names its group's mask, so groups of one warp may run different trip counts; they are brought
+// together again by full-warp barriers between the phases (kswv_pair).
 #ifdef BSW_HOST_EMUL
-inline int w_lane() { return wf::lane(); }
-inline uint32_t w_up1(uint32_t v) { return wf::shfl_up1(v); }
-inline uint32_t w_from(uint32_t v, int src) { return wf::shfl(v, src); }
-inline bool w_any(bool p) { return wf::any(p); }
-inline uint32_t w_ballot(bool p) { return wf::ballot(p); }
-inline uint32_t w_max(uint32_t v) { return wf::reduce_max(v); }
-inline void w_sync() { wf::syncwarp(); }
+inline int hw_lane() { return wf::lane(); }
 inline uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) { return emul::prmt(a, b, sel); }
+inline void sync_all() { wf::syncwarp(0xFFFFFFFFu); }
 #else
-__device__ __forceinline__ int w_lane() { return (int)(threadIdx.x & 31u); }
-__device__ __forceinline__ uint32_t w_up1(uint32_t v) { return __shfl_up_sync(0xFFFFFFFFu, v, 1); }
-__device__ __forceinline__ uint32_t w_from(uint32_t v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
-__device__ __forceinline__ bool w_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
-__device__ __forceinline__ uint32_t w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
-__device__ __forceinline__ uint32_t w_max(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
-__device__ __forceinline__ void w_sync() { __syncwarp(); }
+__device__ __forceinline__ int hw_lane() { return (int)(threadIdx.x & 31u); }
 // PTX prmt.b32, default mode: a selector nibble with bit 3 set replicates the selected byte's sign bit
 __device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
 }
+__device__ __forceinline__ void sync_all() { __syncwarp(0xFFFFFFFFu); }
 #endif
+
+template <int W>
+struct Grp {
+    static __device__ __forceinline__ int lane() { return hw_lane() & (W - 1); }
+    static __device__ __forceinline__ int base() { return hw_lane() & ~(W - 1); }
+    static __device__ __forceinline__ uint32_t mask() {
+        return W == 32 ? 0xFFFFFFFFu : (((1u << (W & 31)) - 1u) << base());
+    }
+#ifdef BSW_HOST_EMUL
+    static uint32_t up1(uint32_t v) { return wf::shfl_up1(v, mask(), W); }
+    static uint32_t from(uint32_t v, int src) { return wf::shfl(v, src, mask(), W); }
+    static bool any(bool p) { return wf::any(p, mask()); }
+    static uint32_t ballot(bool p) { return W == 32 ? wf::ballot(p, mask()) : (wf::ballot(p, mask()) >> base()); }
+    static uint32_t maxu(uint32_t v) { return wf::reduce_max(v, mask()); }
+    static void sync() { wf::syncwarp(mask()); }
+#else
+    static __device__ __forceinline__ uint32_t up1(uint32_t v) { return __shfl_up_sync(mask(), v, 1, W); }
+    static __device__ __forceinline__ uint32_t from(uint32_t v, int src) { return __shfl_sync(mask(), v, src, W); }
+    static __device__ __forceinline__ bool any(bool p) { return __any_sync(mask(), p) != 0; }
+    static __device__ __forceinline__ uint32_t ballot(bool p) {
+        return W == 32 ? __ballot_sync(mask(), p) : (__ballot_sync(mask(), p) >> base());
+    }
+    static __device__ __forceinline__ uint32_t maxu(uint32_t v) { return __reduce_max_sync(mask(), v); }
+    static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+#endif
+};
 
 // host side of KParams: the two LUT words. Byte q of lut_lo(r) is the score of reference base r against query
 // code q = 0..3; lut_hi holds query codes 4 (ambiguous), 5 (zero-score padding column), 6 (left filler: negative).
@@ -98,21 +117,27 @@ inline KParams make_kparams(int o_del, int e_del, int o_ins, int e_ins, int matc
 
 struct Best { int32_t gmax, te, qe, rows; bool dead; };
 
-// The DP of tlen reference rows x q[0..qlen) (padded) on one warp.
-//  lutw  : per reference row, the four scores of its base against query codes 0..3 (one byte each; row_luts())
-//  thr   : gmax >= thr ends the lane (kNoStop: never)
+constexpr int kMaxC32 = 8, kMaxC16 = 16, kMaxC8 = 20;     // columns per lane, by group width
+// widest padded query a group of W lanes takes in one pass
+__host__ __device__ constexpr int group_cols(int W) { return W == 32 ? 32 * kMaxC32 : (W == 16 ? 16 * kMaxC16 : 8 * kMaxC8); }
+
+// The DP of tlen reference rows x q[0..qlen) (padded) on one group of W lanes.
+//  lutw  : per reference row, the four scores of its base against query codes 0..3 (one byte each)
+//  thr   : gmax >= thr ends the pair (kNoStop: never)
 //  rowkey: row i's key (row maximum << 16 | 0xFFFF - its first column, fillers included) for rows 0 .. rows-1
-//  bnd   : boundary column between passes (MP: queries above 256 columns), tlen entries
-// gmax / te / qe are taken from the stored keys after the loop: the lane that sees a finished row only stores its
+//  bnd   : boundary column between passes (MP: queries above 256 columns, W = 32 only), tlen entries
+// The padded columns are cut into strips of C consecutive columns, one per lane; lane k works on row s - k at step
+// s. gmax / te / qe are taken from the stored keys after the loop: the lane that sees a finished row only stores its
 // key and tests the stop threshold, because whatever a single lane does costs the whole warp an issue slot.
 // SAT: the diagonal term can reach the 8-bit class's ceiling (255 - shift) and is clamped there by a VIADDMNMX.
 // When min(tlen, qlen) * match stays below the ceiling (every pair bwa-mem2 puts in the 8-bit class: l_ms * a < 250)
 // and in the 16-bit class, the sum is an IMAD by a run-time 1 instead -- the FMA pipe has room, the ALU pipe binds.
-template <int C, bool SAT, bool MP>
+template <int W, int C, bool SAT, bool MP>
 __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restrict__ lutw, int tlen,
                                      const uint8_t *__restrict__ q, int qlen, bool byte, int thr,
                                      uint32_t *rowkey, uint2 *bnd) {
-    const int k = w_lane();
+    typedef Grp<W> G;
+    const int k = G::lane();
     const int quantum = byte ? 16 : 8;
     int ncol = (qlen + quantum - 1) / quantum * quantum;
     if (ncol == 0) ncol = quantum;          // an empty query is all padding: every H stays 0
@@ -127,7 +152,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
     int pad = 0;
     for (int p = 0; p < npass; ++p) {
         const int c_lo = p * kPassCols;
-        const int pcols = (ncol - c_lo < kPassCols) ? ncol - c_lo : kPassCols;
+        const int pcols = MP ? ((ncol - c_lo < kPassCols) ? ncol - c_lo : kPassCols) : ncol;
         const int nl = (pcols + C - 1) / C;
         pad = nl * C - pcols;               // only non-zero in a single-pass DP (C divides 256)
         const int last = nl - 1;
@@ -159,49 +184,49 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
         uint32_t out_he = 0, out_key = 0;
         const int steps = tlen + nl - 1;
         int s4 = 0;
-        // four steps per stop test: a lane that has reached thr keeps going for at most three rows, which the
+        // four steps per stop test: a pair that has reached thr keeps going for at most three rows, which the
         // scan after the loop drops again
         for (; s4 < steps; s4 += 4) {
-            if (w_any(dead)) break;
+            if (G::any(dead)) break;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-            const int s = s4 + u;
-            uint32_t in_he = w_up1(out_he) & not0, in_key = w_up1(out_key) & not0;
-            const int i = s - k;
-            const bool active = (unsigned)i < (unsigned)my_rows;
-            if (MP && p > 0 && k == 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
-            if (active) {
-                const uint32_t lut_lo = lutw[i];
-                const int hl = (int)(in_he & 0xFFFFu);
-                int e = (int)(in_he >> 16);
-                int key = (int)in_key;
-                int diag = hdiag;
-                int kprev = 0;
+                const int s = s4 + u;
+                uint32_t in_he = G::up1(out_he) & not0, in_key = G::up1(out_key) & not0;
+                const int i = s - k;
+                const bool active = (unsigned)i < (unsigned)my_rows;
+                if (MP && p > 0 && k == 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
+                if (active) {
+                    const uint32_t lut_lo = lutw[i];
+                    const int hl = (int)(in_he & 0xFFFFu);
+                    int e = (int)(in_he >> 16);
+                    int key = (int)in_key;
+                    int diag = hdiag;
+                    int kprev = 0;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const int sc = (int)prmt_sx(lut_lo, lut_hi, sel[c]);
-                    const int x = SAT ? __viaddmin_s32(diag, sc, clamp) : diag * one + sc;
-                    diag = H[c];
-                    const int f = F[c];
-                    const int h = __vimax3_s32_relu(x, e, f);
-                    const int kcur = (h << 16) + kc[c];             // IMAD
-                    if (c & 1) key = __vimax3_s32(key, kprev, kcur);  // one VIMNMX3 per two columns
-                    else if (c == C - 1) key = max(key, kcur);
-                    kprev = kcur;
-                    e = __viaddmax_s32_relu(h, noe_ins, e - e_ins);
-                    F[c] = __viaddmax_s32_relu(h, noe_del, f - e_del);
-                    H[c] = h;
+                    for (int c = 0; c < C; ++c) {
+                        const int sc = (int)prmt_sx(lut_lo, lut_hi, sel[c]);
+                        const int x = SAT ? __viaddmin_s32(diag, sc, clamp) : diag * one + sc;
+                        diag = H[c];
+                        const int f = F[c];
+                        const int h = __vimax3_s32_relu(x, e, f);
+                        const int kcur = (h << 16) + kc[c];             // IMAD
+                        if (c & 1) key = __vimax3_s32(key, kprev, kcur);  // one VIMNMX3 per two columns
+                        else if (c == C - 1) key = max(key, kcur);
+                        kprev = kcur;
+                        e = __viaddmax_s32_relu(h, noe_ins, e - e_ins);
+                        F[c] = __viaddmax_s32_relu(h, noe_del, f - e_del);
+                        H[c] = h;
+                    }
+                    hdiag = hl;
+                    out_he = (uint32_t)H[C - 1] | ((uint32_t)e << 16);
+                    out_key = (uint32_t)key;
+                    if (keeper) rowkey[i] = (uint32_t)key;
+                    dead |= keeper && (key >> 16) >= thr;   // gmax >= thr first holds on the first row that reaches thr
+                    if (MP && feeder) bnd[i] = make_uint2(out_he, out_key);
                 }
-                hdiag = hl;
-                out_he = (uint32_t)H[C - 1] | ((uint32_t)e << 16);
-                out_key = (uint32_t)key;
-                if (keeper) rowkey[i] = (uint32_t)key;
-                dead |= keeper && (key >> 16) >= thr;   // gmax >= thr first holds on the first row that reaches thr
-                if (MP && feeder) bnd[i] = make_uint2(out_he, out_key);
-            }
             }
         }
-        if (MP && !lastpass) w_sync();      // the next pass's lane 0 reads what this pass's last lane wrote
+        if (MP && !lastpass) G::sync();     // the next pass's lane 0 reads what this pass's last lane wrote
         if (lastpass) {
             // the loop ran s4 steps; the keeper's last finished row is s4 - 1 - last
             rows = s4 - last;
@@ -209,30 +234,30 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
             if (rows < 0) rows = 0;
         }
     }
-    w_sync();                               // rowkey: one lane wrote, all lanes read
+    G::sync();                              // rowkey: one lane wrote, all lanes read
     // the stop row: the first row whose maximum reaches thr (Block II's exit, kswv.cpp:535-548); rows past it
     // were computed by the lanes that were ahead of the keeper and do not exist for the reference
     {
         uint32_t first = 0;
-        for (int base = 0; base < rows; base += 32) {
+        for (int base = 0; base < rows; base += W) {
             const int i = base + k;
             if (i < rows && (int)(rowkey[i] >> 16) >= thr) { first = (uint32_t)(0xFFFF - i); break; }
         }
-        first = w_max(first);
+        first = G::maxu(first);
         dead = first != 0u;
         if (dead) rows = 0xFFFF - (int)first + 1;
     }
     // Block II (kswv.cpp:526-548): gmax is the largest row maximum up to the stop row, te its FIRST row, qe that
     // row's first column
     uint32_t best = 0;
-    for (int base = 0; base < rows; base += 32) {
+    for (int base = 0; base < rows; base += W) {
         const int i = base + k;
         if (i < rows) {
             const uint32_t cand = (rowkey[i] & 0xFFFF0000u) | (uint32_t)(0xFFFF - i);
             best = cand > best ? cand : best;
         }
     }
-    best = w_max(best);
+    best = G::maxu(best);
     Best B;
     B.gmax = (int)(best >> 16); B.rows = rows; B.dead = dead;
     B.te = -1; B.qe = 0;
@@ -244,41 +269,75 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
     return B;
 }
 
-template <int C>
-struct DpCall {
-    static __device__ Best run(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
-                               bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
-        const int bound = (tlen < qlen ? tlen : qlen) * K.a;          // no H can exceed it
-        if (byte && bound >= 255 - K.shift) return kswv_dp<C, true, false>(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-        return kswv_dp<C, false, false>(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-    }
-};
-
-__device__ inline Best kswv_dp_any(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
-                                   bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
+// does the pair need the clamped (SAT) arithmetic? (host and device agree on this)
+__host__ __device__ inline bool needs_sat(int a, int shift, int tlen, int qlen, bool byte) {
+    return byte && (tlen < qlen ? tlen : qlen) * a >= 255 - shift;
+}
+__host__ __device__ inline int padded_cols(int qlen, bool byte) {
     const int quantum = byte ? 16 : 8;
-    int ncol = (qlen + quantum - 1) / quantum * quantum;
-    if (ncol == 0) ncol = quantum;
-    if (ncol > kPassCols) return kswv_dp<8, true, true>(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+    const int n = (qlen + quantum - 1) / quantum * quantum;
+    return n == 0 ? quantum : n;
+}
+
+#define KSWV_DP_ARGS K, t, tlen, q, qlen, byte, thr, rowkey, bnd
+template <int W>
+__device__ inline Best kswv_dp_any(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
+                                   bool byte, int thr, uint32_t *rowkey, uint2 *bnd);
+
+// W = 32: any pair -- strips of 1..8 columns, the clamped variant where needed, several passes above 256 columns
+template <>
+__device__ inline Best kswv_dp_any<32>(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
+                                       bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
+    const int ncol = padded_cols(qlen, byte);
+    if (ncol > kPassCols) return kswv_dp<32, 8, true, true>(KSWV_DP_ARGS);
+    const bool sat = needs_sat(K.a, K.shift, tlen, qlen, byte);
+#define KSWV_CASE32(CC) case CC: return sat ? kswv_dp<32, CC, true, false>(KSWV_DP_ARGS) : kswv_dp<32, CC, false, false>(KSWV_DP_ARGS);
     switch ((ncol + 31) / 32) {
-        case 1: return DpCall<1>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-        case 2: return DpCall<2>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-        case 3: return DpCall<3>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-        case 4: return DpCall<4>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-        case 5: return DpCall<5>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-        case 6: return DpCall<6>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-        case 7: return DpCall<7>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
-        default: return DpCall<8>::run(K, t, tlen, q, qlen, byte, thr, rowkey, bnd);
+        KSWV_CASE32(1) KSWV_CASE32(2) KSWV_CASE32(3) KSWV_CASE32(4) KSWV_CASE32(5) KSWV_CASE32(6) KSWV_CASE32(7)
+        default: return sat ? kswv_dp<32, 8, true, false>(KSWV_DP_ARGS) : kswv_dp<32, 8, false, false>(KSWV_DP_ARGS);
+    }
+#undef KSWV_CASE32
+}
+// W = 16: pairs without clamping, up to 256 padded columns; strips of 2, 4, .. 16 columns
+template <>
+__device__ inline Best kswv_dp_any<16>(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
+                                       bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
+    const int ncol = padded_cols(qlen, byte);
+    switch ((ncol + 31) / 32) {
+        case 1: return kswv_dp<16, 2, false, false>(KSWV_DP_ARGS);
+        case 2: return kswv_dp<16, 4, false, false>(KSWV_DP_ARGS);
+        case 3: return kswv_dp<16, 6, false, false>(KSWV_DP_ARGS);
+        case 4: return kswv_dp<16, 8, false, false>(KSWV_DP_ARGS);
+        case 5: return kswv_dp<16, 10, false, false>(KSWV_DP_ARGS);
+        case 6: return kswv_dp<16, 12, false, false>(KSWV_DP_ARGS);
+        case 7: return kswv_dp<16, 14, false, false>(KSWV_DP_ARGS);
+        default: return kswv_dp<16, 16, false, false>(KSWV_DP_ARGS);
     }
 }
+// W = 8: pairs without clamping, up to 160 padded columns; strips of 4, 8, .. 20 columns
+template <>
+__device__ inline Best kswv_dp_any<8>(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
+                                      bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
+    const int ncol = padded_cols(qlen, byte);
+    switch ((ncol + 31) / 32) {
+        case 1: return kswv_dp<8, 4, false, false>(KSWV_DP_ARGS);
+        case 2: return kswv_dp<8, 8, false, false>(KSWV_DP_ARGS);
+        case 3: return kswv_dp<8, 12, false, false>(KSWV_DP_ARGS);
+        case 4: return kswv_dp<8, 16, false, false>(KSWV_DP_ARGS);
+        default: return kswv_dp<8, 20, false, false>(KSWV_DP_ARGS);
+    }
+}
+#undef KSWV_DP_ARGS
 
 // Second best (kswv.cpp:589-703, :1139-1212) from the stored row maxima. Row i's maximum is kept when row i+1
 // did not rise above it and row i-1 was not kept (Block I's mask, kswv.cpp:510-523), it reached minsc, and the
 // lane was still live when the reference stored it. kept(i) = nr(i+1) & !kept(i-1) is a one-bit recurrence:
-// 32 rows per step, the bits of one ballot word resolved in a short serial loop that every lane runs.
+// W rows per step, the bits of one ballot word resolved in a short serial loop that every lane runs.
+template <int W>
 __device__ inline void kswv_second(const KParams &K, const uint32_t *rowkey, int tlen, const Best &B, bool byte,
                                    bool has_minsc, int minsc, int32_t *score2, int32_t *te2) {
-    const int k = w_lane();
+    typedef Grp<W> G;
+    const int k = G::lane();
     const int R = B.dead ? B.rows - 1 : tlen;           // rows whose stored maximum can be kept
     const int val = (B.gmax + K.qmax - 1) / K.qmax;
     const int low = (int16_t)(B.te - val), high = (int16_t)(B.te + val);
@@ -286,13 +345,13 @@ __device__ inline void kswv_second(const KParams &K, const uint32_t *rowkey, int
     uint32_t best = 0;
     if (has_minsc) {
         uint32_t carry = 0;
-        for (int base = 0; base < R; base += 32) {
+        for (int base = 0; base < R; base += W) {
             const int i = base + k;
             const int cur = i < R ? (int)(rowkey[i] >> 16) : 0;
             const int nxt = (i + 1 < B.rows && i < R) ? (int)(rowkey[i + 1] >> 16) : 0;   // past the last row: not rising
-            const uint32_t N = w_ballot(i < R && !(nxt > cur));
+            const uint32_t N = G::ballot(i < R && !(nxt > cur));
             uint32_t X = 0, prev = carry;
-            for (int b = 0; b < 32; ++b) {
+            for (int b = 0; b < W; ++b) {
                 const uint32_t bit = (N >> b) & 1u & (prev ^ 1u);
                 X |= bit << b;
                 prev = bit;
@@ -306,14 +365,18 @@ __device__ inline void kswv_second(const KParams &K, const uint32_t *rowkey, int
             }
         }
     }
-    best = w_max(best);
+    best = G::maxu(best);
     if (best == 0u) { *score2 = -1; *te2 = -1; }
     else { *score2 = (int)(best >> 16) - (int)off; *te2 = 0xFFFF - (int)(best & 0xFFFFu); }
 }
 
-// One pair on one warp: phase 0, second best, phase 1. Every lane returns the same Result.
+// One pair on one group of W lanes: phase 0, second best, phase 1. Every lane of the group returns the same Result.
+// The groups of a warp meet at three full-warp barriers so that they run the two row loops side by side instead of
+// one after the other; a group without a pair gets an empty task (tlen = qlen = 0, xtra = 0) and still takes part.
+template <int W>
 __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_t *ref, const uint8_t *qer,
                                    uint32_t *rowkey, uint2 *bnd, uint32_t *lutw, uint8_t *qbuf) {
+    typedef Grp<W> G;
     const int xtra = T.xtra;
     const bool byte = (xtra & kXByte) != 0;
     const int lim = byte ? 255 : 32767;
@@ -328,61 +391,72 @@ __device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_
 
     // per reference row the four scores of its base (LUT word): built once per phase by all lanes, so that a step
     // of the row loop loads one word instead of a base and five instructions of LUT arithmetic
-    const int k = w_lane();
-    for (int i = k; i < T.tlen; i += 32) {
+    const int k = G::lane();
+    for (int i = k; i < T.tlen; i += W) {
         const uint32_t b = t[i];
         lutw[i] = b > 3u ? K.lut_amb : (K.lut_mis ^ (K.lut_ab << (8u * b)));
     }
-    w_sync();
+    if (W < 32) sync_all(); else G::sync();
     Result r;
-    Best B = kswv_dp_any(K, lutw, T.tlen, q, T.qlen, byte, thr, rowkey, bnd);
+    Best B = kswv_dp_any<W>(K, lutw, T.tlen, q, T.qlen, byte, thr, rowkey, bnd);
     r.score = byte ? (B.gmax + K.shift < 255 ? B.gmax : 255) : B.gmax;   // kswv.cpp:568
     r.te = B.te; r.qe = B.qe;
     r.tb = r.qb = -1;
     if (byte && r.score == 255) { r.score2 = -1; r.te2 = -1; }
-    else kswv_second(K, rowkey, T.tlen, B, byte, has_minsc, minsc, &r.score2, &r.te2);
+    else kswv_second<W>(K, rowkey, T.tlen, B, byte, has_minsc, minsc, &r.score2, &r.te2);
 
-    if ((xtra & kXStart) && !((xtra & kXSubo) && r.score < (xtra & 0xffff))) {   // bwamem_pair.cpp:667, :685
-        int thr1 = r.score;                                             // h0 = KSW_XSTOP | score
-        if (sat < thr1) thr1 = sat;
+    const bool phase1 = (xtra & kXStart) && !((xtra & kXSubo) && r.score < (xtra & 0xffff));   // bwamem_pair.cpp:667, :685
+    const int rt = r.te + 1, q1 = r.qe + 1;
+    G::sync();                                                           // every lane is done with phase 0's words
+    if (phase1) {
         // the reversed prefixes (revseq, bwamem_pair.cpp:673, :691) are written out once so that the row loop
         // reads its sequences the same way in both phases; the rows below te keep their order (len1 is unchanged)
-        const int rt = r.te + 1, q1 = r.qe + 1;
-        w_sync();                                                        // every lane is done with phase 0's words
-        for (int i = k; i < T.tlen; i += 32) {
+        for (int i = k; i < T.tlen; i += W) {
             const uint32_t b = t[i < rt ? rt - 1 - i : i];
             lutw[i] = b > 3u ? K.lut_amb : (K.lut_mis ^ (K.lut_ab << (8u * b)));
         }
-        for (int j = k; j < q1; j += 32) qbuf[j] = q[q1 - 1 - j];
-        w_sync();                                                        // also: phase 0's keys are no longer needed
-        const Best V = kswv_dp_any(K, lutw, T.tlen, qbuf, q1, byte, thr1, rowkey, bnd);
+        for (int j = k; j < q1; j += W) qbuf[j] = q[q1 - 1 - j];
+    }
+    if (W < 32) sync_all(); else G::sync();                              // also: phase 0's keys are no longer needed
+    if (phase1) {
+        int thr1 = r.score;                                             // h0 = KSW_XSTOP | score
+        if (sat < thr1) thr1 = sat;
+        const Best V = kswv_dp_any<W>(K, lutw, T.tlen, qbuf, q1, byte, thr1, rowkey, bnd);
         if (r.score == V.gmax) { r.tb = r.te - V.te; r.qb = r.qe - V.qe; }
     }
+    if (W < 32) sync_all();
     return r;
 }
 
 #ifndef BSW_HOST_EMUL
 constexpr int kKswvWarps = 4;       // warps per block
 
-// Persistent warps: each takes the next task (the host orders them by decreasing rows x columns) until none is left.
+// Persistent warps: each takes the next 32 / W tasks (the host orders them by decreasing size, equal strip widths
+// together) until none is left. Scratch (row keys, LUT words, reversed query, boundary column) is per group.
+template <int W>
 __global__ void __launch_bounds__(kKswvWarps * 32)
 kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint8_t *__restrict__ ref,
             const uint8_t *__restrict__ qer, Result *__restrict__ out, uint32_t *rowkey_all, uint2 *bnd_all,
             uint32_t *lutw_all, uint8_t *qbuf_all, int scratch_rows, int scratch_q, int *counter) {
+    constexpr int kGroups = 32 / W;
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    uint32_t *rowkey = rowkey_all + (size_t)warp * scratch_rows;
-    uint2 *bnd = bnd_all ? bnd_all + (size_t)warp * scratch_rows : nullptr;
-    uint32_t *lutw = lutw_all + (size_t)warp * scratch_rows;
-    uint8_t *qbuf = qbuf_all + (size_t)warp * scratch_q;
+    const int grp = warp * kGroups + (hw_lane() / W);
+    uint32_t *rowkey = rowkey_all + (size_t)grp * scratch_rows;
+    uint2 *bnd = bnd_all ? bnd_all + (size_t)grp * scratch_rows : nullptr;
+    uint32_t *lutw = lutw_all + (size_t)grp * scratch_rows;
+    uint8_t *qbuf = qbuf_all + (size_t)grp * scratch_q;
     for (;;) {
         int id = 0;
-        if (w_lane() == 0) id = atomicAdd(counter, 1);
-        id = (int)w_from((uint32_t)id, 0);
+        if (hw_lane() == 0) id = atomicAdd(counter, kGroups);
+        id = __shfl_sync(0xFFFFFFFFu, id, 0);
         if (id >= ntasks) break;
-        const Task T = tasks[id];
-        const Result r = kswv_pair(K, T, ref, qer, rowkey, bnd, lutw, qbuf);
-        if (w_lane() == 0) out[T.out] = r;
-        w_sync();
+        const int mine = id + hw_lane() / W;
+        Task T;
+        if (mine < ntasks) T = tasks[mine];
+        else { T.roff = 0; T.qoff = 0; T.tlen = 0; T.qlen = 0; T.xtra = 0; T.out = -1; }
+        const Result r = kswv_pair<W>(K, T, ref, qer, rowkey, bnd, lutw, qbuf);
+        if (Grp<W>::lane() == 0 && T.out >= 0) out[T.out] = r;
+        __syncwarp();
     }
 }
 #endif

@@ -27,13 +27,14 @@ class Params(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("n_gpus", C.c_int32), ("chunks", C.c_int32), ("pairs", C.c_int64), ("pairs8", C.c_int64),
+    _fields_ = [("n_gpus", C.c_int32), ("chunks", C.c_int32), ("lanes_per_pair", C.c_int32), ("reserved", C.c_int32),
+                ("pairs", C.c_int64), ("pairs8", C.c_int64),
                 ("cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("kernel_launches", C.c_int64), ("gathered", C.c_int64), ("kernel_ms", C.c_double),
                 ("wall_ms", C.c_double)]
 
     def asdict(self) -> dict:
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
 _bound = False

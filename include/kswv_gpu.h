@@ -45,6 +45,8 @@ typedef struct kswv_result { int32_t score, te, qe, score2, te2, tb, qb; } kswv_
 typedef struct kswv_gpu_stats {
     int32_t n_gpus;
     int32_t chunks;             /* last batch: pipeline chunks */
+    int32_t lanes_per_pair;     /* last chunk: lanes per pair of its plain pairs (8, 16 or 32) */
+    int32_t reserved;
     int64_t pairs;              /* last batch */
     int64_t pairs8;             /* last batch: pairs of the 8-bit class (KSWV_XBYTE) */
     int64_t cells;              /* last batch: phase-0 DP cells, len1 x padded query columns (the CUPS numerator) */

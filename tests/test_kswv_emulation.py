@@ -26,13 +26,13 @@ def emul():
                         "-I", d, "-I", os.path.join(ROOT, "genarchbench_b200", "csrc"),
                         "-I", os.path.join(ROOT, "include"), "-o", so, srcs[0]], check=True)
     L = C.CDLL(so)
-    L.kswv_emul_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
+    L.kswv_emul_batch.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_int32]
 
-    def run(pairs, ref, qer, params=None):
+    def run(pairs, ref, qer, params=None, width=32):
         aln = np.full((len(pairs), 7), -7, np.int32)
         rc = L.kswv_emul_batch(kswv._params(params), pairs.ctypes.data, np.ascontiguousarray(ref).ctypes.data,
-                               np.ascontiguousarray(qer).ctypes.data, len(pairs), aln.ctypes.data)
-        assert rc == 0, f"lanes of a warp disagree ({rc})"
+                               np.ascontiguousarray(qer).ctypes.data, len(pairs), aln.ctypes.data, width)
+        assert rc == 0, f"lanes of a group disagree, or a pair does not fit the width ({rc})"
         return aln
     return run
 
@@ -67,3 +67,31 @@ def test_empty_sequences(emul):
     pairs["len2"][1::4] = 0
     want, _ = kswv.oracle_batch(pairs, ref, qer)
     assert_same_aln(emul(pairs, ref, qer), want, pairs, "empty reference / query")
+
+
+# lanes per pair below 32: several pairs share a warp, each on its own group of lanes
+NARROW = [
+    (8, "151 bp reads", None, dict(n=203, read_len=(100, 151))),
+    (8, "every strip width up to 160 columns", None, dict(n=403, read_len=(1, 160), window=(0.3, 4.0), min_seed_len=5)),
+    (8, "stop + start, a = 2", dict(match=2, mismatch=5, o_del=4, e_del=2, o_ins=7, e_ins=1),
+     dict(n=201, match=2, read_len=(40, 110), xtra=lambda l: KSW_XSTOP | KSW_XSTART | KSW_XBYTE | 45)),
+    (16, "both classes up to 256 columns", None, dict(n=203, read_len=(120, 256), window=(0.5, 3.0))),
+    (16, "every strip width up to 256 columns", None, dict(n=301, read_len=(1, 249), window=(0.3, 4.0), min_seed_len=5)),
+]
+
+
+@pytest.mark.parametrize("width,what,params,kw", NARROW, ids=[f"W{c[0]}: {c[1]}" for c in NARROW])
+def test_several_pairs_per_warp(emul, width, what, params, kw):
+    pairs, ref, qer = kswv.make_workload(seed=23, **kw)
+    want, _ = kswv.oracle_batch(pairs, ref, qer, params)
+    assert_same_aln(emul(pairs, ref, qer, params, width=width), want, pairs, what)
+
+
+def test_groups_with_empty_and_unequal_pairs(emul):
+    """Neighbouring pairs of very different sizes, empty sequences and a ragged tail share warps."""
+    pairs, ref, qer = kswv.make_workload(101, seed=24, read_len=(5, 150), window=(0.2, 6.0), min_seed_len=3)
+    pairs["len1"][::5] = 0
+    pairs["len2"][2::7] = 0
+    want, _ = kswv.oracle_batch(pairs, ref, qer)
+    for width in (8, 16):
+        assert_same_aln(emul(pairs, ref, qer, width=width), want, pairs, f"W={width}")
