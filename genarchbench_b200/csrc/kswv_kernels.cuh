@@ -145,6 +145,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
     // scalars by value: K sits in the caller's local memory and would be re-read every step
     const int clamp = byte ? 255 - K.shift : 32767;
     const int noe_ins = -K.oe_ins, noe_del = -K.oe_del, e_ins = K.e_ins, e_del = K.e_del, one = K.one;
+    const int x10000 = K.one << 16;         // a register, so that the key's IMAD can take the column as its immediate
     const uint32_t lut_hi = K.lut_hi;
 
     int rows = 0;
@@ -157,7 +158,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
         pad = nl * C - pcols;               // only non-zero in a single-pass DP (C divides 256)
         const int last = nl - 1;
         const bool lastpass = !MP || p == npass - 1;
-        int H[C], F[C], kc[C];
+        int H[C], F[C];
         uint32_t sel[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -171,11 +172,9 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
             }
             sel[c] = code * 0x1111u + 0x8880u;
             H[c] = 0; F[c] = 0;
-            kc[c] = 0xFFFF - (c_lo + k * C + c);
-#ifndef BSW_HOST_EMUL
-            asm volatile("" : "+r"(kc[c]));     // keep one register per column: base + immediate would bring VIADDMNMX back
-#endif
         }
+        // a key's low half is 0xFFFF - column: the strip works with C - 1 - c and adds its own offset once per row
+        const int kbase = 0xFFFF - (c_lo + k * C) - (C - 1);
         const int my_rows = k < nl ? tlen : 0;
         const bool keeper = k == last && lastpass;      // the lane that sees finished rows
         const bool feeder = MP && k == last && !lastpass;
@@ -188,6 +187,18 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
         // scan after the loop drops again
         for (; s4 < steps; s4 += 4) {
             if (G::any(dead)) break;
+            // the four rows' LUT words up front (clamped into the scratch, which has slack past tlen): four loads in
+            // flight instead of one L2 round trip at the head of every step
+            uint32_t lut4[4];
+            {
+                const int i0 = s4 - k;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int iu = i0 + u;
+                    iu = iu < 0 ? 0 : (iu > tlen ? tlen : iu);
+                    lut4[u] = lutw[iu];
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int s = s4 + u;
@@ -196,10 +207,10 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
                 const bool active = (unsigned)i < (unsigned)my_rows;
                 if (MP && p > 0 && k == 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
                 if (active) {
-                    const uint32_t lut_lo = lutw[i];
+                    const uint32_t lut_lo = lut4[u];
                     const int hl = (int)(in_he & 0xFFFFu);
                     int e = (int)(in_he >> 16);
-                    int key = (int)in_key;
+                    int key = 0;
                     int diag = hdiag;
                     int kprev = 0;
 #pragma unroll
@@ -209,7 +220,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
                         diag = H[c];
                         const int f = F[c];
                         const int h = __vimax3_s32_relu(x, e, f);
-                        const int kcur = (h << 16) + kc[c];             // IMAD
+                        const int kcur = h * x10000 + (C - 1 - c);      // IMAD, FMA pipe
                         if (c & 1) key = __vimax3_s32(key, kprev, kcur);  // one VIMNMX3 per two columns
                         else if (c == C - 1) key = max(key, kcur);
                         kprev = kcur;
@@ -219,6 +230,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
                     }
                     hdiag = hl;
                     out_he = (uint32_t)H[C - 1] | ((uint32_t)e << 16);
+                    key = max(key + kbase, (int)in_key);
                     out_key = (uint32_t)key;
                     if (keeper) rowkey[i] = (uint32_t)key;
                     dead |= keeper && (key >> 16) >= thr;   // gmax >= thr first holds on the first row that reaches thr
@@ -434,7 +446,7 @@ constexpr int kKswvWarps = 4;       // warps per block
 // Persistent warps: each takes the next 32 / W tasks (the host orders them by decreasing size, equal strip widths
 // together) until none is left. Scratch (row keys, LUT words, reversed query, boundary column) is per group.
 template <int W>
-__global__ void __launch_bounds__(kKswvWarps * 32)
+__global__ void __launch_bounds__(kKswvWarps * 32, 4)
 kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint8_t *__restrict__ ref,
             const uint8_t *__restrict__ qer, Result *__restrict__ out, uint32_t *rowkey_all, uint2 *bnd_all,
             uint32_t *lutw_all, uint8_t *qbuf_all, int scratch_rows, int scratch_q, int *counter) {
