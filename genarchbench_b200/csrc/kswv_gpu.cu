@@ -2,6 +2,7 @@
 // slots per GPU (tasks + sequences H2D, one persistent-warp kernel, results D2H), the host orders each chunk's
 // tasks by decreasing DP size and scatters finished results to aln[regid]. Kernels: kswv_kernels.cuh.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <omp.h>
 
 #include <algorithm>
@@ -31,7 +32,10 @@ struct KSlot {
     Result *h_out = nullptr, *d_out = nullptr;
     uint8_t *h_seq = nullptr;                   // gather staging (only when a chunk is not one dense range)
     uint8_t *d_ref = nullptr, *d_qer = nullptr;
-    int *d_counter = nullptr;
+    int *d_counter = nullptr;                   // four task counters: phase 0 / phase 1 x plain / special
+    uint32_t *d_p1 = nullptr;                   // 4 x cap_pairs: phase-1 keys, task indices, and both sorted
+    void *d_sort = nullptr;
+    size_t cap_sort = 0;
     size_t cap_pairs = 0, cap_ref = 0, cap_qer = 0, cap_seq = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
     bool busy = false;
@@ -108,11 +112,11 @@ int ensure_dev(kswv_handle *h, KDev &d) {
         KCU(cudaEventCreate(&s.ev_start));
         KCU(cudaEventCreate(&s.ev_stop));
         KCU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-        KCU(cudaMalloc((void **)&s.d_counter, 2 * sizeof(int)));
+        KCU(cudaMalloc((void **)&s.d_counter, 4 * sizeof(int)));
     }
-    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[0], kswv_kernel<8>, kKswvWarps * 32, 0));
-    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[1], kswv_kernel<16>, kKswvWarps * 32, 0));
-    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[2], kswv_kernel<32>, kKswvWarps * 32, 0));
+    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[0], kswv_phase0_kernel<8>, kKswvWarps * 32, 0));
+    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[1], kswv_phase0_kernel<16>, kKswvWarps * 32, 0));
+    KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[2], kswv_phase0_kernel<32>, kKswvWarps * 32, 0));
     for (int &o : d.occ) o = std::max(1, std::min(o, kBlocksPerSm));
     d.warps = d.sms * kBlocksPerSm * kKswvWarps;
     d.groups = d.warps * 4;                     // 8 lanes per pair at the narrowest
@@ -124,13 +128,20 @@ int ensure_slot(kswv_handle *h, KSlot &s, size_t npairs, size_t ref_bytes, size_
         const size_t want = npairs + npairs / 4 + 256;
         if (s.d_tasks) KCU(cudaFree(s.d_tasks));
         if (s.d_out) KCU(cudaFree(s.d_out));
-        s.d_tasks = nullptr; s.d_out = nullptr; s.cap_pairs = 0;
+        if (s.d_p1) KCU(cudaFree(s.d_p1));
+        if (s.d_sort) KCU(cudaFree(s.d_sort));
+        s.d_tasks = nullptr; s.d_out = nullptr; s.d_p1 = nullptr; s.d_sort = nullptr; s.cap_pairs = 0; s.cap_sort = 0;
         int rc = grow_host(h, s.h_tasks, 0, want);
         if (rc) return rc;
         rc = grow_host(h, s.h_out, 0, want);
         if (rc) return rc;
         KCU(cudaMalloc((void **)&s.d_tasks, want * sizeof(Task)));
         KCU(cudaMalloc((void **)&s.d_out, want * sizeof(Result)));
+        KCU(cudaMalloc((void **)&s.d_p1, 4 * want * sizeof(uint32_t)));
+        size_t bytes = 0;
+        KCU(cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, s.d_p1, s.d_p1, s.d_p1, s.d_p1, (int)want, 0, 28));
+        KCU(cudaMalloc(&s.d_sort, bytes + 256));
+        s.cap_sort = bytes + 256;
         s.cap_pairs = want;
     }
     int rc = grow_dev(h, s.d_ref, s.cap_ref, ref_bytes + 64);
@@ -154,6 +165,8 @@ void free_dev(KDev &d) {
         if (s.h_seq) cudaFreeHost(s.h_seq);
         if (s.d_tasks) cudaFree(s.d_tasks);
         if (s.d_out) cudaFree(s.d_out);
+        if (s.d_p1) cudaFree(s.d_p1);
+        if (s.d_sort) cudaFree(s.d_sort);
         if (s.d_ref) cudaFree(s.d_ref);
         if (s.d_qer) cudaFree(s.d_qer);
         if (s.d_counter) cudaFree(s.d_counter);
@@ -413,26 +426,40 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, s.h_seq, ref_bytes, cudaMemcpyHostToDevice, d.st));
             if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, s.h_seq + rsum, qer_bytes, cudaMemcpyHostToDevice, d.st));
         }
-        KCU(cudaMemsetAsync(s.d_counter, 0, 2 * sizeof(int), d.st));
+        KCU(cudaMemsetAsync(s.d_counter, 0, 4 * sizeof(int), d.st));
         KCU(cudaEventRecord(s.ev_start, d.st));
         // lanes per pair for the plain pairs: 8 up to 160 padded columns (strips of up to 20), 16 up to 256, else 32
         int width = plain_cols <= group_cols(8) ? 8 : (plain_cols <= group_cols(16) ? 16 : 32);
         if (h->force_width) width = std::max(width, h->force_width);
-        auto launch = [&](int W, const Task *tasks, int64_t nt, int *counter) -> cudaError_t {
+        // one class of tasks [off, off + nt): phase 0, the phase-1 tasks ordered by (strip width, te) so that the pairs
+        // of a warp have similar trip counts, phase 1
+        auto run_class = [&](int W, int64_t off, int64_t nt, int *counters) -> cudaError_t {
             if (nt <= 0) return cudaSuccess;
             const int per_block = kKswvWarps * (32 / W);
             const int blocks = (int)std::min<int64_t>((nt + per_block - 1) / per_block,
                                                       (int64_t)d.sms * d.occ[W == 8 ? 0 : (W == 16 ? 1 : 2)]);
             uint2 *bnd = (W == 32 && maxCols > kPassCols) ? d.d_bnd : nullptr;
-#define KSWV_LAUNCH(WW) kswv_kernel<WW><<<blocks, kKswvWarps * 32, 0, d.st>>>(h->K, tasks, (int)nt, s.d_ref, s.d_qer, s.d_out, \
-                            d.d_rowmx, bnd, d.d_lutw, d.d_qbuf, scratch_rows, scratch_q, counter)
-            if (W == 8) KSWV_LAUNCH(8); else if (W == 16) KSWV_LAUNCH(16); else KSWV_LAUNCH(32);
-#undef KSWV_LAUNCH
-            ++S.kernel_launches;
+            const Task *tasks = s.d_tasks + off;
+            uint32_t *key = s.d_p1 + off, *val = s.d_p1 + s.cap_pairs + off;
+            uint32_t *key_s = s.d_p1 + 2 * s.cap_pairs + off, *val_s = s.d_p1 + 3 * s.cap_pairs + off;
+#define KSWV_P0(WW) kswv_phase0_kernel<WW><<<blocks, kKswvWarps * 32, 0, d.st>>>(h->K, tasks, (int)nt, s.d_ref, s.d_qer, s.d_out, \
+                        key, val, d.d_rowmx, bnd, d.d_lutw, scratch_rows, counters)
+#define KSWV_P1(WW) kswv_phase1_kernel<WW><<<blocks, kKswvWarps * 32, 0, d.st>>>(h->K, tasks, (int)nt, key_s, val_s, s.d_ref, s.d_qer, \
+                        s.d_out, d.d_rowmx, bnd, d.d_lutw, d.d_qbuf, scratch_rows, scratch_q, counters + 1)
+            if (W == 8) KSWV_P0(8); else if (W == 16) KSWV_P0(16); else KSWV_P0(32);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            size_t bytes = s.cap_sort;
+            e = cub::DeviceRadixSort::SortPairsDescending(s.d_sort, bytes, key, key_s, val, val_s, (int)nt, 0, 28, d.st);
+            if (e != cudaSuccess) return e;
+            if (W == 8) KSWV_P1(8); else if (W == 16) KSWV_P1(16); else KSWV_P1(32);
+#undef KSWV_P0
+#undef KSWV_P1
+            S.kernel_launches += 2;
             return cudaGetLastError();
         };
-        KCU(launch(width, s.d_tasks, n_plain, s.d_counter));
-        KCU(launch(32, s.d_tasks + n_plain, cnt - n_plain, s.d_counter + 1));
+        KCU(run_class(width, 0, n_plain, s.d_counter));
+        KCU(run_class(32, n_plain, cnt - n_plain, s.d_counter + 2));
         S.lanes_per_pair = width;
         KCU(cudaEventRecord(s.ev_stop, d.st));
         KCU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(Result) * (size_t)cnt, cudaMemcpyDeviceToHost, d.st));

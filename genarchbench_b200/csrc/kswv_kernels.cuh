@@ -52,8 +52,8 @@ struct Result { int32_t score, te, qe, score2, te2, tb, qb; };   // == kswr_t, k
 
 // ------------------------------------------------------------------ lane-group primitives
 // A pair is worked on by a group of W = 8, 16 or 32 adjacent lanes (32 / W pairs per warp). Every collective of
-// the per-pair code names its group's mask, so groups of one warp may run different trip counts; they are brought
-// together again by full-warp barriers between the phases (kswv_pair).
+// the per-pair code names its group's mask, so groups of one warp may run different trip counts (the task order keeps
+// them close); they meet again where the warp fetches its next tasks.
 #ifdef BSW_HOST_EMUL
 inline int hw_lane() { return wf::lane(); }
 inline uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) { return emul::prmt(a, b, sel); }
@@ -382,62 +382,73 @@ __device__ inline void kswv_second(const KParams &K, const uint32_t *rowkey, int
     else { *score2 = (int)(best >> 16) - (int)off; *te2 = 0xFFFF - (int)(best & 0xFFFFu); }
 }
 
-// One pair on one group of W lanes: phase 0, second best, phase 1. Every lane of the group returns the same Result.
-// The groups of a warp meet at three full-warp barriers so that they run the two row loops side by side instead of
-// one after the other; a group without a pair gets an empty task (tlen = qlen = 0, xtra = 0) and still takes part.
-template <int W>
-__device__ inline Result kswv_pair(const KParams &K, const Task &T, const uint8_t *ref, const uint8_t *qer,
-                                   uint32_t *rowkey, uint2 *bnd, uint32_t *lutw, uint8_t *qbuf) {
-    typedef Grp<W> G;
-    const int xtra = T.xtra;
-    const bool byte = (xtra & kXByte) != 0;
-    const int lim = byte ? 255 : 32767;
-    int v = (xtra & kXSubo) ? (xtra & 0xffff) : 0x10000;                 // kswv.cpp:422-437, :976-993
-    const bool has_minsc = v <= lim;
-    const int minsc = v;
-    v = (xtra & kXStop) ? (xtra & 0xffff) : 0x10000;
-    int thr = v <= lim ? v : kNoStop;
-    const int sat = byte ? 255 - K.shift : kNoStop;                      // adds_epu8(gmax, shift) == 255, kswv.cpp:539-540
-    if (sat < thr) thr = sat;
-    const uint8_t *t = ref + T.roff, *q = qer + T.qoff;
+// The two phases of a pair are separate kernels: phase 1's trip count (te + 1 rows, qe + 1 columns) is only known
+// after phase 0, and pairs that share a warp should have similar trip counts, so the phase-1 tasks are re-ordered on
+// the device in between (by strip width and te, a radix sort on p1key).
 
-    // per reference row the four scores of its base (LUT word): built once per phase by all lanes, so that a step
-    // of the row loop loads one word instead of a base and five instructions of LUT arithmetic
-    const int k = G::lane();
-    for (int i = k; i < T.tlen; i += W) {
-        const uint32_t b = t[i];
+struct Thresholds { bool byte, has_minsc; int minsc, thr, sat; };
+__device__ inline Thresholds kswv_thresholds(const KParams &K, int xtra) {
+    Thresholds t;
+    t.byte = (xtra & kXByte) != 0;
+    const int lim = t.byte ? 255 : 32767;
+    int v = (xtra & kXSubo) ? (xtra & 0xffff) : 0x10000;                 // kswv.cpp:422-437, :976-993
+    t.has_minsc = v <= lim;
+    t.minsc = v;
+    v = (xtra & kXStop) ? (xtra & 0xffff) : 0x10000;
+    t.thr = v <= lim ? v : kNoStop;
+    t.sat = t.byte ? 255 - K.shift : kNoStop;                           // adds_epu8(gmax, shift) == 255, kswv.cpp:539-540
+    if (t.sat < t.thr) t.thr = t.sat;
+    return t;
+}
+
+// per reference row the four scores of its base (LUT word): built once per phase by all lanes of the group, so that
+// a step of the row loop loads one word instead of a base and five instructions of LUT arithmetic. The first rt
+// rows are read backwards (phase 1: revseq of the aligned prefix, bwamem_pair.cpp:673, :691; len1 is unchanged).
+template <int W>
+__device__ inline void row_luts(const KParams &K, const uint8_t *t, int tlen, int rt, uint32_t *lutw) {
+    for (int i = Grp<W>::lane(); i < tlen; i += W) {
+        const uint32_t b = t[i < rt ? rt - 1 - i : i];
         lutw[i] = b > 3u ? K.lut_amb : (K.lut_mis ^ (K.lut_ab << (8u * b)));
     }
-    if (W < 32) sync_all(); else G::sync();
+}
+
+// Phase 0 of one pair on one group of W lanes: score, te, qe, score2, te2 (tb = qb = -1). *p1key = 0 if the pair has
+// no phase 1 (bwamem_pair.cpp:667, :685), else (strip-width bucket of phase 1 << 16) | rows of the reversed prefix.
+template <int W>
+__device__ inline Result kswv_phase0(const KParams &K, const Task &T, const uint8_t *ref, const uint8_t *qer,
+                                     uint32_t *rowkey, uint2 *bnd, uint32_t *lutw, uint32_t *p1key) {
+    const Thresholds th = kswv_thresholds(K, T.xtra);
+    const uint8_t *t = ref + T.roff, *q = qer + T.qoff;
+    row_luts<W>(K, t, T.tlen, 0, lutw);
+    Grp<W>::sync();
     Result r;
-    Best B = kswv_dp_any<W>(K, lutw, T.tlen, q, T.qlen, byte, thr, rowkey, bnd);
-    r.score = byte ? (B.gmax + K.shift < 255 ? B.gmax : 255) : B.gmax;   // kswv.cpp:568
+    const Best B = kswv_dp_any<W>(K, lutw, T.tlen, q, T.qlen, th.byte, th.thr, rowkey, bnd);
+    r.score = th.byte ? (B.gmax + K.shift < 255 ? B.gmax : 255) : B.gmax;   // kswv.cpp:568
     r.te = B.te; r.qe = B.qe;
     r.tb = r.qb = -1;
-    if (byte && r.score == 255) { r.score2 = -1; r.te2 = -1; }
-    else kswv_second<W>(K, rowkey, T.tlen, B, byte, has_minsc, minsc, &r.score2, &r.te2);
-
-    const bool phase1 = (xtra & kXStart) && !((xtra & kXSubo) && r.score < (xtra & 0xffff));   // bwamem_pair.cpp:667, :685
-    const int rt = r.te + 1, q1 = r.qe + 1;
-    G::sync();                                                           // every lane is done with phase 0's words
-    if (phase1) {
-        // the reversed prefixes (revseq, bwamem_pair.cpp:673, :691) are written out once so that the row loop
-        // reads its sequences the same way in both phases; the rows below te keep their order (len1 is unchanged)
-        for (int i = k; i < T.tlen; i += W) {
-            const uint32_t b = t[i < rt ? rt - 1 - i : i];
-            lutw[i] = b > 3u ? K.lut_amb : (K.lut_mis ^ (K.lut_ab << (8u * b)));
-        }
-        for (int j = k; j < q1; j += W) qbuf[j] = q[q1 - 1 - j];
-    }
-    if (W < 32) sync_all(); else G::sync();                              // also: phase 0's keys are no longer needed
-    if (phase1) {
-        int thr1 = r.score;                                             // h0 = KSW_XSTOP | score
-        if (sat < thr1) thr1 = sat;
-        const Best V = kswv_dp_any<W>(K, lutw, T.tlen, qbuf, q1, byte, thr1, rowkey, bnd);
-        if (r.score == V.gmax) { r.tb = r.te - V.te; r.qb = r.qe - V.qe; }
-    }
-    if (W < 32) sync_all();
+    if (th.byte && r.score == 255) { r.score2 = -1; r.te2 = -1; }
+    else kswv_second<W>(K, rowkey, T.tlen, B, th.byte, th.has_minsc, th.minsc, &r.score2, &r.te2);
+    const bool phase1 = (T.xtra & kXStart) && !((T.xtra & kXSubo) && r.score < (T.xtra & 0xffff));
+    *p1key = phase1 ? ((uint32_t)((padded_cols(r.qe + 1, th.byte) + 31) / 32) << 16) | (uint32_t)(r.te + 1) : 0u;
+    Grp<W>::sync();                                                      // the scratch is free for the next pair
     return r;
+}
+
+// Phase 1 (bwamem_pair.cpp:660-699): the prefixes ref[0..te], qer[0..qe] reversed, h0 = KSW_XSTOP | score, same class.
+template <int W>
+__device__ inline void kswv_phase1(const KParams &K, const Task &T, const uint8_t *ref, const uint8_t *qer,
+                                   uint32_t *rowkey, uint2 *bnd, uint32_t *lutw, uint8_t *qbuf, Result *r) {
+    const Thresholds th = kswv_thresholds(K, T.xtra);
+    const uint8_t *t = ref + T.roff, *q = qer + T.qoff;
+    const int rt = r->te + 1, q1 = r->qe + 1;
+    row_luts<W>(K, t, T.tlen, rt, lutw);
+    for (int j = Grp<W>::lane(); j < q1; j += W) qbuf[j] = q[q1 - 1 - j];
+    Grp<W>::sync();
+    int thr1 = r->score;
+    if (th.sat < thr1) thr1 = th.sat;
+    const Best V = kswv_dp_any<W>(K, lutw, T.tlen, qbuf, q1, th.byte, thr1, rowkey, bnd);
+    if (r->score == V.gmax) { r->tb = r->te - V.te; r->qb = r->qe - V.qe; }
+    Grp<W>::sync();                                                      // the scratch is free for the next pair
 }
 
 #ifndef BSW_HOST_EMUL
@@ -447,9 +458,38 @@ constexpr int kKswvWarps = 4;       // warps per block
 // together) until none is left. Scratch (row keys, LUT words, reversed query, boundary column) is per group.
 template <int W>
 __global__ void __launch_bounds__(kKswvWarps * 32, 4)
-kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint8_t *__restrict__ ref,
-            const uint8_t *__restrict__ qer, Result *__restrict__ out, uint32_t *rowkey_all, uint2 *bnd_all,
-            uint32_t *lutw_all, uint8_t *qbuf_all, int scratch_rows, int scratch_q, int *counter) {
+kswv_phase0_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint8_t *__restrict__ ref,
+                   const uint8_t *__restrict__ qer, Result *__restrict__ out, uint32_t *__restrict__ p1key,
+                   uint32_t *__restrict__ p1val, uint32_t *rowkey_all, uint2 *bnd_all, uint32_t *lutw_all,
+                   int scratch_rows, int *counter) {
+    constexpr int kGroups = 32 / W;
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int grp = warp * kGroups + (hw_lane() / W);
+    uint32_t *rowkey = rowkey_all + (size_t)grp * scratch_rows;
+    uint2 *bnd = bnd_all ? bnd_all + (size_t)grp * scratch_rows : nullptr;
+    uint32_t *lutw = lutw_all + (size_t)grp * scratch_rows;
+    for (;;) {
+        int id = 0;
+        if (hw_lane() == 0) id = atomicAdd(counter, kGroups);
+        id = __shfl_sync(0xFFFFFFFFu, id, 0);
+        if (id >= ntasks) break;
+        const int mine = id + hw_lane() / W;
+        if (mine < ntasks) {
+            const Task T = tasks[mine];
+            uint32_t key;
+            const Result r = kswv_phase0<W>(K, T, ref, qer, rowkey, bnd, lutw, &key);
+            if (Grp<W>::lane() == 0) { out[T.out] = r; p1key[mine] = key; p1val[mine] = (uint32_t)mine; }
+        }
+    }
+}
+
+// Phase 1 over the re-ordered tasks: order[j] is a task index, key[j] == 0 ends the list.
+template <int W>
+__global__ void __launch_bounds__(kKswvWarps * 32, 4)
+kswv_phase1_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ key,
+                   const uint32_t *__restrict__ order, const uint8_t *__restrict__ ref,
+                   const uint8_t *__restrict__ qer, Result *out, uint32_t *rowkey_all, uint2 *bnd_all,
+                   uint32_t *lutw_all, uint8_t *qbuf_all, int scratch_rows, int scratch_q, int *counter) {
     constexpr int kGroups = 32 / W;
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int grp = warp * kGroups + (hw_lane() / W);
@@ -461,14 +501,14 @@ kswv_kernel(const KParams K, const Task *__restrict__ tasks, int ntasks, const u
         int id = 0;
         if (hw_lane() == 0) id = atomicAdd(counter, kGroups);
         id = __shfl_sync(0xFFFFFFFFu, id, 0);
-        if (id >= ntasks) break;
+        if (id >= ntasks || key[id] == 0u) break;
         const int mine = id + hw_lane() / W;
-        Task T;
-        if (mine < ntasks) T = tasks[mine];
-        else { T.roff = 0; T.qoff = 0; T.tlen = 0; T.qlen = 0; T.xtra = 0; T.out = -1; }
-        const Result r = kswv_pair<W>(K, T, ref, qer, rowkey, bnd, lutw, qbuf);
-        if (Grp<W>::lane() == 0 && T.out >= 0) out[T.out] = r;
-        __syncwarp();
+        if (mine < ntasks && key[mine] != 0u) {
+            const Task T = tasks[order[mine]];
+            Result r = out[T.out];
+            kswv_phase1<W>(K, T, ref, qer, rowkey, bnd, lutw, qbuf, &r);
+            if (Grp<W>::lane() == 0) { out[T.out].tb = r.tb; out[T.out].qb = r.qb; }
+        }
     }
 }
 #endif

@@ -1,54 +1,88 @@
-// TEST INFRASTRUCTURE: runs the product's per-pair kswv device code (kswv_pair<W> from
+// TEST INFRASTRUCTURE: runs the product's per-pair kswv device code (kswv_phase0<W> / kswv_phase1<W> from
 // genarchbench_b200/csrc/kswv_kernels.cuh) on the CPU: DPX / PRMT through dpx_host_emul.h, the warp through the
-// 32-fiber emulation in warp_fibers.h, 32 / W pairs per warp exactly as the kernel assigns them. Used only by
+// 32-fiber emulation in warp_fibers.h, 32 / W pairs per warp exactly as the kernels assign them, phase-1 tasks
+// re-ordered by the key phase 0 leaves (the kernels' radix sort is a std::stable_sort here). Used only by
 // tests/test_kswv_emulation.py to check the kernel's ALGORITHM against the oracle where no GPU exists; it is not a
 // product path.
 #define BSW_HOST_EMUL 1
 #include "kswv_kernels.cuh"
 #include "bsw_types.h"
+#include <algorithm>
 #include <cstring>
+#include <numeric>
 #include <vector>
 
 using namespace kswvk;
 
 namespace {
+struct Scratch {
+    std::vector<uint32_t> rowkey, lutw;
+    std::vector<uint2> bnd;
+    std::vector<uint8_t> qbuf;
+    // exactly what the kernel gets per group, poisoned so that a read of something nobody stored shows up
+    void reset(const Task &T) {
+        rowkey.assign((size_t)T.tlen + 8, 0xDEADBEEFu);
+        lutw.assign((size_t)T.tlen + 8, 0xDEADBEEFu);
+        bnd.assign((size_t)T.tlen + 8, uint2{0xDEADBEEFu, 0xDEADBEEFu});
+        qbuf.assign((size_t)T.qlen + 64, (uint8_t)0xEE);
+    }
+};
+
 template <int W>
 int run_batch(const KParams &K, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer, int64_t n, int32_t *aln) {
     constexpr int G = 32 / W;
     int rc = 0;
+    std::vector<Task> tasks((size_t)n);
+    std::vector<Result> out((size_t)n);
+    std::vector<uint32_t> key((size_t)n), order((size_t)n);
+    for (int64_t i = 0; i < n; ++i)
+        tasks[(size_t)i] = Task{(uint32_t)pairs[i].idr, (uint32_t)pairs[i].idq, pairs[i].len1, pairs[i].len2, pairs[i].h0, (int32_t)i};
+    for (int phase = 0; phase < 2; ++phase) {
+        int64_t ntask = n;
+        if (phase == 1) {
+            std::iota(order.begin(), order.end(), 0u);
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
+            ntask = 0;
+            while (ntask < n && key[order[(size_t)ntask]] != 0u) ++ntask;
+        }
 #pragma omp parallel
-    {
-        wf::Warp warp;
-        std::vector<uint32_t> rowkey[G], lutw[G];
-        std::vector<uint2> bnd[G];
-        std::vector<uint8_t> qbuf[G];
+        {
+            wf::Warp warp;
+            Scratch sc[G];
 #pragma omp for schedule(dynamic, 4)
-        for (int64_t i0 = 0; i0 < n; i0 += G) {
-            Task T[G];
-            for (int g = 0; g < G; ++g) {
-                if (i0 + g < n) {
-                    const bsw_seqpair &sp = pairs[i0 + g];
-                    T[g] = Task{(uint32_t)sp.idr, (uint32_t)sp.idq, sp.len1, sp.len2, sp.h0, (int32_t)(i0 + g)};
-                } else T[g] = Task{0u, 0u, 0, 0, 0, -1};
-                // exactly what the kernel gets per group, poisoned so that a read of something nobody stored shows up
-                rowkey[g].assign((size_t)T[g].tlen + 8, 0xDEADBEEFu);
-                lutw[g].assign((size_t)T[g].tlen + 8, 0xDEADBEEFu);
-                bnd[g].assign((size_t)T[g].tlen + 8, uint2{0xDEADBEEFu, 0xDEADBEEFu});
-                qbuf[g].assign((size_t)T[g].qlen + 64, (uint8_t)0xEE);
-            }
-            Result res[32];
-            wf::run_warp(warp, [&]() {
-                const int g = hw_lane() / W;
-                const Result r = kswv_pair<W>(K, T[g], ref, qer, rowkey[g].data(), bnd[g].data(), lutw[g].data(), qbuf[g].data());
-                res[hw_lane()] = r;
-            });
-            for (int g = 0; g < G; ++g) {
-                for (int l = 1; l < W; ++l)
-                    if (memcmp(&res[g * W + l], &res[g * W], sizeof(Result)) != 0) rc = -2 - l;   // lanes of a group must agree
-                if (T[g].out >= 0) memcpy(aln + 7 * (int64_t)pairs[i0 + g].regid, &res[g * W], sizeof(Result));
+            for (int64_t j0 = 0; j0 < ntask; j0 += G) {
+                int idx[G];
+                for (int g = 0; g < G; ++g) {
+                    idx[g] = j0 + g < ntask ? (int)(phase ? order[(size_t)(j0 + g)] : (uint32_t)(j0 + g)) : -1;
+                    if (idx[g] >= 0) sc[g].reset(tasks[(size_t)idx[g]]);
+                }
+                Result res[32];
+                uint32_t keys[32];
+                wf::run_warp(warp, [&]() {
+                    const int g = hw_lane() / W;
+                    if (idx[g] < 0) return;
+                    const Task &T = tasks[(size_t)idx[g]];
+                    if (phase == 0) {
+                        res[hw_lane()] = kswv_phase0<W>(K, T, ref, qer, sc[g].rowkey.data(), sc[g].bnd.data(), sc[g].lutw.data(),
+                                                        &keys[hw_lane()]);
+                    } else {
+                        Result r = out[(size_t)T.out];
+                        kswv_phase1<W>(K, T, ref, qer, sc[g].rowkey.data(), sc[g].bnd.data(), sc[g].lutw.data(), sc[g].qbuf.data(), &r);
+                        res[hw_lane()] = r;
+                    }
+                });
+                for (int g = 0; g < G; ++g) {
+                    if (idx[g] < 0) continue;
+                    for (int l = 1; l < W; ++l)                                                   // lanes of a group must agree
+                        if (memcmp(&res[g * W + l], &res[g * W], sizeof(Result)) != 0 || (phase == 0 && keys[g * W + l] != keys[g * W]))
+                            rc = -2 - l;
+                    out[(size_t)idx[g]] = res[g * W];
+                    if (phase == 0) key[(size_t)idx[g]] = keys[g * W];
+                }
             }
         }
     }
+    for (int64_t i = 0; i < n; ++i) memcpy(aln + 7 * (int64_t)pairs[i].regid, &out[(size_t)i], sizeof(Result));
     return rc;
 }
 }  // namespace
