@@ -182,32 +182,39 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
         int hdiag = 0;
         uint32_t out_he = 0, out_key = 0;
         const int steps = tlen + nl - 1;
+        uint32_t nxt4[4] = {0u, 0u, 0u, 0u}, out_lut = 0;
+        if (k == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nxt4[u] = lutw[u > tlen ? tlen : u];
+        }
         int s4 = 0;
         // four steps per stop test: a pair that has reached thr keeps going for at most three rows, which the
         // scan after the loop drops again
         for (; s4 < steps; s4 += 4) {
             if (G::any(dead)) break;
-            // the four rows' LUT words up front (clamped into the scratch, which has slack past tlen): four loads in
-            // flight instead of one L2 round trip at the head of every step
+            // Lane 0 reads the rows' LUT words, one block of four steps ahead of their use; every other lane gets its
+            // row's word from its left neighbour, which worked on that row one step earlier.
             uint32_t lut4[4];
-            {
-                const int i0 = s4 - k;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) lut4[u] = nxt4[u];
+            if (k == 0) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    int iu = i0 + u;
-                    iu = iu < 0 ? 0 : (iu > tlen ? tlen : iu);
-                    lut4[u] = lutw[iu];
+                    const int iu = s4 + 4 + u;
+                    nxt4[u] = lutw[iu > tlen ? tlen : iu];      // the scratch has slack past tlen
                 }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int s = s4 + u;
                 uint32_t in_he = G::up1(out_he) & not0, in_key = G::up1(out_key) & not0;
+                const uint32_t in_lut = G::up1(out_lut);
                 const int i = s - k;
                 const bool active = (unsigned)i < (unsigned)my_rows;
                 if (MP && p > 0 && k == 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
                 if (active) {
-                    const uint32_t lut_lo = lut4[u];
+                    const uint32_t lut_lo = k == 0 ? lut4[u] : in_lut;
+                    out_lut = lut_lo;
                     const int hl = (int)(in_he & 0xFFFFu);
                     int e = (int)(in_he >> 16);
                     int key = 0;
