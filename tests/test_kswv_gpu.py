@@ -113,3 +113,21 @@ def test_domain_errors(dev):
     assert e.value.code == 1                                                   # BSW_ERR_ARG
     want, _ = okswv.oracle_batch(pairs, ref, qer)
     assert_same_aln(dev.align(pairs, ref, qer), want, pairs, "after rejected calls")
+
+
+def test_chunks_over_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from genarchbench_b200 import kswv
+    pairs, ref, qer = okswv.make_workload(70000, seed=36, read_len=(20, 60), window=(1.0, 3.0), min_seed_len=5)
+    want, _ = okswv.oracle_batch(pairs, ref, qer)
+    g = kswv.Kswv(n_gpus=2)
+    try:
+        assert_same_aln(g.align(pairs, ref, qer), want, pairs, "two GPUs")
+        st = g.stats()
+        assert st["n_gpus"] == 2 and st["chunks"] >= 2
+        small = pairs[:5].copy()
+        assert_same_aln(g.align(small, ref, qer), want[:5], small, "five pairs on a two-GPU handle")
+    finally:
+        g.close()
