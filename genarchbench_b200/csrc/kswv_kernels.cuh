@@ -182,7 +182,7 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
         int hdiag = 0;
         uint32_t out_he = 0, out_key = 0;
         const int steps = tlen + nl - 1;
-        uint32_t nxt4[4] = {0u, 0u, 0u, 0u}, out_lut = 0;
+        uint32_t nxt4[4] = {0u, 0u, 0u, 0u}, out_lut = 0x80808080u;     // four scores of -128: nothing rises from 0
         if (k == 0) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) nxt4[u] = lutw[u > tlen ? tlen : u];
@@ -212,7 +212,11 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
                 const int i = s - k;
                 const bool active = (unsigned)i < (unsigned)my_rows;
                 if (MP && p > 0 && k == 0 && active) { const uint2 bv = bnd[i]; in_he = bv.x; in_key = bv.y; }
-                if (active) {
+                // No branch around the cells: a lane computes every step, so the four steps are one straight line of
+                // code (no register shuffling at block boundaries). Before its first row a lane sees all-negative
+                // scores and zero inputs, which keeps its H, E and F at 0; past its last row it computes values that
+                // only ever flow to lanes that are past their last row too.
+                {
                     const uint32_t lut_lo = k == 0 ? lut4[u] : in_lut;
                     out_lut = lut_lo;
                     const int hl = (int)(in_he & 0xFFFFu);
@@ -239,9 +243,9 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
                     out_he = (uint32_t)H[C - 1] | ((uint32_t)e << 16);
                     key = max(key + kbase, (int)in_key);
                     out_key = (uint32_t)key;
-                    if (keeper) rowkey[i] = (uint32_t)key;
-                    dead |= keeper && (key >> 16) >= thr;   // gmax >= thr first holds on the first row that reaches thr
-                    if (MP && feeder) bnd[i] = make_uint2(out_he, out_key);
+                    if (keeper && active) rowkey[i] = (uint32_t)key;
+                    dead |= keeper && active && (key >> 16) >= thr;   // gmax >= thr first holds on the first row that reaches thr
+                    if (MP && feeder && active) bnd[i] = make_uint2(out_he, out_key);
                 }
             }
         }
