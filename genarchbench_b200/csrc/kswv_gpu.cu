@@ -1,5 +1,5 @@
 // kswv_gpu.cu -- host side of the kswv path (include/kswv_gpu.h): chunks of pairs flow through a ring of three
-// slots per GPU (tasks + sequences H2D, one persistent-warp kernel, results D2H), the host orders each chunk's
+// slots per GPU (tasks + sequences H2D, the two kernels, results D2H, each on its own stream), the host orders each chunk's
 // tasks by decreasing DP size and scatters finished results to aln[regid]. Kernels: kswv_kernels.cuh.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -37,7 +37,7 @@ struct KSlot {
     void *d_sort = nullptr;
     size_t cap_sort = 0;
     size_t cap_pairs = 0, cap_ref = 0, cap_qer = 0, cap_seq = 0;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr, ev_in = nullptr, ev_k = nullptr;
     bool busy = false;
     int64_t first = 0, count = 0;               // the chunk in flight: pairs [first, first + count)
 };
@@ -45,7 +45,7 @@ struct KSlot {
 struct KDev {
     int id = 0, sms = 0, warps = 0, groups = 0;
     int occ[3] = {0, 0, 0};                      // resident blocks per SM of the 8-, 16- and 32-lane kernels
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;   // kernels; H2D; D2H (copies overlap the kernels)
     KSlot slot[kRing];
     uint32_t *d_rowmx = nullptr;
     uint2 *d_bnd = nullptr;
@@ -108,10 +108,14 @@ int ensure_dev(kswv_handle *h, KDev &d) {
     if (d.st) return BSW_OK;
     KCU(cudaSetDevice(d.id));
     KCU(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
+    KCU(cudaStreamCreateWithFlags(&d.st_in, cudaStreamNonBlocking));
+    KCU(cudaStreamCreateWithFlags(&d.st_out, cudaStreamNonBlocking));
     for (KSlot &s : d.slot) {
         KCU(cudaEventCreate(&s.ev_start));
         KCU(cudaEventCreate(&s.ev_stop));
         KCU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        KCU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        KCU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
         KCU(cudaMalloc((void **)&s.d_counter, 4 * sizeof(int)));
     }
     KCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.occ[0], kswv_phase0_kernel<8>, kKswvWarps * 32, 0));
@@ -173,12 +177,16 @@ void free_dev(KDev &d) {
         if (s.ev_start) cudaEventDestroy(s.ev_start);
         if (s.ev_stop) cudaEventDestroy(s.ev_stop);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.ev_in) cudaEventDestroy(s.ev_in);
+        if (s.ev_k) cudaEventDestroy(s.ev_k);
     }
     if (d.d_rowmx) cudaFree(d.d_rowmx);
     if (d.d_bnd) cudaFree(d.d_bnd);
     if (d.d_lutw) cudaFree(d.d_lutw);
     if (d.d_qbuf) cudaFree(d.d_qbuf);
     if (d.st) cudaStreamDestroy(d.st);
+    if (d.st_in) cudaStreamDestroy(d.st_in);
+    if (d.st_out) cudaStreamDestroy(d.st_out);
 }
 
 // waits for the slot's chunk, scatters its results to aln[regid], adds its kernel time
@@ -263,7 +271,9 @@ int kswv_gpu_batch(kswv_handle *h, const bsw_seqpair *pairs, const uint8_t *ref,
         for (KDev &d : h->devs) {
             if (!d.st) continue;
             cudaSetDevice(d.id);
+            cudaStreamSynchronize(d.st_in);
             cudaStreamSynchronize(d.st);
+            cudaStreamSynchronize(d.st_out);
             for (KSlot &s : d.slot) s.busy = false;
         }
     return rc;
@@ -276,6 +286,10 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
     kswv_gpu_stats &S = h->stats;
     S.chunks = 0; S.pairs = n; S.pairs8 = 0; S.cells = 0; S.h2d_bytes = 0; S.d2h_bytes = 0; S.kernel_launches = 0;
     S.gathered = 0; S.kernel_ms = 0; S.wall_ms = 0; S.lanes_per_pair = 0;
+    S.host_check_ms = 0; S.host_prep_ms = 0; S.host_wait_ms = 0;
+    auto ms_since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    };
     h->err[0] = 0;
     if (n == 0) return BSW_OK;
 
@@ -309,6 +323,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         return bad_kind == 2 ? BSW_ERR_ARG : BSW_ERR_RANGE;
     }
     S.pairs8 = n8; S.cells = cells;
+    S.host_check_ms = ms_since(t0);
 
     // ---- per-device scratch: one row-maximum column (and one boundary column for queries above 256 columns) per warp
     for (KDev &d : h->devs) {
@@ -359,8 +374,13 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         KCU(cudaSetDevice(d.id));
         KSlot &s = d.slot[d.next];
         d.next = (d.next + 1) % kRing;
-        rc = drain_slot(h, d, s, pairs, aln);
+        {
+            const auto tw = std::chrono::steady_clock::now();
+            rc = drain_slot(h, d, s, pairs, aln);
+            S.host_wait_ms += ms_since(tw);
+        }
         if (rc) break;
+        const auto tp = std::chrono::steady_clock::now();
         const size_t ref_bytes = dense ? (size_t)(rhi - rlo) : (size_t)rsum;
         const size_t qer_bytes = dense ? (size_t)(qhi - qlo) : (size_t)qsum;
         rc = ensure_slot(h, s, (size_t)cnt, ref_bytes, qer_bytes, dense ? 0 : (size_t)(rsum + qsum) + 64);
@@ -417,15 +437,18 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             }
             ++S.gathered;
         }
+        S.host_prep_ms += ms_since(tp);
         // ---- enqueue
-        KCU(cudaMemcpyAsync(s.d_tasks, s.h_tasks, sizeof(Task) * (size_t)cnt, cudaMemcpyHostToDevice, d.st));
+        KCU(cudaMemcpyAsync(s.d_tasks, s.h_tasks, sizeof(Task) * (size_t)cnt, cudaMemcpyHostToDevice, d.st_in));
         if (dense) {
-            if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, ref + rlo, ref_bytes, cudaMemcpyHostToDevice, d.st));
-            if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, qer + qlo, qer_bytes, cudaMemcpyHostToDevice, d.st));
+            if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, ref + rlo, ref_bytes, cudaMemcpyHostToDevice, d.st_in));
+            if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, qer + qlo, qer_bytes, cudaMemcpyHostToDevice, d.st_in));
         } else {
-            if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, s.h_seq, ref_bytes, cudaMemcpyHostToDevice, d.st));
-            if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, s.h_seq + rsum, qer_bytes, cudaMemcpyHostToDevice, d.st));
+            if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, s.h_seq, ref_bytes, cudaMemcpyHostToDevice, d.st_in));
+            if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, s.h_seq + rsum, qer_bytes, cudaMemcpyHostToDevice, d.st_in));
         }
+        KCU(cudaEventRecord(s.ev_in, d.st_in));
+        KCU(cudaStreamWaitEvent(d.st, s.ev_in, 0));
         KCU(cudaMemsetAsync(s.d_counter, 0, 4 * sizeof(int), d.st));
         KCU(cudaEventRecord(s.ev_start, d.st));
         // lanes per pair for the plain pairs: 8 up to 160 padded columns (strips of up to 20), 16 up to 256, else 32
@@ -462,8 +485,10 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         KCU(run_class(32, n_plain, cnt - n_plain, s.d_counter + 2));
         S.lanes_per_pair = width;
         KCU(cudaEventRecord(s.ev_stop, d.st));
-        KCU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(Result) * (size_t)cnt, cudaMemcpyDeviceToHost, d.st));
-        KCU(cudaEventRecord(s.ev_done, d.st));
+        KCU(cudaEventRecord(s.ev_k, d.st));
+        KCU(cudaStreamWaitEvent(d.st_out, s.ev_k, 0));
+        KCU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(Result) * (size_t)cnt, cudaMemcpyDeviceToHost, d.st_out));
+        KCU(cudaEventRecord(s.ev_done, d.st_out));
         s.busy = true; s.first = first; s.count = cnt;
         S.h2d_bytes += (int64_t)(sizeof(Task) * (size_t)cnt + ref_bytes + qer_bytes);
         S.d2h_bytes += (int64_t)(sizeof(Result) * (size_t)cnt);
@@ -471,12 +496,14 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         first += cnt;
     }
     // ---- drain, oldest first on every device
+    const auto tw = std::chrono::steady_clock::now();
     for (KDev &d : h->devs)
         for (int j = 0; j < kRing; ++j) {
             KSlot &s = d.slot[(d.next + j) % kRing];
             const int rc2 = drain_slot(h, d, s, pairs, aln);
             if (rc == BSW_OK) rc = rc2;
         }
+    S.host_wait_ms += ms_since(tw);
     S.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;
 }

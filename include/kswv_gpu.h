@@ -55,6 +55,9 @@ typedef struct kswv_gpu_stats {
     int64_t gathered;           /* last batch: chunks whose sequences were gathered on the host (not one dense range) */
     double kernel_ms;           /* last batch: sum over chunks of the kernel's event time (max over GPUs per chunk wave) */
     double wall_ms;             /* last batch: the call, host clock */
+    double host_check_ms;       /* last batch: validation pass over the records */
+    double host_prep_ms;        /* last batch: task ordering + task records (+ gather), summed over chunks */
+    double host_wait_ms;        /* last batch: blocked on a slot's results (includes the scatter to aln) */
 } kswv_gpu_stats;
 
 /* Scoring is fixed per handle, as in the reference's constructor. n_gpus <= 0: all visible devices.

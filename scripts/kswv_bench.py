@@ -105,7 +105,8 @@ if __name__ == "__main__":
                                "match 1 / mismatch 4 / gap 6+1, xtra = SUBO|START|BYTE|19",
                    "pairs": n, "l2": "inputs larger than L2 (sequences %.0f MB per step)" % ((rb + qb) * reps / 1e6)},
         "run": {"cells_forward_per_step": int(cells), "cells_computed_per_step": int(computed), "chunks": st["chunks"],
-                "lanes_per_pair": st["lanes_per_pair"], "pairs_8bit_class": st["pairs8"]},
+                "lanes_per_pair": st["lanes_per_pair"], "pairs_8bit_class": st["pairs8"],
+                "host_ms_last_step": {k: round(st[k], 3) for k in ("host_check_ms", "host_prep_ms", "host_wait_ms", "wall_ms")}},
         "e2e": {"value": cells / wall_s / 1e9, "unit": "GCUPS", "ms_per_step": wall_s * 1e3,
                 "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
                 "api": "kswv_gpu_batch from page-locked host buffers (ranges DMA'd in place), results scattered to aln[regid]"},
