@@ -347,25 +347,35 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
     // ---- chunks
     int rc = BSW_OK;
     size_t dev_rr = 0;
-    std::vector<uint32_t> order, bucket_start;
+    std::vector<uint32_t> order, bucket_start, bkt;
     for (int64_t first = 0; first < n && rc == BSW_OK;) {
         // cut: at most kChunkPairs pairs / kChunkBytes sequence bytes; small batches are split across the GPUs
         int64_t target = kChunkPairs;
         const int64_t per_gpu = (n + (int64_t)h->devs.size() - 1) / (int64_t)h->devs.size();
         if (per_gpu < target) target = std::max<int64_t>(per_gpu, 1);
-        int64_t cnt = 0, bytes = 0;
-        int64_t rlo = INT64_MAX, rhi = 0, qlo = INT64_MAX, qhi = 0, rsum = 0, qsum = 0;
-        bool ordered = true;
-        while (first + cnt < n && cnt < target) {
-            const bsw_seqpair &sp = pairs[first + cnt];
-            if (cnt > 0 && bytes + sp.len1 + sp.len2 > kChunkBytes) break;
-            if (sp.idr < rhi || sp.idq < qhi) ordered = false;
-            rlo = std::min<int64_t>(rlo, sp.idr); rhi = std::max<int64_t>(rhi, sp.idr + sp.len1);
-            qlo = std::min<int64_t>(qlo, sp.idq); qhi = std::max<int64_t>(qhi, sp.idq + sp.len2);
-            rsum += sp.len1; qsum += sp.len2;
-            bytes += sp.len1 + sp.len2;
-            ++cnt;
+        int64_t cnt = std::min<int64_t>(target, n - first);
+        int64_t rlo, rhi, qlo, qhi, rsum, qsum;
+        bool ordered;
+        const auto tc = std::chrono::steady_clock::now();
+        for (;;) {      // extents of the chunk by a parallel reduction; halve it while its sequences exceed kChunkBytes
+            int64_t a_rlo = INT64_MAX, a_rhi = 0, a_qlo = INT64_MAX, a_qhi = 0, a_rsum = 0, a_qsum = 0;
+            int unordered = 0;
+            const bsw_seqpair *cp0 = pairs + first;
+#pragma omp parallel for schedule(static) reduction(min : a_rlo, a_qlo) reduction(max : a_rhi, a_qhi) \
+    reduction(+ : a_rsum, a_qsum) reduction(| : unordered) if (cnt > 4096)
+            for (int64_t i = 0; i < cnt; ++i) {
+                const bsw_seqpair &sp = cp0[i];
+                a_rlo = std::min<int64_t>(a_rlo, sp.idr); a_rhi = std::max<int64_t>(a_rhi, sp.idr + sp.len1);
+                a_qlo = std::min<int64_t>(a_qlo, sp.idq); a_qhi = std::max<int64_t>(a_qhi, sp.idq + sp.len2);
+                a_rsum += sp.len1; a_qsum += sp.len2;
+                // in order: every pair starts at or after the end of the one before it, in both buffers
+                if (i > 0 && (sp.idr < cp0[i - 1].idr + cp0[i - 1].len1 || sp.idq < cp0[i - 1].idq + cp0[i - 1].len2)) unordered = 1;
+            }
+            rlo = a_rlo; rhi = a_rhi; qlo = a_qlo; qhi = a_qhi; rsum = a_rsum; qsum = a_qsum; ordered = !unordered;
+            if (rsum + qsum <= kChunkBytes || cnt == 1) break;
+            cnt = (cnt + 1) / 2;
         }
+        S.host_prep_ms += ms_since(tc);
         // one dense range per buffer (the production layout: mem_matesw_batch_pre appends, bwamem_pair.cpp:1006-1013)?
         const bool dense = ordered && (rhi - rlo) <= rsum + rsum / 8 + 4096 && (qhi - qlo) <= qsum + qsum / 8 + 4096 &&
                            (rhi - rlo) < (1ll << 32) && (qhi - qlo) < (1ll << 32);
@@ -405,13 +415,19 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
                 if (plain) { *plain = !special; *cols = nc; }
                 return ((special ? 1 : 0) * kColBins + (kColBins - 1 - cb)) * kLenBins + (kLenBins - 1 - (cp[i].len1 >> 3));
             };
-            for (int64_t i = 0; i < cnt; ++i) {
+            bkt.resize((size_t)cnt);
+            int64_t np = 0;
+            int pc = 0;
+#pragma omp parallel for schedule(static) reduction(+ : np) reduction(max : pc) if (cnt > 4096)
+            for (int64_t i = 0; i < cnt; ++i) {      // the only pass over the 72-byte records; the rest works on 4-byte keys
                 bool plain; int cols;
-                ++bucket_start[(size_t)bucket_of(i, &plain, &cols) + 1];
-                if (plain) { ++n_plain; plain_cols = std::max(plain_cols, cols); }
+                bkt[(size_t)i] = (uint32_t)bucket_of(i, &plain, &cols);
+                if (plain) { ++np; pc = std::max(pc, cols); }
             }
+            n_plain = np; plain_cols = pc;
+            for (int64_t i = 0; i < cnt; ++i) ++bucket_start[(size_t)bkt[(size_t)i] + 1];
             for (int b = 0; b < kBuckets; ++b) bucket_start[(size_t)b + 1] += bucket_start[(size_t)b];
-            for (int64_t i = 0; i < cnt; ++i) order[bucket_start[(size_t)bucket_of(i, nullptr, nullptr)]++] = (uint32_t)i;
+            for (int64_t i = 0; i < cnt; ++i) order[bucket_start[(size_t)bkt[(size_t)i]]++] = (uint32_t)i;
         }
         if (dense) {
 #pragma omp parallel for schedule(static) if (cnt > 4096)
