@@ -95,3 +95,24 @@ def test_groups_with_empty_and_unequal_pairs(emul):
     want, _ = kswv.oracle_batch(pairs, ref, qer)
     for width in (8, 16):
         assert_same_aln(emul(pairs, ref, qer, width=width), want, pairs, f"W={width}")
+
+
+def test_emulated_device_code_is_clean_under_asan(tmp_path):
+    """Out-of-bounds check of the kswv device code at all three lane-group widths (the GPU pool has no
+    compute-sanitizer): an AddressSanitizer build of the emulation library, scratch and sequence buffers at exactly
+    the sizes the kernels get."""
+    import sys
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    asan = subprocess.run([cxx, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not asan or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    d = os.path.join(ROOT, "tests", "host_emul")
+    so = str(tmp_path / "libkswv_emul_asan.so")
+    subprocess.run([cxx, "-O1", "-g", "-std=c++17", "-fPIC", "-fopenmp", "-shared", "-w", "-fsanitize=address",
+                    "-fno-omit-frame-pointer", f"-I{d}", f"-I{ROOT}/genarchbench_b200/csrc", f"-I{ROOT}/include",
+                    "-o", so, os.path.join(d, "kswv_emul_lib.cpp")], check=True)
+    # the fibers switch stacks behind ASan's back: its stack-use-after-return machinery is off, heap checks stay on
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0", OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(d, "kswv_asan_check.py"), so], capture_output=True, text=True,
+                       env=env, timeout=900)
+    assert r.returncode == 0 and "ERROR: AddressSanitizer" not in r.stderr, (r.stdout[-500:], r.stderr[-2000:])

@@ -131,3 +131,25 @@ def test_chunks_over_two_gpus():
         assert_same_aln(g.align(small, ref, qer), want[:5], small, "five pairs on a two-GPU handle")
     finally:
         g.close()
+
+
+def test_random_call_sequences_on_one_handle(dev):
+    """Twenty calls of random size (0 .. 70k pairs), order (dense / shuffled), read lengths and flags on one handle:
+    slots, scratch and the phase-1 ordering buffers grow and are reused; every call against the oracle."""
+    rng = np.random.default_rng(77)
+    lens = [(1, 24), (20, 60), (100, 151), (200, 300), (257, 500)]
+    for call in range(20):
+        lo, hi = lens[int(rng.integers(0, len(lens)))]
+        big = hi <= 60
+        n = int(rng.choice([0, 1, 2, 33, 500, 3000] + ([40000, 70000] if big else [])))
+        if n == 0:
+            pairs, ref, qer = okswv.make_workload(1, seed=call)
+            assert dev.align(pairs[:0].copy(), ref, qer).shape == (0, 7)
+            continue
+        flags = [None, 0, KSW_XSTART, KSW_XSUBO | 25, lambda l: KSW_XSTOP | KSW_XSTART | (KSW_XBYTE if l < 200 else 0) | 30]
+        pairs, ref, qer = okswv.make_workload(n, seed=100 + call, read_len=(lo, hi), window=(0.5, 3.0), min_seed_len=3,
+                                              xtra=flags[int(rng.integers(0, len(flags)))])
+        want, _ = okswv.oracle_batch(pairs, ref, qer)
+        if rng.random() < 0.5:
+            pairs = pairs[rng.permutation(n)].copy()
+        assert_same_aln(dev.align(pairs, ref, qer), want, None, f"call {call}: n={n} reads {lo}-{hi}")
