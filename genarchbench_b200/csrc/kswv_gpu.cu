@@ -330,7 +330,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         int rc = ensure_dev(h, d);
         if (rc) return rc;
         KCU(cudaSetDevice(d.id));
-        const size_t rows = (size_t)maxT + 8;
+        const size_t rows = (size_t)((maxT + kScratchSlack + 3) & ~3);     // a multiple of 4 words: every group's scratch is 16-byte aligned
         rc = grow_dev(h, d.d_rowmx, d.cap_rows, rows * (size_t)d.groups);
         if (rc) return rc;
         if (maxCols > kPassCols) {
@@ -342,7 +342,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         rc = grow_dev(h, d.d_qbuf, d.cap_qbuf, (size_t)(maxQ + 64) * (size_t)d.groups);
         if (rc) return rc;
     }
-    const int scratch_rows = maxT + 8, scratch_q = maxQ + 64;
+    const int scratch_rows = (maxT + kScratchSlack + 3) & ~3, scratch_q = maxQ + 64;
 
     // ---- chunks
     int rc = BSW_OK;

@@ -38,6 +38,7 @@ namespace kswvk {
 constexpr int kXByte = 0x10000, kXStop = 0x20000, kXSubo = 0x40000, kXStart = 0x80000;   // ksw.h:31-34
 constexpr int kPassCols = 256;      // columns one pass of a warp covers (32 lanes x 8)
 constexpr int kNoStop = 0x7FFFFFFF;
+constexpr int kScratchSlack = 48;   // words of per-group scratch past the longest reference (LUT words are read ahead)
 
 struct KParams {
     int32_t a, b, amb;                        // match, mismatch (negative), ambiguous (-1, kswv.cpp:131)
@@ -183,9 +184,10 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
         uint32_t out_he = 0, out_key = 0;
         const int steps = tlen + nl - 1;
         uint32_t nxt4[4] = {0u, 0u, 0u, 0u}, out_lut = 0x80808080u;     // four scores of -128: nothing rises from 0
+        // (16-byte loads: the scratch of a group starts on a 16-byte boundary and has kScratchSlack words past tlen)
         if (k == 0) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) nxt4[u] = lutw[u > tlen ? tlen : u];
+            const uint4 v = *reinterpret_cast<const uint4 *>(lutw);
+            nxt4[0] = v.x; nxt4[1] = v.y; nxt4[2] = v.z; nxt4[3] = v.w;
         }
         int s4 = 0;
         // four steps per stop test: a pair that has reached thr keeps going for at most three rows, which the
@@ -198,12 +200,10 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
 #pragma unroll
             for (int u = 0; u < 4; ++u) lut4[u] = nxt4[u];
             if (k == 0) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int iu = s4 + 4 + u;
-                    nxt4[u] = lutw[iu > tlen ? tlen : iu];      // the scratch has slack past tlen
-                }
+                const uint4 v = *reinterpret_cast<const uint4 *>(lutw + s4 + 4);
+                nxt4[0] = v.x; nxt4[1] = v.y; nxt4[2] = v.z; nxt4[3] = v.w;
             }
+            uint32_t key4[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int s = s4 + u;
@@ -243,10 +243,20 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
                     out_he = (uint32_t)H[C - 1] | ((uint32_t)e << 16);
                     key = max(key + kbase, (int)in_key);
                     out_key = (uint32_t)key;
-                    if (keeper && active) rowkey[i] = (uint32_t)key;
-                    dead |= keeper && active && (key >> 16) >= thr;   // gmax >= thr first holds on the first row that reaches thr
+                    key4[u] = active ? (uint32_t)key : 0u;
                     if (MP && feeder && active) bnd[i] = make_uint2(out_he, out_key);
                 }
+            }
+            // the keeper's four finished rows: one address, up to four stores, one stop test (gmax >= thr first holds
+            // on the first row that reaches thr; rows at or past tlen carry key 0)
+            if (keeper) {
+                const int i0 = s4 - k;
+                uint32_t *rk = rowkey + i0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if ((unsigned)(i0 + u) < (unsigned)tlen) rk[u] = key4[u];
+                const uint32_t m4 = max(max(key4[0], key4[1]), max(key4[2], key4[3]));
+                dead |= i0 + 3 >= 0 && i0 < tlen && (int)(m4 >> 16) >= thr;   // only rows that exist can stop the pair
             }
         }
         if (MP && !lastpass) G::sync();     // the next pass's lane 0 reads what this pass's last lane wrote
@@ -260,7 +270,11 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
     G::sync();                              // rowkey: one lane wrote, all lanes read
     // the stop row: the first row whose maximum reaches thr (Block II's exit, kswv.cpp:535-548); rows past it
     // were computed by the lanes that were ahead of the keeper and do not exist for the reference
-    {
+    // (no H can exceed min(tlen, qlen) * match: a threshold above that is never reached and the scan is skipped --
+    // phase 0 of every pair whose only threshold is the 8-bit ceiling)
+    uint32_t best = 0;
+    dead = false;
+    if (thr <= (tlen < qlen ? tlen : qlen) * K.a) {
         uint32_t first = 0;
         for (int base = 0; base < rows; base += W) {
             const int i = base + k;
@@ -268,19 +282,24 @@ __device__ __noinline__ Best kswv_dp(const KParams &K, const uint32_t *__restric
         }
         first = G::maxu(first);
         dead = first != 0u;
-        if (dead) rows = 0xFFFF - (int)first + 1;
+        if (dead) {
+            // every earlier row stayed below thr, so the stop row holds gmax and is its first row
+            rows = 0xFFFF - (int)first + 1;
+            best = (rowkey[rows - 1] & 0xFFFF0000u) | first;
+        }
     }
     // Block II (kswv.cpp:526-548): gmax is the largest row maximum up to the stop row, te its FIRST row, qe that
     // row's first column
-    uint32_t best = 0;
-    for (int base = 0; base < rows; base += W) {
-        const int i = base + k;
-        if (i < rows) {
-            const uint32_t cand = (rowkey[i] & 0xFFFF0000u) | (uint32_t)(0xFFFF - i);
-            best = cand > best ? cand : best;
+    if (!dead) {
+        for (int base = 0; base < rows; base += W) {
+            const int i = base + k;
+            if (i < rows) {
+                const uint32_t cand = (rowkey[i] & 0xFFFF0000u) | (uint32_t)(0xFFFF - i);
+                best = cand > best ? cand : best;
+            }
         }
+        best = G::maxu(best);
     }
-    best = G::maxu(best);
     Best B;
     B.gmax = (int)(best >> 16); B.rows = rows; B.dead = dead;
     B.te = -1; B.qe = 0;

@@ -21,8 +21,8 @@ struct Scratch {
     std::vector<uint8_t> qbuf;
     // exactly what the kernel gets per group, poisoned so that a read of something nobody stored shows up
     void reset(const Task &T) {
-        rowkey.assign((size_t)T.tlen + 8, 0xDEADBEEFu);
-        lutw.assign((size_t)T.tlen + 8, 0xDEADBEEFu);
+        rowkey.assign((size_t)T.tlen + kScratchSlack, 0xDEADBEEFu);
+        lutw.assign((size_t)T.tlen + kScratchSlack, 0xDEADBEEFu);
         bnd.assign((size_t)T.tlen + 8, uint2{0xDEADBEEFu, 0xDEADBEEFu});
         qbuf.assign((size_t)T.qlen + 64, (uint8_t)0xEE);
     }

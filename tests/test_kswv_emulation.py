@@ -49,6 +49,7 @@ CASES = [
     ("several passes, 8-bit class", None, dict(n=60, read_len=(257, 600), p_sub=0.3,
                                               xtra=lambda l: KSW_XSUBO | KSW_XSTART | KSW_XBYTE | 19)),
     ("stop + start", None, dict(n=200, xtra=lambda l: KSW_XSTOP | KSW_XSTART | (KSW_XBYTE if l < 120 else 0) | 45)),
+    ("stop at zero: the first row ends the pair", None, dict(n=150, read_len=(1, 300), window=(0.3, 3.0), xtra=lambda l: KSW_XSTOP | KSW_XSTART)),
     ("asymmetric gaps, a=2", dict(match=2, mismatch=5, o_del=4, e_del=2, o_ins=7, e_ins=1),
      dict(n=200, match=2, read_len=(60, 180), p_indel=0.03)),
 ]

@@ -46,6 +46,7 @@ CASES = [
                               xtra=lambda l: KSW_XSUBO | KSW_XSTART | KSW_XBYTE | 19)),
     ("stop + start", dict(n=2000, xtra=lambda l: KSW_XSTOP | KSW_XSTART | (KSW_XBYTE if l < 120 else 0) | 45)),
     ("no flags", dict(n=1000, xtra=0)),
+    ("stop at zero: the first row ends the pair", dict(n=2000, read_len=(1, 300), window=(0.3, 3.0), xtra=lambda l: KSW_XSTOP | KSW_XSTART)),
     ("ambiguous bases", dict(n=2000, p_n=0.2)),
     ("long windows", dict(n=300, read_len=(100, 151), window=(20.0, 60.0))),
 ]

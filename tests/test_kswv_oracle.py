@@ -46,6 +46,8 @@ CASES = [
     ("stop, 8-bit", None, dict(xtra=KSW_XSTOP | KSW_XBYTE | 40)),
     ("stop + start, 16-bit", None, dict(xtra=KSW_XSTOP | KSW_XSTART | 60)),
     ("ambiguous bases", None, dict(p_n=0.2)),
+    ("stop at zero, 16-bit", None, dict(read_len=(1, 200), window=(0.3, 3.0), xtra=KSW_XSTOP | KSW_XSTART)),
+    ("stop at zero, 8-bit", None, dict(read_len=(1, 200), window=(0.3, 3.0), xtra=KSW_XSTOP | KSW_XSUBO | KSW_XSTART | KSW_XBYTE)),
     ("indel-rich", None, dict(p_indel=0.05, p_sub=0.1)),
     ("asymmetric gaps", dict(o_del=4, e_del=2, o_ins=7, e_ins=1), {}),
     ("minsc above every score", None, dict(xtra=KSW_XSUBO | KSW_XSTART | 300)),
