@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -68,7 +69,11 @@ struct kswv_handle {
 
 namespace {
 
+std::mutex g_err_mutex;
+
 void set_err(kswv_handle *h, const char *fmt, ...) {
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    if (h->err[0]) return;                      // the first error of a call is the one reported
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(h->err, sizeof h->err, fmt, ap);
@@ -190,17 +195,17 @@ void free_dev(KDev &d) {
 }
 
 // waits for the slot's chunk, scatters its results to aln[regid], adds its kernel time
-int drain_slot(kswv_handle *h, KDev &d, KSlot &s, const bsw_seqpair *pairs, kswv_result *aln) {
+int drain_slot(kswv_handle *h, KDev &d, KSlot &s, const bsw_seqpair *pairs, kswv_result *aln, kswv_gpu_stats &S, int inner) {
     if (!s.busy) return BSW_OK;
     KCU(cudaSetDevice(d.id));
     KCU(cudaEventSynchronize(s.ev_done));
     float ms = 0;
     KCU(cudaEventElapsedTime(&ms, s.ev_start, s.ev_stop));
-    h->stats.kernel_ms += ms;
+    S.kernel_ms += ms;
     const bsw_seqpair *p = pairs + s.first;
     const Result *r = s.h_out;
     static_assert(sizeof(Result) == sizeof(kswv_result), "Result is kswr_t");
-#pragma omp parallel for schedule(static) if (s.count > 4096)
+#pragma omp parallel for schedule(static) num_threads(inner) if (s.count > 4096)
     for (int64_t i = 0; i < s.count; ++i) memcpy(&aln[p[i].regid], &r[i], sizeof(Result));
     s.busy = false;
     return BSW_OK;
@@ -344,16 +349,17 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
     }
     const int scratch_rows = (maxT + kScratchSlack + 3) & ~3, scratch_q = maxQ + 64;
 
-    // ---- chunks
+    // ---- chunks. One host thread per GPU prepares, enqueues and drains that GPU's contiguous share of the pairs
+    // (no collective and no shared state between them: pairs are independent).
+    const int n_dev = (int)h->devs.size();
+    auto run_range = [&](KDev &d, int64_t lo, int64_t hi, kswv_gpu_stats &S, int inner) -> int {
     int rc = BSW_OK;
-    size_t dev_rr = 0;
     std::vector<uint32_t> order, bucket_start, bkt;
-    for (int64_t first = 0; first < n && rc == BSW_OK;) {
-        // cut: at most kChunkPairs pairs / kChunkBytes sequence bytes; small batches are split across the GPUs
-        int64_t target = kChunkPairs;
-        const int64_t per_gpu = (n + (int64_t)h->devs.size() - 1) / (int64_t)h->devs.size();
-        if (per_gpu < target) target = std::max<int64_t>(per_gpu, 1);
-        int64_t cnt = std::min<int64_t>(target, n - first);
+    for (int64_t first = lo; first < hi && rc == BSW_OK;) {
+        // cut: at most kChunkPairs pairs / kChunkBytes sequence bytes
+        // (a share that is smaller than three chunks is still cut in three, so that copies and kernels overlap)
+        const int64_t target = std::max<int64_t>(4096, std::min<int64_t>(kChunkPairs, (hi - lo + 2) / 3));
+        int64_t cnt = std::min<int64_t>(target, hi - first);
         int64_t rlo, rhi, qlo, qhi, rsum, qsum;
         bool ordered;
         const auto tc = std::chrono::steady_clock::now();
@@ -362,7 +368,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             int unordered = 0;
             const bsw_seqpair *cp0 = pairs + first;
 #pragma omp parallel for schedule(static) reduction(min : a_rlo, a_qlo) reduction(max : a_rhi, a_qhi) \
-    reduction(+ : a_rsum, a_qsum) reduction(| : unordered) if (cnt > 4096)
+    reduction(+ : a_rsum, a_qsum) reduction(| : unordered) num_threads(inner) if (cnt > 4096)
             for (int64_t i = 0; i < cnt; ++i) {
                 const bsw_seqpair &sp = cp0[i];
                 a_rlo = std::min<int64_t>(a_rlo, sp.idr); a_rhi = std::max<int64_t>(a_rhi, sp.idr + sp.len1);
@@ -379,14 +385,12 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         // one dense range per buffer (the production layout: mem_matesw_batch_pre appends, bwamem_pair.cpp:1006-1013)?
         const bool dense = ordered && (rhi - rlo) <= rsum + rsum / 8 + 4096 && (qhi - qlo) <= qsum + qsum / 8 + 4096 &&
                            (rhi - rlo) < (1ll << 32) && (qhi - qlo) < (1ll << 32);
-        KDev &d = h->devs[dev_rr % h->devs.size()];
-        ++dev_rr;
         KCU(cudaSetDevice(d.id));
         KSlot &s = d.slot[d.next];
         d.next = (d.next + 1) % kRing;
         {
             const auto tw = std::chrono::steady_clock::now();
-            rc = drain_slot(h, d, s, pairs, aln);
+            rc = drain_slot(h, d, s, pairs, aln, S, inner);
             S.host_wait_ms += ms_since(tw);
         }
         if (rc) break;
@@ -418,7 +422,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             bkt.resize((size_t)cnt);
             int64_t np = 0;
             int pc = 0;
-#pragma omp parallel for schedule(static) reduction(+ : np) reduction(max : pc) if (cnt > 4096)
+#pragma omp parallel for schedule(static) reduction(+ : np) reduction(max : pc) num_threads(inner) if (cnt > 4096)
             for (int64_t i = 0; i < cnt; ++i) {      // the only pass over the 72-byte records; the rest works on 4-byte keys
                 bool plain; int cols;
                 bkt[(size_t)i] = (uint32_t)bucket_of(i, &plain, &cols);
@@ -430,7 +434,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             for (int64_t i = 0; i < cnt; ++i) order[bucket_start[(size_t)bkt[(size_t)i]]++] = (uint32_t)i;
         }
         if (dense) {
-#pragma omp parallel for schedule(static) if (cnt > 4096)
+#pragma omp parallel for schedule(static) num_threads(inner) if (cnt > 4096)
             for (int64_t j = 0; j < cnt; ++j) {
                 const uint32_t i = order[(size_t)j];
                 const bsw_seqpair &sp = cp[i];
@@ -442,7 +446,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
             uint32_t ro = 0, qo = 0;
             for (int64_t i = 0; i < cnt; ++i) { roff[(size_t)i] = ro; qoff[(size_t)i] = qo; ro += (uint32_t)cp[i].len1; qo += (uint32_t)cp[i].len2; }
             uint8_t *gr = s.h_seq, *gq = s.h_seq + rsum;
-#pragma omp parallel for schedule(static) if (cnt > 1024)
+#pragma omp parallel for schedule(static) num_threads(inner) if (cnt > 1024)
             for (int64_t i = 0; i < cnt; ++i) {
                 memcpy(gr + roff[(size_t)i], ref + cp[i].idr, (size_t)cp[i].len1);
                 memcpy(gq + qoff[(size_t)i], qer + cp[i].idq, (size_t)cp[i].len2);
@@ -511,15 +515,42 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         ++S.chunks;
         first += cnt;
     }
-    // ---- drain, oldest first on every device
+    // ---- drain this GPU's slots, oldest first
     const auto tw = std::chrono::steady_clock::now();
-    for (KDev &d : h->devs)
-        for (int j = 0; j < kRing; ++j) {
-            KSlot &s = d.slot[(d.next + j) % kRing];
-            const int rc2 = drain_slot(h, d, s, pairs, aln);
-            if (rc == BSW_OK) rc = rc2;
-        }
+    for (int j = 0; j < kRing; ++j) {
+        KSlot &s = d.slot[(d.next + j) % kRing];
+        const int rc2 = drain_slot(h, d, s, pairs, aln, S, inner);
+        if (rc == BSW_OK) rc = rc2;
+    }
     S.host_wait_ms += ms_since(tw);
+    return rc;
+    };  // run_range
+
+    int rc = BSW_OK;
+    const int max_threads = std::max(1, omp_get_max_threads());
+    if (n_dev == 1) {
+        rc = run_range(h->devs[0], 0, n, S, max_threads);
+    } else {
+        std::vector<kswv_gpu_stats> part((size_t)n_dev);
+        std::vector<int> rcs((size_t)n_dev, BSW_OK);
+        // the workers are an OpenMP team (kept alive between calls); inside a worker the per-chunk passes run serially,
+        // which is enough: a chunk's preparation is several times shorter than its kernels
+#pragma omp parallel for schedule(static, 1) num_threads(n_dev)
+        for (int g = 0; g < n_dev; ++g) {
+            memset(&part[(size_t)g], 0, sizeof(kswv_gpu_stats));
+            const int64_t lo = n * g / n_dev, hi = n * (g + 1) / n_dev;
+            rcs[(size_t)g] = run_range(h->devs[(size_t)g], lo, hi, part[(size_t)g], 1);
+        }
+        for (int g = 0; g < n_dev; ++g) {
+            const kswv_gpu_stats &P = part[(size_t)g];
+            S.chunks += P.chunks; S.h2d_bytes += P.h2d_bytes; S.d2h_bytes += P.d2h_bytes; S.kernel_launches += P.kernel_launches;
+            S.gathered += P.gathered; S.kernel_ms += P.kernel_ms;
+            S.host_prep_ms = std::max(S.host_prep_ms, P.host_prep_ms);      // the workers run side by side
+            S.host_wait_ms = std::max(S.host_wait_ms, P.host_wait_ms);
+            if (P.lanes_per_pair) S.lanes_per_pair = P.lanes_per_pair;
+            if (rc == BSW_OK) rc = rcs[(size_t)g];
+        }
+    }
     S.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;
 }
