@@ -1,5 +1,6 @@
 // kswv_gpu.cu -- host side of the kswv path (include/kswv_gpu.h): chunks of pairs flow through a ring of three
-// slots per GPU (tasks + sequences H2D, the two kernels, results D2H, each on its own stream), the host orders each chunk's
+// slots per GPU (tasks + sequences H2D, the two kernels, results D2H, each on its own stream; one host worker per GPU
+// over that GPU's contiguous share of the call), the host orders each chunk's
 // tasks by decreasing DP size and scatters finished results to aln[regid]. Kernels: kswv_kernels.cuh.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>

@@ -82,7 +82,7 @@ if __name__ == "__main__":
         g.align(pairs, ref, qer, aln)
         wall.append(time.perf_counter() - t)
         st = g.stats()
-        kern.append(st["kernel_ms"] * 1e-3 / a.gpus)      # chunks are dealt round-robin: per-GPU share of the summed kernel time
+        kern.append(st["kernel_ms"] * 1e-3 / a.gpus)      # every GPU gets an equal share of the pairs: the summed kernel time / GPUs
         h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]; launches += st["kernel_launches"]
     clocks = sampler.stop()
     cells = st["cells"]
