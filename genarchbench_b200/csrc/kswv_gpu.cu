@@ -291,7 +291,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
     const auto t0 = std::chrono::steady_clock::now();
     kswv_gpu_stats &S = h->stats;
     S.chunks = 0; S.pairs = n; S.pairs8 = 0; S.cells = 0; S.h2d_bytes = 0; S.d2h_bytes = 0; S.kernel_launches = 0;
-    S.gathered = 0; S.kernel_ms = 0; S.wall_ms = 0; S.lanes_per_pair = 0;
+    S.gathered = 0; S.staged = 0; S.kernel_ms = 0; S.wall_ms = 0; S.lanes_per_pair = 0;
     S.host_check_ms = 0; S.host_prep_ms = 0; S.host_wait_ms = 0;
     auto ms_since = [](std::chrono::steady_clock::time_point a) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
@@ -353,6 +353,13 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
     // ---- chunks. One host thread per GPU prepares, enqueues and drains that GPU's contiguous share of the pairs
     // (no collective and no shared state between them: pairs are independent).
     const int n_dev = (int)h->devs.size();
+    // are the caller's sequence buffers page-locked (bsw_gpu_host_alloc / cudaHostRegister)? Then ranges are DMA'd in place.
+    auto is_pinned = [](const void *p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool caller_pinned = is_pinned(ref) && is_pinned(qer);
     auto run_range = [&](KDev &d, int64_t lo, int64_t hi, kswv_gpu_stats &S, int inner) -> int {
     int rc = BSW_OK;
     std::vector<uint32_t> order, bucket_start, bkt;
@@ -398,7 +405,10 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         const auto tp = std::chrono::steady_clock::now();
         const size_t ref_bytes = dense ? (size_t)(rhi - rlo) : (size_t)rsum;
         const size_t qer_bytes = dense ? (size_t)(qhi - qlo) : (size_t)qsum;
-        rc = ensure_slot(h, s, (size_t)cnt, ref_bytes, qer_bytes, dense ? 0 : (size_t)(rsum + qsum) + 64);
+        // a dense chunk in pageable caller memory is copied into the slot's page-locked staging by this thread(s): the
+        // driver's own staging of a pageable source blocks the call for the whole copy at a third of the rate
+        const bool stage = dense && !caller_pinned;
+        rc = ensure_slot(h, s, (size_t)cnt, ref_bytes, qer_bytes, (dense && !stage) ? 0 : ref_bytes + qer_bytes + 64);
         if (rc) break;
 
         // Task order. Plain pairs first: no clamped arithmetic and at most 256 padded columns, the ones a group of
@@ -461,7 +471,24 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         S.host_prep_ms += ms_since(tp);
         // ---- enqueue
         KCU(cudaMemcpyAsync(s.d_tasks, s.h_tasks, sizeof(Task) * (size_t)cnt, cudaMemcpyHostToDevice, d.st_in));
-        if (dense) {
+        if (stage) {
+            const size_t total = ref_bytes + qer_bytes, piece = 1u << 20;
+            const int64_t npieces = (int64_t)((total + piece - 1) / piece);
+#pragma omp parallel for schedule(static) num_threads(inner) if (npieces > 4)
+            for (int64_t pc = 0; pc < npieces; ++pc) {
+                // piece pc of the concatenation [ref range | qer range]
+                size_t lo_b = (size_t)pc * piece, hi_b = std::min(total, lo_b + piece);
+                if (lo_b < ref_bytes) {
+                    const size_t e = std::min(hi_b, ref_bytes);
+                    memcpy(s.h_seq + lo_b, ref + rlo + lo_b, e - lo_b);
+                    lo_b = e;
+                }
+                if (lo_b < hi_b) memcpy(s.h_seq + lo_b, qer + qlo + (lo_b - ref_bytes), hi_b - lo_b);
+            }
+            if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, s.h_seq, ref_bytes, cudaMemcpyHostToDevice, d.st_in));
+            if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, s.h_seq + ref_bytes, qer_bytes, cudaMemcpyHostToDevice, d.st_in));
+            ++S.staged;
+        } else if (dense) {
             if (ref_bytes) KCU(cudaMemcpyAsync(s.d_ref, ref + rlo, ref_bytes, cudaMemcpyHostToDevice, d.st_in));
             if (qer_bytes) KCU(cudaMemcpyAsync(s.d_qer, qer + qlo, qer_bytes, cudaMemcpyHostToDevice, d.st_in));
         } else {
@@ -545,7 +572,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         for (int g = 0; g < n_dev; ++g) {
             const kswv_gpu_stats &P = part[(size_t)g];
             S.chunks += P.chunks; S.h2d_bytes += P.h2d_bytes; S.d2h_bytes += P.d2h_bytes; S.kernel_launches += P.kernel_launches;
-            S.gathered += P.gathered; S.kernel_ms += P.kernel_ms;
+            S.gathered += P.gathered; S.staged += P.staged; S.kernel_ms += P.kernel_ms;
             S.host_prep_ms = std::max(S.host_prep_ms, P.host_prep_ms);      // the workers run side by side
             S.host_wait_ms = std::max(S.host_wait_ms, P.host_wait_ms);
             if (P.lanes_per_pair) S.lanes_per_pair = P.lanes_per_pair;

@@ -32,7 +32,7 @@ class Stats(C.Structure):
                 ("cells", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
                 ("kernel_launches", C.c_int64), ("gathered", C.c_int64), ("kernel_ms", C.c_double),
                 ("wall_ms", C.c_double), ("host_check_ms", C.c_double), ("host_prep_ms", C.c_double),
-                ("host_wait_ms", C.c_double)]
+                ("host_wait_ms", C.c_double), ("staged", C.c_int64)]
 
     def asdict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

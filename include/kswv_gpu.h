@@ -58,6 +58,7 @@ typedef struct kswv_gpu_stats {
     double host_check_ms;       /* last batch: validation pass over the records */
     double host_prep_ms;        /* last batch: task ordering + task records (+ gather), summed over chunks */
     double host_wait_ms;        /* last batch: blocked on a slot's results (includes the scatter to aln) */
+    int64_t staged;             /* last batch: dense chunks copied through page-locked staging (pageable caller buffers) */
 } kswv_gpu_stats;
 
 /* Scoring is fixed per handle, as in the reference's constructor. n_gpus <= 0: all visible devices.
@@ -74,7 +75,8 @@ void kswv_gpu_free(kswv_handle *h);
  * Domain (BSW_ERR_RANGE, nothing computed): 0 <= len1, len2 <= 32767 (te and qe are int16 in the reference), and
  * for the 16-bit class min(len1, len2) * match <= 32767 (the reference's int16 lanes wrap above that).
  * Sequences are sent as one range per chunk when a chunk's pairs lie densely and in order in ref / qer (the
- * production layout); page-locked buffers (bsw_gpu_host_alloc) then go to the device without any host copy. */
+ * production layout); page-locked buffers (bsw_gpu_host_alloc / cudaHostRegister) then go to the device without any
+ * host copy, pageable ones through the library's page-locked staging. */
 int kswv_gpu_batch(kswv_handle *h, const bsw_seqpair *pairs, const uint8_t *ref, const uint8_t *qer,
                    int64_t n_pairs, kswv_result *aln);
 

@@ -36,6 +36,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--read-len", type=int, default=151)
     ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--pageable", action="store_true", help="caller buffers from malloc instead of page-locked memory")
     a = ap.parse_args()
     if a.reps:
         a.steps = a.reps
@@ -53,6 +54,8 @@ if __name__ == "__main__":
     L = bsw.lib()
 
     def pinned(nbytes, dtype):
+        if a.pageable:
+            return np.zeros(nbytes, np.uint8).view(dtype)
         p = L.bsw_gpu_host_alloc(nbytes + 64)
         assert p
         return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p)).view(dtype)
@@ -109,7 +112,7 @@ if __name__ == "__main__":
                 "host_ms_last_step": {k: round(st[k], 3) for k in ("host_check_ms", "host_prep_ms", "host_wait_ms", "wall_ms")}},
         "e2e": {"value": cells / wall_s / 1e9, "unit": "GCUPS", "ms_per_step": wall_s * 1e3,
                 "h2d_bytes_per_step": h2d // a.steps, "d2h_bytes_per_step": d2h // a.steps,
-                "api": "kswv_gpu_batch from page-locked host buffers (ranges DMA'd in place), results scattered to aln[regid]"},
+                "api": "kswv_gpu_batch from " + ("pageable" if a.pageable else "page-locked") + " host buffers, results scattered to aln[regid]"},
         "gpu_launches": launches,
         "roofline": {"bound": "alu_int", "kernel": "kswv_phase0_kernel / kswv_phase1_kernel", "achieved": achieved, "peak": dpx,
                      "unit": "Ginstr/s (ALU-pipe thread-instructions)", "frac": achieved / dpx,

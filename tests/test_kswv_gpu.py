@@ -85,9 +85,26 @@ def test_many_chunks_shuffled_order_and_regid(dev):
     assert_same_aln(got, want, pairs, "shuffled order")
     st = dev.stats()
     assert st["chunks"] >= 3 and st["gathered"] == st["chunks"]
-    got = dev.align(pairs, ref, qer)            # dense, in order: sent as ranges
+    got = dev.align(pairs, ref, qer)            # dense, in order: sent as ranges (numpy memory is pageable: staged)
     assert_same_aln(got, want, pairs, "dense order")
-    assert dev.stats()["gathered"] == 0
+    st = dev.stats()
+    assert st["gathered"] == 0 and st["staged"] == st["chunks"]
+    # the same from page-locked buffers: DMA'd in place
+    import ctypes as C
+    from genarchbench_b200 import bsw
+    L = bsw.lib()
+
+    def pinned_copy(a):
+        p = L.bsw_gpu_host_alloc(a.nbytes + 64)
+        v = np.ctypeslib.as_array((C.c_uint8 * a.nbytes).from_address(p)).view(a.dtype)
+        v[:] = a
+        return v, p
+    (pref, p1), (pqer, p2) = pinned_copy(ref), pinned_copy(qer)
+    got = dev.align(pairs, pref, pqer)
+    assert_same_aln(got, want, pairs, "page-locked buffers")
+    st = dev.stats()
+    assert st["gathered"] == 0 and st["staged"] == 0
+    L.bsw_gpu_host_free(p1); L.bsw_gpu_host_free(p2)
 
 
 def test_empty_sequences_and_empty_batch(dev):
