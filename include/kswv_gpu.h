@@ -19,6 +19,7 @@
 #define KSWV_GPU_H
 
 #include <stdint.h>
+#include "bsw_gpu.h"   /* BSW_OK / BSW_ERR_* and bsw_gpu_strerror, bsw_gpu_host_alloc */
 #include "bsw_types.h"
 
 #ifdef __cplusplus

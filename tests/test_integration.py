@@ -59,3 +59,32 @@ def test_patched_reference_driver_prints_the_stock_scores(tmp_path):
         assert got.returncode == 0, got.stderr[-500:]
         assert scores(got.stderr, len(b)) == want, f"-b {bflag}"
         assert "libbsw_gpu.so" in got.stdout and "Total Pairs processed: 100000" in got.stdout
+
+
+KSWV_BINDING = os.path.join(BUILD, "kswv_binding")
+KSWV_REF = os.path.join(ROOT, "oracle", "_ref", "libkswv_ref_avx512.so")
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference not present (the GPU box uses the prebuilt binaries)")
+def test_kswv_binding_compiles_against_the_reference_headers():
+    """a translation unit that includes the reference's kswv.h (SeqPair, kswr_t, KSW_X*) and ours,
+    with the layouts asserted equal at compile time, builds and links with libbsw_gpu.so."""
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "integration"), "all"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert os.path.exists(KSWV_BINDING)
+    assert "libbsw_gpu.so" in subprocess.run(["ldd", KSWV_BINDING], capture_output=True, text=True).stdout
+
+
+@pytest.mark.gpu
+def test_kswv_binding_matches_the_reference_class():
+    """The reference-typed arrays through kswv_gpu_batch (both classes, both phases) against the unmodified kswv class
+    on the same batch, in one C++ program."""
+    from oracle import kswv as okswv
+    if not os.path.exists(KSWV_BINDING):
+        pytest.skip("integration/_build not built (make -C integration, where /root/reference exists)")
+    if not okswv.reference_available():
+        pytest.skip("the compiled reference needs AVX512BW on this host")
+    r = subprocess.run([KSWV_BINDING, "20000", KSWV_REF], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    m = re.search(r"kswv binding: (\d+) pairs, score sum (\d+), (\d+) with start positions, mismatches vs the reference class: (-?\d+)", r.stdout)
+    assert m and int(m.group(1)) == 20000 and int(m.group(4)) == 0 and int(m.group(3)) > 10000, r.stdout
