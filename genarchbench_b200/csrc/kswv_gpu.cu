@@ -412,7 +412,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         if (rc) break;
 
         // Task order. Plain pairs first: no clamped arithmetic and at most 256 padded columns, the ones a group of
-        // fewer than 32 lanes can take. Inside each class by decreasing strip-width bucket (padded columns / 32) and
+        // fewer than 32 lanes can take. Inside each class by decreasing strip-width bucket (padded columns / 16) and
         // decreasing reference length (8-row bins): the pairs that share a warp get the same code and nearly the same
         // trip counts, and the largest DPs start first. One counting sort.
         const bsw_seqpair *cp = pairs + first;
@@ -420,13 +420,13 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         int64_t n_plain = 0;
         int plain_cols = 0;
         {
-            constexpr int kLenBins = 4096, kColBins = 9, kBuckets = 2 * kColBins * kLenBins;
+            constexpr int kLenBins = 4096, kColBins = 17, kBuckets = 2 * kColBins * kLenBins;
             bucket_start.assign((size_t)kBuckets + 1, 0);
             auto bucket_of = [&](int64_t i, bool *plain, int *cols) {
                 const bool byte = (cp[i].h0 & kXByte) != 0;
                 const int nc = padded_cols(cp[i].len2, byte);
                 const bool special = nc > kPassCols || needs_sat(h->K.a, h->K.shift, cp[i].len1, cp[i].len2, byte);
-                const int cb = std::min((nc + 31) / 32, kColBins - 1);
+                const int cb = std::min((nc + 15) / 16, kColBins - 1);
                 if (plain) { *plain = !special; *cols = nc; }
                 return ((special ? 1 : 0) * kColBins + (kColBins - 1 - cb)) * kLenBins + (kLenBins - 1 - (cp[i].len1 >> 3));
             };

@@ -356,16 +356,21 @@ __device__ inline Best kswv_dp_any<16>(const KParams &K, const uint32_t *t, int 
         default: return kswv_dp<16, 16, false, false>(KSWV_DP_ARGS);
     }
 }
-// W = 8: pairs without clamping, up to 160 padded columns; strips of 4, 8, .. 20 columns
+// W = 8: pairs without clamping, up to 160 padded columns; strips of 2, 4, .. 20 columns
 template <>
 __device__ inline Best kswv_dp_any<8>(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
                                       bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
     const int ncol = padded_cols(qlen, byte);
-    switch ((ncol + 31) / 32) {
-        case 1: return kswv_dp<8, 4, false, false>(KSWV_DP_ARGS);
-        case 2: return kswv_dp<8, 8, false, false>(KSWV_DP_ARGS);
-        case 3: return kswv_dp<8, 12, false, false>(KSWV_DP_ARGS);
-        case 4: return kswv_dp<8, 16, false, false>(KSWV_DP_ARGS);
+    switch ((ncol + 15) / 16) {
+        case 1: return kswv_dp<8, 2, false, false>(KSWV_DP_ARGS);
+        case 2: return kswv_dp<8, 4, false, false>(KSWV_DP_ARGS);
+        case 3: return kswv_dp<8, 6, false, false>(KSWV_DP_ARGS);
+        case 4: return kswv_dp<8, 8, false, false>(KSWV_DP_ARGS);
+        case 5: return kswv_dp<8, 10, false, false>(KSWV_DP_ARGS);
+        case 6: return kswv_dp<8, 12, false, false>(KSWV_DP_ARGS);
+        case 7: return kswv_dp<8, 14, false, false>(KSWV_DP_ARGS);
+        case 8: return kswv_dp<8, 16, false, false>(KSWV_DP_ARGS);
+        case 9: return kswv_dp<8, 18, false, false>(KSWV_DP_ARGS);
         default: return kswv_dp<8, 20, false, false>(KSWV_DP_ARGS);
     }
 }
@@ -459,7 +464,7 @@ __device__ inline Result kswv_phase0(const KParams &K, const Task &T, const uint
     if (th.byte && r.score == 255) { r.score2 = -1; r.te2 = -1; }
     else kswv_second<W>(K, rowkey, T.tlen, B, th.byte, th.has_minsc, th.minsc, &r.score2, &r.te2);
     const bool phase1 = (T.xtra & kXStart) && !((T.xtra & kXSubo) && r.score < (T.xtra & 0xffff));
-    *p1key = phase1 ? ((uint32_t)((padded_cols(r.qe + 1, th.byte) + 31) / 32) << 16) | (uint32_t)(r.te + 1) : 0u;
+    *p1key = phase1 ? ((uint32_t)((padded_cols(r.qe + 1, th.byte) + 15) / 16) << 16) | (uint32_t)(r.te + 1) : 0u;
     Grp<W>::sync();                                                      // the scratch is free for the next pair
     return r;
 }
