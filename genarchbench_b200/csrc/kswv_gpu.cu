@@ -412,7 +412,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         if (rc) break;
 
         // Task order. Plain pairs first: no clamped arithmetic and at most 256 padded columns, the ones a group of
-        // fewer than 32 lanes can take. Inside each class by decreasing strip-width bucket (padded columns / 16) and
+        // fewer than 32 lanes can take. Inside each class by decreasing strip-width class (strip_bucket) and
         // decreasing reference length (8-row bins): the pairs that share a warp get the same code and nearly the same
         // trip counts, and the largest DPs start first. One counting sort.
         const bsw_seqpair *cp = pairs + first;
@@ -426,7 +426,7 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
                 const bool byte = (cp[i].h0 & kXByte) != 0;
                 const int nc = padded_cols(cp[i].len2, byte);
                 const bool special = nc > kPassCols || needs_sat(h->K.a, h->K.shift, cp[i].len1, cp[i].len2, byte);
-                const int cb = std::min((nc + 15) / 16, kColBins - 1);
+                const int cb = std::min(strip_bucket(nc), kColBins - 1);
                 if (plain) { *plain = !special; *cols = nc; }
                 return ((special ? 1 : 0) * kColBins + (kColBins - 1 - cb)) * kLenBins + (kLenBins - 1 - (cp[i].len1 >> 3));
             };

@@ -321,6 +321,14 @@ __host__ __device__ inline int padded_cols(int qlen, bool byte) {
     return n == 0 ? quantum : n;
 }
 
+// Strip-width class of a padded query: pairs of one class run the same kswv_dp instance at every group width (the
+// host's task order and the phase-1 key keep a warp's pairs in one class). Columns: <=32, 64, 80, 96, 112, 128, 160,
+// then one class per further 32 columns.
+__host__ __device__ inline int strip_bucket(int ncol) {
+    return ncol <= 32 ? 0 : ncol <= 64 ? 1 : ncol <= 80 ? 2 : ncol <= 96 ? 3 : ncol <= 112 ? 4 : ncol <= 128 ? 5
+         : ncol <= 160 ? 6 : 6 + (ncol - 160 + 31) / 32;
+}
+
 #define KSWV_DP_ARGS K, t, tlen, q, qlen, byte, thr, rowkey, bnd
 template <int W>
 __device__ inline Best kswv_dp_any(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
@@ -356,21 +364,19 @@ __device__ inline Best kswv_dp_any<16>(const KParams &K, const uint32_t *t, int 
         default: return kswv_dp<16, 16, false, false>(KSWV_DP_ARGS);
     }
 }
-// W = 8: pairs without clamping, up to 160 padded columns; strips of 2, 4, .. 20 columns
+// W = 8: pairs without clamping, up to 160 padded columns; strips of 4, 8, 10, 12, 14, 16 or 20 columns (the multiples
+// of four plus the widths of 76- and 100-bp reads; more instances cost more in instruction cache than they save in
+// filler columns: with every even width the 151-bp workload ran 3 % slower)
 template <>
 __device__ inline Best kswv_dp_any<8>(const KParams &K, const uint32_t *t, int tlen, const uint8_t *q, int qlen,
                                       bool byte, int thr, uint32_t *rowkey, uint2 *bnd) {
-    const int ncol = padded_cols(qlen, byte);
-    switch ((ncol + 15) / 16) {
-        case 1: return kswv_dp<8, 2, false, false>(KSWV_DP_ARGS);
-        case 2: return kswv_dp<8, 4, false, false>(KSWV_DP_ARGS);
-        case 3: return kswv_dp<8, 6, false, false>(KSWV_DP_ARGS);
-        case 4: return kswv_dp<8, 8, false, false>(KSWV_DP_ARGS);
-        case 5: return kswv_dp<8, 10, false, false>(KSWV_DP_ARGS);
-        case 6: return kswv_dp<8, 12, false, false>(KSWV_DP_ARGS);
-        case 7: return kswv_dp<8, 14, false, false>(KSWV_DP_ARGS);
-        case 8: return kswv_dp<8, 16, false, false>(KSWV_DP_ARGS);
-        case 9: return kswv_dp<8, 18, false, false>(KSWV_DP_ARGS);
+    switch (strip_bucket(padded_cols(qlen, byte))) {
+        case 0: return kswv_dp<8, 4, false, false>(KSWV_DP_ARGS);
+        case 1: return kswv_dp<8, 8, false, false>(KSWV_DP_ARGS);
+        case 2: return kswv_dp<8, 10, false, false>(KSWV_DP_ARGS);
+        case 3: return kswv_dp<8, 12, false, false>(KSWV_DP_ARGS);
+        case 4: return kswv_dp<8, 14, false, false>(KSWV_DP_ARGS);
+        case 5: return kswv_dp<8, 16, false, false>(KSWV_DP_ARGS);
         default: return kswv_dp<8, 20, false, false>(KSWV_DP_ARGS);
     }
 }
@@ -464,7 +470,7 @@ __device__ inline Result kswv_phase0(const KParams &K, const Task &T, const uint
     if (th.byte && r.score == 255) { r.score2 = -1; r.te2 = -1; }
     else kswv_second<W>(K, rowkey, T.tlen, B, th.byte, th.has_minsc, th.minsc, &r.score2, &r.te2);
     const bool phase1 = (T.xtra & kXStart) && !((T.xtra & kXSubo) && r.score < (T.xtra & 0xffff));
-    *p1key = phase1 ? ((uint32_t)((padded_cols(r.qe + 1, th.byte) + 15) / 16) << 16) | (uint32_t)(r.te + 1) : 0u;
+    *p1key = phase1 ? ((uint32_t)(strip_bucket(padded_cols(r.qe + 1, th.byte)) + 1) << 16) | (uint32_t)(r.te + 1) : 0u;
     Grp<W>::sync();                                                      // the scratch is free for the next pair
     return r;
 }
