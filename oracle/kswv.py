@@ -142,3 +142,42 @@ def make_workload(n, seed=0, read_len=(100, 151), window=(2.0, 5.0), match=1, mi
         pairs[f] = -1
     pad = np.zeros(64, np.uint8)
     return pairs, np.concatenate(refs + [pad]), np.concatenate(qers + [pad])
+
+
+def make_low_complexity(n, seed=0, kind="tandem"):
+    """-> (pairs, ref, qer): sequences full of ties -- the cases where "first column of the row maximum", "first row
+    of gmax" and the rising-row filter decide the outputs. kind: homopolymer | two-letter | tandem | identical-prefix.
+    Lengths 1..259 x 1..699, a mix of flag words in both classes."""
+    from genarchbench_b200 import pairio
+    rng = np.random.default_rng(seed)
+    pairs = np.zeros(n, dtype=pairio.SEQPAIR_DTYPE)
+    refs, qers = [], []
+    ro = qo = 0
+    flags = [KSW_XSUBO | KSW_XSTART | 19, KSW_XSUBO | KSW_XSTART | KSW_XBYTE | 19, KSW_XSTART, KSW_XSTART | KSW_XBYTE,
+             KSW_XSTOP | KSW_XSTART | 30, KSW_XSUBO | KSW_XSTART | KSW_XBYTE | 1, KSW_XSUBO | KSW_XSTART]
+    for k in range(n):
+        l2, l1 = int(rng.integers(1, 260)), int(rng.integers(1, 700))
+        if kind == "homopolymer":
+            t = np.full(l1, rng.integers(0, 4), np.uint8)
+            q = np.full(l2, t[0] if rng.random() < 0.7 else rng.integers(0, 4), np.uint8)
+            t[rng.random(l1) < 0.05] = rng.integers(0, 4)
+            q[rng.random(l2) < 0.05] = rng.integers(0, 4)
+        elif kind == "two-letter":
+            t, q = rng.integers(0, 2, l1).astype(np.uint8), rng.integers(0, 2, l2).astype(np.uint8)
+        elif kind == "tandem":
+            u = rng.integers(0, 4, int(rng.integers(1, 6))).astype(np.uint8)
+            t, q = np.resize(u, l1).copy(), np.resize(u, l2).copy()
+            t[rng.random(l1) < 0.03] = rng.integers(0, 4)
+            q[rng.random(l2) < 0.03] = rng.integers(0, 4)
+        else:
+            t = rng.integers(0, 4, l1).astype(np.uint8)
+            q = t[:l2].copy() if l2 <= l1 else rng.integers(0, 4, l2).astype(np.uint8)
+        p = pairs[k]
+        p["idr"], p["idq"], p["id"], p["len1"], p["len2"], p["regid"] = ro, qo, k, l1, l2, k
+        p["h0"] = int(flags[int(rng.integers(0, len(flags)))])
+        refs.append(t); qers.append(q)
+        ro += l1; qo += l2
+    for f in ("seqid",) + pairio.OUTPUT_FIELDS:
+        pairs[f] = -1
+    pad = np.zeros(64, np.uint8)
+    return pairs, np.concatenate(refs + [pad]), np.concatenate(qers + [pad])

@@ -62,6 +62,19 @@ def test_device_code_matches_oracle(emul, what, params, kw):
     assert_same_aln(emul(pairs, ref, qer, params), want, pairs, what)
 
 
+@pytest.mark.parametrize("kind", ("homopolymer", "two-letter", "tandem", "identical-prefix"))
+def test_device_code_on_ties(emul, kind):
+    pairs, ref, qer = kswv.make_low_complexity(300, seed=4, kind=kind)
+    want, _ = kswv.oracle_batch(pairs, ref, qer)
+    assert_same_aln(emul(pairs, ref, qer), want, pairs, kind)
+    keep = pairs["len2"] <= 160                      # the narrow groups take what fits them and needs no clamp
+    sub = pairs[keep].copy()
+    sub["h0"] &= ~KSW_XBYTE | 0                      # 16-bit class: never clamped
+    sub["regid"] = np.arange(len(sub))
+    want, _ = kswv.oracle_batch(sub, ref, qer)
+    assert_same_aln(emul(sub, ref, qer, width=8), want, sub, kind + ", 8 lanes")
+
+
 def test_empty_sequences(emul):
     pairs, ref, qer = kswv.make_workload(40, seed=3, read_len=(5, 40), min_seed_len=3)
     pairs["len1"][::4] = 0

@@ -171,3 +171,11 @@ def test_random_call_sequences_on_one_handle(dev):
         if rng.random() < 0.5:
             pairs = pairs[rng.permutation(n)].copy()
         assert_same_aln(dev.align(pairs, ref, qer), want, None, f"call {call}: n={n} reads {lo}-{hi}")
+
+
+@pytest.mark.parametrize("kind", ("homopolymer", "two-letter", "tandem", "identical-prefix"))
+def test_ties(dev, kind):
+    """Low-complexity sequences: equal row maxima and scores everywhere."""
+    pairs, ref, qer = okswv.make_low_complexity(4000, seed=5, kind=kind)
+    want, _ = okswv.oracle_batch(pairs, ref, qer)
+    assert_same_aln(dev.align(pairs, ref, qer), want, pairs, kind)

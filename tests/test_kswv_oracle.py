@@ -75,3 +75,17 @@ def test_a_lane_does_not_depend_on_its_batch_mates():
     perm = rng.permutation(len(pairs))
     got = kswv.reference_batch(pairs[perm].copy(), ref, qer)
     assert_same_aln(got, want, pairs, "shuffled batch")
+
+
+KINDS = ("homopolymer", "two-letter", "tandem", "identical-prefix")
+
+
+@pytest.mark.skipif(not kswv.reference_available(), reason="needs oracle/_ref/libkswv_ref_avx512.so and AVX512BW")
+@pytest.mark.parametrize("kind", KINDS)
+def test_oracle_matches_compiled_reference_on_ties(kind):
+    """Low-complexity sequences: many equal row maxima and equal scores, where first-column / first-row rules and the
+    rising-row filter decide the outputs."""
+    for seed in (1, 2):
+        pairs, ref, qer = kswv.make_low_complexity(400, seed=seed, kind=kind)
+        got, _ = kswv.oracle_batch(pairs, ref, qer)
+        assert_same_aln(got, kswv.reference_batch(pairs, ref, qer), pairs, kind)
