@@ -504,6 +504,10 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         KCU(cudaEventRecord(s.ev_start, d.st));
         // lanes per pair for the plain pairs: 8 up to 160 padded columns (strips of up to 20), 16 up to 256, else 32
         int width = plain_cols <= group_cols(8) ? 8 : (plain_cols <= group_cols(16) ? 16 : 32);
+        // a chunk that would leave most warps of the GPU idle at that width takes more lanes per pair instead: the
+        // steps get shorter (fewer columns per lane), and a small batch is as long as its longest pair's row loops
+        const int64_t warps = (int64_t)d.sms * kBlocksPerSm * kKswvWarps;
+        while (width < 32 && n_plain * (width * 2) / 32 <= warps) width *= 2;
         if (h->force_width) width = std::max(width, h->force_width);
         // one class of tasks [off, off + nt): phase 0, the phase-1 tasks ordered by (strip width, te) so that the pairs
         // of a warp have similar trip counts, phase 1
