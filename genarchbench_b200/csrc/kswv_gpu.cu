@@ -25,9 +25,10 @@ using namespace kswvk;
 namespace {
 
 constexpr int kRing = 3;
-constexpr int64_t kChunkPairs = 32768;          // pairs per chunk (about 40 MB of sequence at 150 bp reads)
+int64_t kChunkPairs = 32768;                    // pairs per chunk (about 20 MB of sequence at 150 bp reads); KSWV_CHUNK_PAIRS
 constexpr int64_t kChunkBytes = 96ll << 20;     // and at most this many sequence bytes
 constexpr int64_t kMinChunk = 16384;            // no chunk smaller than this unless the share is
+constexpr int64_t kMaxChunk = 131072;           // chunks grow with the share up to this
 constexpr int kBlocksPerSm = 4;                 // x kKswvWarps warps
 
 struct KSlot {
@@ -234,6 +235,10 @@ int kswv_gpu_init(const kswv_params *params, int n_gpus, kswv_handle **out) {
     h->P = p;
     h->K = make_kparams(p.o_del, p.e_del, p.o_ins, p.e_ins, p.match, p.mismatch);
     h->err[0] = 0;
+    if (const char *e = getenv("KSWV_CHUNK_PAIRS")) {       // developer switch
+        const long v = atol(e);
+        if (v >= 1024 && v <= (1 << 22)) kChunkPairs = v;
+    }
     if (const char *e = getenv("KSWV_MIN_LANES")) {
         const int w = atoi(e);
         if (w == 8 || w == 16 || w == 32) h->force_width = w;
@@ -369,7 +374,11 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         // (a share smaller than three chunks is cut in three so that copies and kernels overlap, but never below
         // kMinChunk pairs: the GPU holds about 9500 pairs at a time at 8 lanes per pair, and chunks that do not fill it
         // only serialise their kernels -- 8000 pairs: 0.89 ms in two chunks, one launch is as long as one pair's rows)
-        const int64_t target = std::max<int64_t>(kMinChunk, std::min<int64_t>(kChunkPairs, (hi - lo + 2) / 3));
+        // Large shares take larger chunks (a sixth of the share, up to kMaxChunk): every chunk's kernels end with a
+        // tail of idle SMs, and the GPU holds about 9500 pairs at once (400 000 pairs: 1556 GCUPS in chunks of 32 Ki,
+        // 1632 in chunks of 64 Ki; four chunks of 128 Ki are faster still on the GPU but overlap the copies less).
+        const int64_t big = std::min<int64_t>(kMaxChunk, std::max<int64_t>(kChunkPairs, (hi - lo) / 6));
+        const int64_t target = std::max<int64_t>(kMinChunk, std::min<int64_t>(big, (hi - lo + 2) / 3));
         int64_t cnt = std::min<int64_t>(target, hi - first);
         int64_t rlo, rhi, qlo, qhi, rsum, qsum;
         bool ordered;
