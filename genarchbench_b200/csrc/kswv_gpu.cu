@@ -1,6 +1,6 @@
 // kswv_gpu.cu -- host side of the kswv path (include/kswv_gpu.h): chunks of pairs flow through a ring of three
 // slots per GPU (tasks + sequences H2D, the two kernels, results D2H, each on its own stream; every GPU a contiguous
-// share of the call, chunks dealt round by round), the host orders each chunk's
+// share of the call; chunks dealt round by round by a coordinator, or by a host worker per GPU above four GPUs), the host orders each chunk's
 // tasks by decreasing DP size and scatters finished results to aln[regid]. Kernels: kswv_kernels.cuh.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -365,9 +365,10 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
         return at.type == cudaMemoryTypeHost;
     };
     const bool caller_pinned = is_pinned(ref) && is_pinned(qer);
-    std::vector<uint32_t> order, bucket_start, bkt;
+    struct HostScratch { std::vector<uint32_t> order, bucket_start, bkt; };
     // one chunk of GPU d's share [lo, hi), starting at `first` (advanced past the chunk)
-    auto one_chunk = [&](KDev &d, int64_t lo, int64_t hi, int64_t &first, kswv_gpu_stats &S, int inner) -> int {
+    auto one_chunk = [&](KDev &d, int64_t lo, int64_t hi, int64_t &first, kswv_gpu_stats &S, int inner, HostScratch &w) -> int {
+    std::vector<uint32_t> &order = w.order, &bucket_start = w.bucket_start, &bkt = w.bkt;
     int rc = BSW_OK;
     for (int once = 0; once < 1 && first < hi; ++once) {
         // cut: at most kChunkPairs pairs / kChunkBytes sequence bytes
@@ -562,30 +563,66 @@ static int kswv_batch_impl(kswv_handle *h, const bsw_seqpair *pairs, const uint8
     return rc;
     };  // one_chunk
 
-    // One coordinator thread deals the chunks round by round over the GPUs (every GPU a contiguous share of the pairs,
-    // no collective: pairs are independent); each chunk's passes over its records run on all host threads. A worker
-    // thread per GPU with serial passes was measured and is slower at N = 4 (5097 against 5412 GCUPS end to end).
+    // Up to four GPUs: one coordinator thread deals the chunks round by round (every GPU a contiguous share of the
+    // pairs, no collective: pairs are independent); each chunk's passes over its records run on all host threads.
+    // More GPUs: one host worker per GPU (an OpenMP team, kept between calls) with serial passes -- the coordinator's
+    // own time per chunk becomes the limit there (N = 8 end to end: 8005 GCUPS coordinator, 9621 workers; N = 4: 5329
+    // against 5097; N = 2: 2913 against 2761). KSWV_HOST_WORKERS=0/1 forces either.
     int rc = BSW_OK;
     const int max_threads = std::max(1, omp_get_max_threads());
+    bool workers = n_dev > 4;
+    if (const char *e = getenv("KSWV_HOST_WORKERS")) workers = e[0] == '1' && n_dev > 1;
     std::vector<int64_t> cur((size_t)n_dev), lo_((size_t)n_dev), hi_((size_t)n_dev);
     for (int g = 0; g < n_dev; ++g) { lo_[(size_t)g] = cur[(size_t)g] = n * g / n_dev; hi_[(size_t)g] = n * (g + 1) / n_dev; }
-    for (bool more = true; more && rc == BSW_OK;) {
-        more = false;
-        for (int g = 0; g < n_dev && rc == BSW_OK; ++g)
-            if (cur[(size_t)g] < hi_[(size_t)g]) {
-                rc = one_chunk(h->devs[(size_t)g], lo_[(size_t)g], hi_[(size_t)g], cur[(size_t)g], S, max_threads);
-                more = true;
-            }
-    }
-    // ---- drain every GPU's slots, oldest first
-    const auto tw = std::chrono::steady_clock::now();
-    for (KDev &d : h->devs)
+    auto drain_dev = [&](KDev &d, kswv_gpu_stats &St, int inner) -> int {
+        int r = BSW_OK;
+        const auto tw = std::chrono::steady_clock::now();
         for (int j = 0; j < kRing; ++j) {
             KSlot &s = d.slot[(d.next + j) % kRing];
-            const int rc2 = drain_slot(h, d, s, pairs, aln, S, max_threads);
+            const int rc2 = drain_slot(h, d, s, pairs, aln, St, inner);
+            if (r == BSW_OK) r = rc2;
+        }
+        St.host_wait_ms += ms_since(tw);
+        return r;
+    };
+    if (!workers) {
+        HostScratch w;
+        for (bool more = true; more && rc == BSW_OK;) {
+            more = false;
+            for (int g = 0; g < n_dev && rc == BSW_OK; ++g)
+                if (cur[(size_t)g] < hi_[(size_t)g]) {
+                    rc = one_chunk(h->devs[(size_t)g], lo_[(size_t)g], hi_[(size_t)g], cur[(size_t)g], S, max_threads, w);
+                    more = true;
+                }
+        }
+        for (KDev &d : h->devs) {           // every GPU's slots, oldest first
+            const int rc2 = drain_dev(d, S, max_threads);
             if (rc == BSW_OK) rc = rc2;
         }
-    S.host_wait_ms += ms_since(tw);
+    } else {
+        std::vector<kswv_gpu_stats> part((size_t)n_dev);
+        std::vector<int> rcs((size_t)n_dev, BSW_OK);
+#pragma omp parallel for schedule(static, 1) num_threads(n_dev)
+        for (int g = 0; g < n_dev; ++g) {
+            HostScratch w;
+            kswv_gpu_stats &P = part[(size_t)g];
+            memset(&P, 0, sizeof P);
+            int r = BSW_OK;
+            while (r == BSW_OK && cur[(size_t)g] < hi_[(size_t)g])
+                r = one_chunk(h->devs[(size_t)g], lo_[(size_t)g], hi_[(size_t)g], cur[(size_t)g], P, 1, w);
+            const int r2 = drain_dev(h->devs[(size_t)g], P, 1);
+            rcs[(size_t)g] = r != BSW_OK ? r : r2;
+        }
+        for (int g = 0; g < n_dev; ++g) {
+            const kswv_gpu_stats &P = part[(size_t)g];
+            S.chunks += P.chunks; S.h2d_bytes += P.h2d_bytes; S.d2h_bytes += P.d2h_bytes; S.kernel_launches += P.kernel_launches;
+            S.gathered += P.gathered; S.staged += P.staged; S.kernel_ms += P.kernel_ms;
+            S.host_prep_ms = std::max(S.host_prep_ms, P.host_prep_ms);      // the workers run side by side
+            S.host_wait_ms = std::max(S.host_wait_ms, P.host_wait_ms);
+            if (P.lanes_per_pair) S.lanes_per_pair = P.lanes_per_pair;
+            if (rc == BSW_OK) rc = rcs[(size_t)g];
+        }
+    }
     S.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return rc;
 }
