@@ -179,3 +179,37 @@ def test_ties(dev, kind):
     pairs, ref, qer = okswv.make_low_complexity(4000, seed=5, kind=kind)
     want, _ = okswv.oracle_batch(pairs, ref, qer)
     assert_same_aln(dev.align(pairs, ref, qer), want, pairs, kind)
+
+
+def test_full_size_properties(dev):
+    """The bench's full-size batch (400 000 pairs; the oracle is only sampled there): properties every result must
+    have whatever the size -- ends inside the sequences, starts before the ends, a score the aligned span can pay
+    for, a second best that never beats the best, and the tiled batch repeating its base batch exactly."""
+    base = 20000
+    pairs0, ref0, qer0 = okswv.make_workload(base, seed=7, read_len=(151, 151))
+    reps = 20
+    rb, qb = int(pairs0["idr"][-1] + pairs0["len1"][-1]), int(pairs0["idq"][-1] + pairs0["len2"][-1])
+    pairs = np.tile(pairs0, reps)
+    ref = np.concatenate([ref0[:rb]] * reps + [np.zeros(64, np.uint8)])
+    qer = np.concatenate([qer0[:qb]] * reps + [np.zeros(64, np.uint8)])
+    for r in range(reps):
+        sl = slice(r * base, (r + 1) * base)
+        pairs["idr"][sl] += r * rb
+        pairs["idq"][sl] += r * qb
+        pairs["regid"][sl] += r * base
+    a = dev.align(pairs, ref, qer)
+    score, te, qe, score2, te2, tb, qb_ = (a[:, k] for k in range(7))
+    hit = score > 0
+    assert (te[hit] >= 0).all() and (te < pairs["len1"]).all() and (qe[hit] < pairs["len2"][hit]).all()
+    assert (te[~hit] == -1).all() and (qe[~hit] == 0).all()
+    started = tb >= 0
+    assert (tb[started] <= te[started]).all() and (qb_[started] >= 0).all() and (qb_[started] <= qe[started]).all()
+    span = np.minimum(te - tb + 1, qe - qb_ + 1)
+    assert (score[started] <= span[started]).all()                       # match = 1: a span of s columns pays at most s
+    assert ((score2 == -1) | (score2 <= score)).all() and ((score2 == -1) == (te2 == -1)).all()
+    assert (np.abs(te2[score2 > 0] - te[score2 > 0]) >= 1).all()
+    # a checksum of checksums: every tile equals the first, and the first equals the oracle
+    tiles = a.reshape(reps, base, 7)
+    assert (tiles == tiles[0]).all()
+    want, _ = okswv.oracle_batch(pairs0, ref0, qer0)
+    assert_same_aln(tiles[0], want, pairs0, "first tile")
